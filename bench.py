@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: GB/s (and % of the HBM roofline) for map!/broadcast and sum on a Float32 DArray.
+
+A "step" is one pass of the hot path over one resident batch:   y .= a .* x .+ b   (8 B/element)  then   s = sum(y)
+(4 B/element, incl. the cross-worker combine and the scalar on the host).  Workload at N GPUs: BASELINE configs[1]/[2], a 1-D
+Float32 DArray of N * 2^30 elements, one 2^30-element (4 GiB) localpart per GPU (weak scaling, defaultdist grid (N,)).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--log2n 30]            # our arm (one process per GPU under torchrun)
+  python bench.py --impl reference ...                                         # the reference's CPU path (oracle port) on host cores
+
+Prints ONE JSON line (rank 0).  value = whole-job algorithmic GB/s with inputs resident in HBM; e2e = same metric through the
+public API with HOST (pinned) input each step; roofline = the dominant kernel (the broadcast) against the measured HBM peak;
+cpu_baseline = the oracle port timed on this box's host cores (bounded sample).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+A_COEF, B_COEF = 1.5, 0.25
+SEED = 1234
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_gbps", "hbm_gb_s"):
+                if k in j:
+                    return float(j[k]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_leg(log2n_per_worker, steps, warmup, workers=None):
+    """The reference's CPU-process path: P single-threaded workers (one per host core), each running Base's loops on its own
+    chunk -- map!(x->a*x+b, d, d) then sum(d) + the caller-side left fold (oracle/oracle_core.c).  Compute only: the reference's
+    remotecall / serialisation overhead is NOT reproduced (that flatters the reference)."""
+    from oracle import core as ocore
+
+    ocore.build()
+    cores = ocore.num_procs()
+    P = workers or cores
+    n_per = 1 << log2n_per_worker
+    best, mean, res = ocore.workers_run(3, P, n_per, SEED, A_COEF, B_COEF, max(1, warmup), max(1, steps))
+    gbs = 12.0 * n_per * P / mean / 1e9
+    return {"value": gbs, "unit": "GB/s", "cores": P, "kind": "port",
+            "sample": f"{P} workers x 2^{log2n_per_worker} Float32 (in-place map! a*x+b, then pairwise-1024 sum + left fold), "
+                      f"{steps} timed passes, mean {mean * 1e3:.2f} ms/pass, best {best * 1e3:.2f} ms; host cores online: {cores}",
+            "ms_per_step": mean * 1e3, "result": float(res)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2n", type=int, default=30, help="log2 of the elements per GPU (default 2^30 = 4 GiB chunk)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(3, args.warmup)
+    n_per = 1 << args.log2n
+    workload = (f"C2/C3: 1-D Float32 DArray, {world} x 2^{args.log2n} elements ({4 * n_per / 2**30:.0f} GiB localpart per GPU); "
+                f"step = y .= {A_COEF}f0 .* x .+ {B_COEF}f0 then sum(y)")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        c = cpu_leg(24, args.steps, warmup)
+        line = {"impl": "reference", "metric": "GB/s for map! and sum on Float32 DArray", "value": c["value"], "unit": "GB/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup, "ms_per_step": c["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "reference_arm": "CPU restatement of the reference's per-worker Base loops (Julia is not "
+                           "installable here; oracle/oracle_core.c), one single-threaded worker per host core, bounded sample"},
+                "cpu_baseline": {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": c["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+
+    import darray_b200 as dab
+
+    rt = dab.init(workers_per_rank=1)
+    a, b = np.float32(A_COEF), np.float32(B_COEF)
+    N = n_per * world
+    x = dab.drand((N,), dtype=np.float32, seed=SEED)       # generated on device, reproducible on the CPU oracle
+    y = dab.similar(x)
+    f = lambda v: a * v + b  # noqa: E731  (traced once -> dab_affine)
+
+    def step():
+        dab.broadcast_into(y, f, x)
+        return dab.sum(y)
+
+    def fence():
+        rt.sync()
+        if rt.dist is not None:
+            rt.dist.barrier()
+
+    def timed(fn, k):
+        e0, e1 = rt.event(), rt.event()
+        fence()
+        rt.record(e0)
+        r = None
+        for _ in range(k):
+            r = fn()
+        rt.record(e1)
+        ms = rt.elapsed_ms(e0, e1)
+        fence()
+        rt.event_destroy(e0)
+        rt.event_destroy(e1)
+        return ms, r
+
+    def max_over_ranks(v):
+        if rt.dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64)
+        rt.dist.all_reduce(t, op=rt.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(warmup):
+        s = step()
+    clocks = ClockSampler(rt.device)
+    if rank == 0:
+        clocks.start()
+    l0 = rt.launches()
+    ms, s = timed(step, args.steps)
+    launches = rt.launches() - l0
+    ms = max_over_ranks(ms)
+    clk = clocks.stop() if rank == 0 else None
+    value = 12.0 * N * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- per-kernel timings (same resident data; inputs 4 GiB >> 126 MB L2, so no flush needed)
+    ms_bc, _ = timed(lambda: dab.broadcast_into(y, f, x), args.steps)
+    ms_sum, _ = timed(lambda: dab.sum(y), args.steps)
+    ms_max, _ = timed(lambda: dab.maximum(y), max(3, args.steps // 2))
+    ms_bc, ms_sum, ms_max = max_over_ranks(ms_bc), max_over_ranks(ms_sum), max_over_ranks(ms_max)
+    peak, peak_kind = measured_peak()
+    bc_gbs = 8.0 * n_per * args.steps / (ms_bc * 1e-3) / 1e9          # per GPU: the kernel's own HBM rate
+    sum_gbs = 4.0 * n_per * args.steps / (ms_sum * 1e-3) / 1e9
+    max_gbs = 4.0 * n_per * max(3, args.steps // 2) / (ms_max * 1e-3) / 1e9
+
+    # ---- parity spot check inside the bench (cheap): sum vs the exact expectation of the generator
+    mean = float(s) / N
+    ok = abs(mean - (A_COEF * 0.5 + B_COEF)) < 1e-3
+
+    # ---- e2e: the same step through the public API with HOST input every step (pinned), scalar result back on the host
+    e2e = None
+    try:
+        from darray_b200 import pinned_empty
+        hx = pinned_empty(rt, (n_per,), np.float32)
+        hx[:] = 0.5
+        hx[::4096] = 0.25
+        e2e_steps = max(1, args.e2e_steps)
+
+        def e2e_step():
+            if world == 1:
+                dab.copyto(x, hx)                                          # copyto!(x::DArray, host::Array): H2D of the step's input
+            else:
+                dab.localpart(x).copy_from_host(hx, sync=False)            # copyto!(localpart(x), host chunk) on every worker
+            dab.broadcast_into(y, f, x)
+            return dab.sum(y)
+
+        for _ in range(2):
+            e2e_step()
+        ms_e, _ = timed(e2e_step, e2e_steps)
+        ms_e = max_over_ranks(ms_e)
+        e2e = {"value": 12.0 * N * e2e_steps / (ms_e * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 4 * N,
+               "d2h_bytes_per_step": 16 * world, "ms_per_step": ms_e / e2e_steps,
+               "path": "copyto!(x::DArray, host Array) [pinned H2D] -> y .= a.*x .+ b -> sum(y) -> host scalar"}
+    except Exception as ex:  # never lose the main line because of the e2e leg
+        e2e = {"value": None, "unit": "GB/s", "error": repr(ex)[:200]}
+
+    line = {"metric": "GB/s for map! and sum on Float32 DArray", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "l2": "inputs (4 GiB/GPU) >> 126 MB L2, no flush needed", "grid": list(x.layout.grid),
+                       "combine": "NCCL all-gather of the P chunk results + ordered left fold" if world > 1 else "single chunk"},
+            "roofline": {"bound": "hbm", "kernel": "ew1_kernel<float, AffineF<float>, 4> (dab_affine)", "achieved": bc_gbs, "peak": peak,
+                         "peak_kind": peak_kind, "unit": "GB/s", "frac": bc_gbs / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": 8 * n_per},
+            "kernels": {"broadcast_GBs_per_gpu": bc_gbs, "sum_GBs_per_gpu": sum_gbs, "maximum_GBs_per_gpu": max_gbs,
+                        "broadcast_frac": bc_gbs / peak, "sum_frac": sum_gbs / peak, "maximum_frac": max_gbs / peak,
+                        "ms_broadcast": ms_bc / args.steps, "ms_sum": ms_sum / args.steps},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clk, "parity_spot_check": ok, "sum": float(s)}
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            try:
+                c = cpu_leg(24, 5, 2)
+                line["cpu_baseline"] = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as ex:
+                line["cpu_baseline"] = {"value": None, "error": repr(ex)[:200]}
+        print(json.dumps(line))
+    fence()
+
+
+if __name__ == "__main__":
+    main()

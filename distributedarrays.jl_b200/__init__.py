@@ -1,0 +1,23 @@
+"""distributedarrays.jl_b200 -- B200-native backend for the DArray map!/broadcast + mapreduce hot path.
+
+Import it as ``darray_b200`` (the directory name is not a Python identifier; ``darray_b200.py`` at the repo root is a
+loader shim).  The public names mirror DistributedArrays.jl's for this path: ``DArray``, ``distribute``, ``localpart``,
+``localindices``, ``locate``, ``makelocal``, ``procs``, ``dzeros/dones/dfill/drand``, ``map`` (``map_``), ``map!``
+(``map_inplace``), broadcast (``broadcast`` / ``broadcast_into``), ``reduce``, ``mapreduce``, ``sum``, ``prod``,
+``maximum``, ``minimum``, ``all``, ``any``, ``count``, ``extrema``, ``Array(d)`` (``to_array``), range ``getindex``.
+
+Everything computes on the GPU through ``csrc/libdab200.so`` (C ABI: ``include/dab200.h``).  There is no CPU fallback:
+importing works anywhere, but the first op without the built extension or without a B200 raises.
+"""
+from . import _lib
+from ._lib import ArgumentError, DabError, DimensionMismatch, UnsupportedError
+from ._broadcast import (Expr, abs2, broadcast, broadcast_into, ceil, cos, exp, floor, ifelse, inv, isnan, jl_max, jl_min,
+                        log, map_, map_bang, map_inplace, mod, rem, sign, sin, sqrt, tan, tanh)
+from ._darray import (B200Array, DArray, SubDArray, allowscalar, dab_dtype, np_dtype, copyto, d_closeall, darray, darray_from_chunks, darray_like,
+                     dfill, distribute, dones, drand, dzeros, fill_, localindices, localpart, locate, makelocal, pinned_empty, procs,
+                     registry_size, similar, to_array)
+from .layout import Layout, chunk_idxs, cuts_for, defaultdist, make_layout, slab_plan
+from ._mapreduce import all, any, count, extrema, mapreduce, mapreducedim, maximum, minimum, prod, reduce, sum  # noqa: A004
+from .runtime import Runtime, init, myid, nworkers, runtime, workers
+
+__all__ = [n for n in dir() if not n.startswith("_")]

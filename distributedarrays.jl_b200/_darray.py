@@ -1,0 +1,563 @@
+"""DArray on B200: each localpart lives in one GPU's HBM.
+
+Python mirror of the reference's L2 layer (src/darray.jl) for exactly what the hot path needs: the ``DArray`` struct
+(:25-31), constructors ``DArray(init, dims[, procs, dist])`` (:159-174), ``DArray(refs)`` (:183-216),
+``distribute`` (:544-570), ``Array(d)`` (:574-582), ``localpart`` / ``localindices`` / ``locate`` / ``makelocal``
+(:309-400, 448-456), range ``getindex`` -> ``SubDArray`` view (:661) and ``Array(::SubDArray)`` -- the halo read
+(:584-602, 798-820).  Names, argument meaning and error behaviour follow the reference; only the chunk type differs:
+``B200Array`` (device pointer + dims) is the ``A`` in ``DArray{T,N,A}`` (the seam at src/darray.jl:25).
+
+SPMD: every rank executes the same DArray program (like ``@everywhere``); constructors and reductions are collective,
+element-wise ops are purely local launches.  Layout metadata is 1-based inclusive like the reference's; Python
+``d[a:b, c:d]`` slicing is the usual 0-based half-open and is translated.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .layout import (Layout, Range, contains, default_procs, layout_from_chunk_shapes, make_layout, rlen, shape_of,
+                     slab_plan)
+from .runtime import Runtime, runtime
+
+_DT = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64, np.dtype(np.int32): _lib.I32,
+       np.dtype(np.int64): _lib.I64, np.dtype(np.bool_): _lib.U8, np.dtype(np.uint8): _lib.U8}
+_NP = {_lib.F32: np.dtype(np.float32), _lib.F64: np.dtype(np.float64), _lib.I32: np.dtype(np.int32),
+       _lib.I64: np.dtype(np.int64), _lib.U8: np.dtype(np.bool_)}
+
+
+def dab_dtype(dt) -> int:
+    dt = np.dtype(dt)
+    if dt not in _DT:
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"element type {dt} is not served by the B200 backend (no host fallback)")
+    return _DT[dt]
+
+
+def np_dtype(code: int) -> np.dtype:
+    return _NP[code]
+
+
+_allowscalar = [True]
+
+
+def allowscalar(flag: bool = True):
+    """reference src/darray.jl:638-640."""
+    _allowscalar[0] = bool(flag)
+
+
+class B200Array:
+    """A dense column-major array in one GPU's HBM: the chunk type ``A`` of ``DArray{T,N,A}``."""
+
+    __slots__ = ("rt", "ptr", "shape", "dtype", "_own", "_keep")
+
+    def __init__(self, rt: Runtime, ptr: int, shape: Sequence[int], dtype, own: bool = True, keep=None):
+        self.rt, self.ptr, self.shape, self.dtype = rt, int(ptr), tuple(int(s) for s in shape), np.dtype(dtype)
+        self._own, self._keep = own, keep
+
+    @classmethod
+    def empty(cls, rt: Runtime, shape: Sequence[int], dtype) -> "B200Array":
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) if len(shape) else 1
+        return cls(rt, rt.alloc(n * dtype.itemsize), shape, dtype)
+
+    @classmethod
+    def from_numpy(cls, rt: Runtime, a: np.ndarray) -> "B200Array":
+        a = np.asarray(a)
+        dab_dtype(a.dtype)
+        out = cls.empty(rt, a.shape, a.dtype)
+        out.copy_from_host(a)
+        return out
+
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.shape)) if len(self.shape) else 1
+
+    @property
+    def nbytes(self) -> int:
+        return self.size * self.dtype.itemsize
+
+    @property
+    def ndim(self) -> int:
+        return len(self.shape)
+
+    def copy_from_host(self, a: np.ndarray, sync: bool = True):
+        a = np.asarray(a, dtype=self.dtype)
+        if tuple(a.shape) != self.shape:
+            raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"host array {a.shape} vs chunk {self.shape}")
+        if self.size == 0:
+            return
+        if not a.flags.f_contiguous:
+            if a.ndim == 2 and a.strides[0] == a.itemsize and a.strides[1] > 0:
+                # a column block of a column-major matrix: strided H2D without a host staging copy
+                _lib.call("dab_h2d_2d", self.rt.ctx, C.c_void_p(self.ptr), a.shape[0] * a.itemsize, C.c_void_p(a.ctypes.data),
+                          a.strides[1], a.shape[0] * a.itemsize, a.shape[1])
+                if sync:
+                    self.rt.sync()
+                return
+            a = np.asfortranarray(a)
+        _lib.call("dab_h2d", self.rt.ctx, C.c_void_p(self.ptr), C.c_void_p(a.ctypes.data), self.nbytes)
+        if sync:
+            self.rt.sync()  # the host buffer may be pageable / temporary
+
+    def to_numpy(self) -> np.ndarray:
+        out = np.empty(self.shape, dtype=self.dtype, order="F")
+        if self.size:
+            _lib.call("dab_d2h", self.rt.ctx, C.c_void_p(out.ctypes.data), C.c_void_p(self.ptr), self.nbytes)
+            self.rt.sync()
+        return out
+
+    def free(self):
+        if self._own and self.ptr:
+            self.rt.free(self.ptr)
+        self.ptr = 0
+
+    def __repr__(self):
+        return f"B200Array({self.dtype}, {self.shape}, ptr=0x{self.ptr:x}, dev={self.rt.device})"
+
+
+def pinned_empty(rt: Runtime, shape, dtype) -> np.ndarray:
+    """A NumPy array over page-locked host memory (``dab_host_alloc``): the staging buffer for ``distribute`` / ``copyto!`` so
+    that H2D runs at PCIe speed asynchronously on the ctx stream.  Freed when the array is garbage collected."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) if len(shape) else 1
+    p = C.c_void_p()
+    _lib.call("dab_host_alloc", rt.ctx, max(1, n * dtype.itemsize), C.byref(p))
+    buf = (C.c_char * max(1, n * dtype.itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape, order="F")
+    import weakref
+    ctx, addr = rt.ctx, p.value
+    weakref.finalize(buf, lambda: _lib.lib().dab_host_free(ctx, C.c_void_p(addr)) if ctx else None)
+    return arr
+
+
+_did = [0]
+
+
+def _next_did(rt: Runtime) -> Tuple[int, int]:
+    """``next_did()`` (src/core.jl:55-66).  Collective constructors run in the same order on every rank, so a local
+    counter yields the same id everywhere."""
+    _did[0] += 1
+    return (1, _did[0])
+
+
+_REGISTRY: Dict[Tuple[int, int], "DArray"] = {}
+
+
+class DArray:
+    """``DArray{T,N,B200Array}`` (reference src/darray.jl:25-31)."""
+
+    def __init__(self, layout: Layout, dtype, chunks: Dict[int, B200Array], rt: Optional[Runtime] = None):
+        self.rt = rt or runtime()
+        self.id = _next_did(self.rt)
+        self.layout = layout
+        self.dtype = np.dtype(dtype)
+        self.chunks = chunks  # pid -> B200Array for the workers of THIS rank
+        # invariant of the reference constructor (src/darray.jl:35-37)
+        if layout.indices and layout.dims != tuple(r[1] for r in layout.indices[-1]):
+            raise ValueError("ArgumentError: dimension of DArray (dim) and indices do not match")
+        for pid, ch in chunks.items():
+            want = shape_of(layout.localindices(pid))
+            if ch.shape != want:
+                raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"chunk of worker {pid} has shape {ch.shape}, layout says {want}")
+        self._handles: Optional[Dict[int, bytes]] = None
+        _REGISTRY[self.id] = self
+
+    # ---- metadata (same names as the reference struct) ---------------------------------------------------------
+    @property
+    def dims(self):
+        return self.layout.dims
+
+    shape = dims
+
+    @property
+    def ndim(self):
+        return len(self.layout.dims)
+
+    @property
+    def size(self):
+        return int(np.prod(self.layout.dims))
+
+    @property
+    def pids(self) -> np.ndarray:
+        return np.asarray(self.layout.pids).reshape(self.layout.grid, order="F")
+
+    @property
+    def indices(self):
+        return self.layout.indices
+
+    @property
+    def cuts(self):
+        return self.layout.cuts
+
+    def __len__(self):
+        return self.size
+
+    def __repr__(self):
+        return f"DArray({self.dtype}, dims={self.dims}, grid={self.layout.grid}, pids={self.layout.pids})"
+
+    # ---- lifetime (src/core.jl:68-105) ----------------------------------------------------------------------------
+    def close(self):
+        for ch in self.chunks.values():
+            ch.free()
+        self.chunks = {}
+        _REGISTRY.pop(self.id, None)
+
+    # ---- peer handles for one-sided halo reads ------------------------------------------------------------------------
+    def peer_ptr(self, pid: int) -> int:
+        """Device address of worker ``pid``'s chunk as seen from this rank (local pointer or CUDA-IPC mapping)."""
+        if pid in self.chunks:
+            return self.chunks[pid].ptr
+        if self._handles is None:
+            raise _lib.DabError(_lib.ERR_ARG, "remote chunk access needs d.share() (collective) first")
+        return self.rt.ipc_open(self._handles[pid])
+
+    def share(self):
+        """Collective: exchange CUDA IPC handles of all chunks so that any rank can read any chunk over NVLink
+        (the B200 counterpart of every worker being able to ``remotecall_fetch`` any chunk, src/darray.jl:458)."""
+        if self.rt.world == 1:
+            self._handles = {}
+            return self
+        mine = {pid: self.rt.ipc_handle(ch.ptr) for pid, ch in self.chunks.items() if ch.size}
+        allh = self.rt.allgather_object(mine)
+        self._handles = {}
+        for h in allh:
+            self._handles.update(h)
+        return self
+
+    # ---- indexing (src/darray.jl:642-661) ---------------------------------------------------------------------------------
+    def __getitem__(self, key):
+        if not isinstance(key, tuple):
+            key = (key,)
+        if len(key) == 1 and self.ndim > 1 and isinstance(key[0], (int, np.integer)):
+            raise IndexError("linear scalar indexing of a multi-dimensional DArray is not supported")
+        if len(key) != self.ndim:
+            raise IndexError(f"expected {self.ndim} indices")
+        if all(isinstance(k, (int, np.integer)) for k in key):
+            if not _allowscalar[0]:
+                raise RuntimeError("ErrorException: scalar indexing disabled")  # src/darray.jl:640
+            J = tuple((int(k) % s + 1, int(k) % s + 1) if -s <= int(k) < s else _oob(k, s) for k, s in zip(key, self.dims))
+            return SubDArray(self, J, tuple(True for _ in key)).to_numpy()[()]
+        J, drop = [], []
+        for k, s in zip(key, self.dims):
+            if isinstance(k, (int, np.integer)):
+                kk = int(k)
+                if not -s <= kk < s:
+                    _oob(kk, s)
+                kk %= s
+                J.append((kk + 1, kk + 1))
+                drop.append(True)
+            elif isinstance(k, slice):
+                lo, hi, st = k.indices(s)
+                if st != 1:
+                    raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "strided (step != 1) views are not served by the B200 backend")
+                J.append((lo + 1, max(lo, hi)))
+                drop.append(False)
+            else:
+                raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"index type {type(k).__name__} is not served by the B200 backend")
+        return SubDArray(self, tuple(J), tuple(drop))
+
+    def __array__(self, dtype=None, copy=None):
+        a = to_array(self)
+        return a.astype(dtype) if dtype is not None else a
+
+
+def _oob(k, s):
+    raise IndexError(f"BoundsError: index {k} out of range for dimension of size {s}")
+
+
+class SubDArray:
+    """``view(d, I...)`` with unit ranges (reference src/darray.jl:65, 661).  ``J`` are 1-based inclusive ranges."""
+
+    def __init__(self, parent: DArray, J: Tuple[Range, ...], drop: Tuple[bool, ...]):
+        self.parent, self.J, self.drop = parent, J, drop
+
+    @property
+    def shape(self):
+        return tuple(rlen(j) for j, d in zip(self.J, self.drop) if not d)
+
+    def to_device(self, rt: Optional[Runtime] = None) -> B200Array:
+        """Dense device copy of the view on the calling rank's GPU: the halo read (src/darray.jl:584-602, 798-820)."""
+        d = self.parent
+        rt = rt or d.rt
+        full_shape = tuple(rlen(j) for j in self.J)
+        out = B200Array.empty(rt, full_shape, d.dtype)
+        for piece in slab_plan(d.layout, self.J):
+            pid = d.layout.pids[piece.chunk]
+            src_ptr = d.peer_ptr(pid)
+            src_shape = shape_of(d.layout.indices[piece.chunk])
+            _lib.call("dab_copy_box", rt.ctx, d.dtype.itemsize, C.c_void_p(out.ptr), _lib.sz4(full_shape),
+                      _lib.sz4([r[0] - 1 for r in piece.dst] + [0] * (4 - len(piece.dst))), C.c_void_p(src_ptr), _lib.sz4(src_shape),
+                      _lib.sz4([r[0] - 1 for r in piece.src] + [0] * (4 - len(piece.src))), _lib.sz4([rlen(r) for r in piece.src]))
+        return out
+
+    def to_numpy(self) -> np.ndarray:
+        dev = self.to_device()
+        a = dev.to_numpy()
+        dev.free()
+        keep = tuple(0 if dr else slice(None) for dr in self.drop)
+        return a[keep]
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.to_numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+
+# ---- constructors --------------------------------------------------------------------------------------------------------
+
+
+def _mk(rt: Runtime, layout: Layout, init: Callable, dtype=None) -> DArray:
+    chunks: Dict[int, B200Array] = {}
+    dts = set()
+    for pid in layout.pids:
+        if not rt.is_local(pid):
+            continue
+        I = layout.localindices(pid)
+        part = init(I)
+        if isinstance(part, np.ndarray) or np.isscalar(part):
+            part = B200Array.from_numpy(rt, np.asarray(part) if dtype is None else np.asarray(part, dtype=dtype))
+        if part.shape != shape_of(I):
+            raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"init returned shape {part.shape} for indices {I}")
+        chunks[pid] = part
+        dts.add(part.dtype)
+    if dtype is None:
+        # "Constructed localparts have different eltype" (src/darray.jl:89-95): checked across all ranks
+        alld = set()
+        for s in rt.allgather_object(sorted(str(x) for x in dts)):
+            alld.update(s)
+        if len(alld) > 1:
+            for ch in chunks.values():
+                ch.free()
+            raise RuntimeError(f"ErrorException: Constructed localparts have different `eltype`: {sorted(alld)}")
+        dtype = np.dtype(alld.pop()) if alld else np.dtype(np.float64)
+    return DArray(layout, dtype, chunks, rt)
+
+
+def darray(init: Callable, dims: Sequence[int], procs: Optional[Sequence[int]] = None, dist: Optional[Sequence[int]] = None,
+           dtype=None, rt: Optional[Runtime] = None) -> DArray:
+    """``DArray(init, dims[, procs[, dist]])`` (reference src/darray.jl:159-174).  ``init(I)`` receives the tuple of
+    1-based inclusive index ranges of a chunk and returns its data (NumPy array or ``B200Array``)."""
+    rt = rt or runtime()
+    dims = tuple(int(d) for d in dims)
+    if procs is None:
+        procs = default_procs(dims, rt.workers())
+    return _mk(rt, make_layout(dims, procs, dist), init, dtype)
+
+
+def darray_like(init: Callable, d: DArray, dtype=None) -> DArray:
+    """``DArray(init, d::DArray)`` (src/darray.jl:236): same layout as ``d``."""
+    return _mk(d.rt, d.layout, init, dtype)
+
+
+def darray_from_chunks(parts: Sequence, grid: Sequence[int], pids: Optional[Sequence[int]] = None, rt: Optional[Runtime] = None) -> DArray:
+    """``DArray(refs)`` (src/darray.jl:183-216): irregular layout from per-worker chunks, column-major grid order.
+    ``parts[k]`` is a NumPy array (uploaded on the owning rank); every rank passes the same list of shapes."""
+    rt = rt or runtime()
+    n = int(np.prod(grid))
+    pids = list(pids) if pids is not None else rt.workers()[:n]
+    layout = layout_from_chunk_shapes([np.shape(p) for p in parts], grid, pids)
+    by_pid = dict(zip(pids, parts))
+    return _mk_from_parts(rt, layout, by_pid)
+
+
+def _mk_from_parts(rt, layout, by_pid):
+    chunks = {pid: B200Array.from_numpy(rt, np.asarray(by_pid[pid])) for pid in layout.pids if rt.is_local(pid)}
+    dts = {np.asarray(p).dtype for p in by_pid.values()}
+    if len(dts) > 1:
+        for ch in chunks.values():
+            ch.free()
+        raise RuntimeError(f"ErrorException: Constructed localparts have different `eltype`: {sorted(map(str, dts))}")
+    return DArray(layout, dts.pop(), chunks, rt)
+
+
+def distribute(A: np.ndarray, procs: Optional[Sequence[int]] = None, dist: Optional[Sequence[int]] = None,
+               like: Optional[DArray] = None, rt: Optional[Runtime] = None) -> DArray:
+    """``distribute(A; procs, dist)`` / ``distribute(A, DA)`` (reference src/darray.jl:544-570): every rank uploads the
+    slices ``A[idxs...]`` of its own workers (H2D), nothing else moves."""
+    A = np.asarray(A)
+    rt = rt or (like.rt if like is not None else runtime())
+    dab_dtype(A.dtype)
+    if like is not None:
+        if tuple(A.shape) != like.dims:
+            raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"Distributed array has size {like.dims} but array has {A.shape}")
+        layout = like.layout
+    else:
+        if procs is None:
+            procs = default_procs(A.shape, rt.workers())
+        layout = make_layout(A.shape, procs, dist)
+    chunks = {}
+    for pid in layout.pids:
+        if rt.is_local(pid):
+            I = layout.localindices(pid)
+            ch = B200Array.empty(rt, shape_of(I), A.dtype)
+            ch.copy_from_host(A[tuple(slice(lo - 1, hi) for lo, hi in I)], sync=False)
+            chunks[pid] = ch
+    rt.sync()
+    return DArray(layout, A.dtype, chunks, rt)
+
+
+def _filled(value, dtype):
+    def ctor(dims, procs=None, dist=None, rt=None):
+        rt = rt or runtime()
+        dt = np.dtype(dtype)
+
+        def init(I):
+            ch = B200Array.empty(rt, shape_of(I), dt)
+            v = np.asarray(value, dtype=dt)
+            _lib.call("dab_fill", rt.ctx, dab_dtype(dt), C.c_void_p(ch.ptr), ch.size, C.c_void_p(v.ctypes.data))
+            return ch
+
+        return darray(init, dims, procs, dist, dtype=dt, rt=rt)
+
+    return ctor
+
+
+def dzeros(dims, procs=None, dist=None, dtype=np.float64, rt=None) -> DArray:
+    """src/darray.jl:468-472."""
+    return _filled(0, dtype)(dims, procs, dist, rt)
+
+
+def dones(dims, procs=None, dist=None, dtype=np.float64, rt=None) -> DArray:
+    """src/darray.jl:481-485."""
+    return _filled(1, dtype)(dims, procs, dist, rt)
+
+
+def dfill(v, dims, procs=None, dist=None, dtype=None, rt=None) -> DArray:
+    """src/darray.jl:493-494."""
+    return _filled(v, dtype if dtype is not None else np.asarray(v).dtype)(dims, procs, dist, rt)
+
+
+def drand(dims, procs=None, dist=None, dtype=np.float64, seed: int = 1234, rt=None) -> DArray:
+    """``drand`` (src/darray.jl:502-518) with the counter-based generator: element with global column-major linear index
+    g is ``(hash32(seed, g) >> 8) * 2^-24`` -- layout-independent and reproducible on the CPU oracle."""
+    rt = rt or runtime()
+    dims = tuple(int(d) for d in dims)
+    dt = np.dtype(dtype)
+
+    def init(I):
+        ch = B200Array.empty(rt, shape_of(I), dt)
+        _rand_block(rt, ch, dims, I, seed)
+        return ch
+
+    return darray(init, dims, procs, dist, dtype=dt, rt=rt)
+
+
+def _rand_block(rt, ch: B200Array, dims, I, seed):
+    """Fill chunk ``I`` of a global array so that values depend on the GLOBAL linear index only: one launch per
+    contiguous run of the chunk (runs = trailing-index combinations of the dims after the first split one)."""
+    code = dab_dtype(ch.dtype)
+    shp = shape_of(I)
+    # length of the prefix of dims the chunk spans completely -> contiguous run in global memory
+    run, k = 1, 0
+    while k < len(dims) and shp[k] == dims[k]:
+        run *= dims[k]
+        k += 1
+    if k < len(dims):
+        run *= shp[k]
+        k += 1
+    strides = np.cumprod((1,) + tuple(dims[:-1])).astype(object)
+    rest = [range(r[0] - 1, r[1]) for r in I[k:]]
+    base0 = sum(int(strides[j]) * (I[j][0] - 1) for j in range(k))
+    off = 0
+    for tail in itertools.product(*reversed(rest)):
+        tail = tuple(reversed(tail))
+        g = base0 + sum(int(strides[k + j]) * tail[j] for j in range(len(tail)))
+        _lib.call("dab_rand_u01", rt.ctx, code, C.c_void_p(ch.ptr + off * ch.dtype.itemsize), run, int(seed), int(g))
+        off += run
+
+
+# ---- access -------------------------------------------------------------------------------------------------------------
+
+
+def procs(d: DArray) -> List[int]:
+    return list(d.layout.pids)
+
+
+def localpart(d: DArray, pid: Optional[int] = None) -> B200Array:
+    """``localpart(d)`` (src/darray.jl:330-337): the chunk of worker ``pid`` (default: this rank's first worker); an
+    empty array if that worker holds no part."""
+    pid = d.rt.myid() if pid is None else pid
+    if pid in d.chunks:
+        return d.chunks[pid]
+    if not d.rt.is_local(pid):
+        raise _lib.DabError(_lib.ERR_ARG, f"worker {pid} does not live on rank {d.rt.rank}")
+    return B200Array.empty(d.rt, (0,) * d.ndim, d.dtype)
+
+
+def localindices(d: DArray, pid: Optional[int] = None):
+    """src/darray.jl:394-400."""
+    return d.layout.localindices(d.rt.myid() if pid is None else pid)
+
+
+def locate(d: DArray, *I: int):
+    """src/darray.jl:448-456."""
+    return d.layout.locate(*I)
+
+
+def makelocal(d: DArray, J: Sequence[Range], pid: Optional[int] = None) -> B200Array:
+    """``makelocal(A, I...)`` (src/darray.jl:351-368) for 1-based unit ranges ``J``: when the ranges lie inside worker
+    ``pid``'s chunk and cover it exactly the chunk itself is returned (zero-copy, :357-360); otherwise a dense device
+    array is allocated and filled by the halo fetch (:361-366)."""
+    pid = d.rt.myid() if pid is None else pid
+    lid = d.layout.localindices(pid)
+    J = tuple(J)
+    if pid in d.chunks and J == lid:
+        return d.chunks[pid]
+    for j, s in zip(J, d.dims):
+        if rlen(j) and (j[0] < 1 or j[1] > s):
+            raise IndexError(f"BoundsError: attempt to access {d.dims} DArray at index {J}")
+    return SubDArray(d, J, tuple(False for _ in J)).to_device()
+
+
+def to_array(d: DArray) -> np.ndarray:
+    """``Array(d)`` (src/darray.jl:574-582): gather every chunk into a host array (collective; on every rank)."""
+    a = np.empty(d.dims, dtype=d.dtype, order="F")
+    mine = {pid: ch.to_numpy() for pid, ch in d.chunks.items()}
+    for part in d.rt.allgather_object(mine):
+        for pid, h in part.items():
+            I = d.layout.localindices(pid)
+            if all(rlen(r) > 0 for r in I):
+                a[tuple(slice(lo - 1, hi) for lo, hi in I)] = h
+    return a
+
+
+def copyto(dest: DArray, src: np.ndarray) -> DArray:
+    """``copyto!(dest::DArray, src::AbstractArray)`` (src/darray.jl:679-687)."""
+    src = np.asarray(src)
+    if tuple(src.shape) != dest.dims:
+        raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"DArray has size {dest.dims} but array has {src.shape}")
+    for pid, ch in dest.chunks.items():
+        I = dest.layout.localindices(pid)
+        ch.copy_from_host(src[tuple(slice(lo - 1, hi) for lo, hi in I)].astype(dest.dtype, copy=False), sync=False)
+    dest.rt.sync()
+    return dest
+
+
+def similar(d: DArray, dtype=None, dims=None) -> DArray:
+    """``similar(d[, T[, dims]])`` (src/darray.jl:240-243): uninitialised, layout of ``d`` when dims are unchanged."""
+    dt = np.dtype(dtype) if dtype is not None else d.dtype
+    if dims is None or tuple(dims) == d.dims:
+        return darray_like(lambda I: B200Array.empty(d.rt, shape_of(I), dt), d, dtype=dt)
+    return darray(lambda I: B200Array.empty(d.rt, shape_of(I), dt), dims, procs(d), dtype=dt, rt=d.rt)
+
+
+def fill_(d: DArray, x) -> DArray:
+    """``fill!(A::DArray, x)`` (src/darray.jl:822-827)."""
+    v = np.asarray(x, dtype=d.dtype)
+    for ch in d.chunks.values():
+        _lib.call("dab_fill", d.rt.ctx, dab_dtype(d.dtype), C.c_void_p(ch.ptr), ch.size, C.c_void_p(v.ctypes.data))
+    return d
+
+
+def d_closeall():
+    """``d_closeall()`` (src/core.jl:97-105)."""
+    for d in list(_REGISTRY.values()):
+        d.close()
+
+
+def registry_size() -> int:
+    """Leak check used by the tests (reference test/runtests.jl:28-37, test/darray.jl:1079-1086)."""
+    return len(_REGISTRY)

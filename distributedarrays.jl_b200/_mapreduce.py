@@ -1,0 +1,360 @@
+"""Distributed reductions: the reference's ``src/mapreduce.jl:17-131`` on B200.
+
+  * ``reduce`` / ``mapreduce`` / ``sum`` / ``prod`` / ``maximum`` / ``minimum``  -- ``Base._mapreduce(f, op, ::IndexCartesian,
+    d::DArray)`` (reference src/mapreduce.jl:29-35): ONE streaming kernel per localpart, the P chunk results are gathered on
+    every rank (NCCL all-gather over NVLink instead of ``remotecall_fetch``), then folded LEFT TO RIGHT in ``procs(d)`` order
+    in the result type -- exactly ``reduce(op, results)`` (:34).
+  * ``mapreduce(...; dims)`` -- ``reducedim_initarray`` (:42-51), ``mapreducedim_within`` (:54-66),
+    ``mapreducedim_between!`` (:71-81), ``mapreducedim!`` (:83-94): every worker reduces its chunk along ``region``; the
+    owners of R (grid index 1 along the reduced dims, :44) receive the partial slabs of their fibre (grouped NCCL
+    send/recv) and accumulate them, in grid order, onto R.
+  * ``all`` / ``any`` / ``count`` / ``extrema`` (:97-131).
+"""
+from __future__ import annotations
+
+import builtins
+import ctypes as C
+import operator
+from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+from ._broadcast import Expr, broadcast, tag_of, trace, _NPT
+from ._darray import B200Array, DArray, dab_dtype, np_dtype
+from .layout import Layout, collapse_for_region, ravel, rlen, shape_of, unravel
+
+_OPS = {"+": _lib.SUM, "add": _lib.SUM, "sum": _lib.SUM, "*": _lib.PROD, "mul": _lib.PROD, "prod": _lib.PROD, "max": _lib.MAX,
+        "min": _lib.MIN}
+_OPF = {operator.add: _lib.SUM, operator.mul: _lib.PROD, builtins.max: _lib.MAX, builtins.min: _lib.MIN, np.add: _lib.SUM,
+        np.multiply: _lib.PROD, np.maximum: _lib.MAX, np.minimum: _lib.MIN}
+
+
+def _op_code(op) -> int:
+    if isinstance(op, str) and op in _OPS:
+        return _OPS[op]
+    if op in _OPF:
+        return _OPF[op]
+    raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"reduction operator {op!r} is not served by a kernel (no host fallback)")
+
+
+_CMPMAP = {"eq": _lib.MAP_EQ, "ne": _lib.MAP_NE, "lt": _lib.MAP_LT, "le": _lib.MAP_LE, "gt": _lib.MAP_GT, "ge": _lib.MAP_GE}
+_FLIP = {"lt": "gt", "le": "ge", "gt": "lt", "ge": "le", "eq": "eq", "ne": "ne"}
+
+
+def classify_map(f: Optional[Callable], dtype) -> Tuple[Optional[int], Optional[np.ndarray], Optional[Expr]]:
+    """f -> (DAB_MAP_* code, predicate parameter, traced expr).  code is None when f needs the general (two-pass) path."""
+    if f is None:
+        return _lib.MAP_ID, None, None
+    tag = tag_of(dtype)
+    e = trace(f, [tag])
+    if e.op == "arg":
+        return _lib.MAP_ID, None, e
+    if e.jt == tag and len(e.args) == 1 and e.args[0].op == "arg":
+        code = {"abs": _lib.MAP_ABS, "abs2": _lib.MAP_ABS2, "neg": _lib.MAP_NEG}.get(e.op)
+        if code is not None:
+            return code, None, e
+    if e.op == "mul" and e.jt == tag and all(a.op == "arg" for a in e.args):  # x*x == abs2 for reals
+        return _lib.MAP_ABS2, None, e
+    if e.op in _CMPMAP:
+        l, r = e.args
+        if l.op == "arg" and r.op == "const" and l.jt == tag:
+            return _CMPMAP[e.op], np.asarray(r.val, dtype=np.dtype(dtype)), e
+        if r.op == "arg" and l.op == "const" and r.jt == tag:
+            return _CMPMAP[_FLIP[e.op]], np.asarray(l.val, dtype=np.dtype(dtype)), e
+    if e.op == "isnan" and e.args[0].op == "arg":
+        return _lib.MAP_ISNAN, None, e
+    return None, None, e
+
+
+def _result_dtype(dtype, op: int, mapc: int) -> np.dtype:
+    out = C.c_int32()
+    _lib.check(_lib.lib().dab_reduce_result_dtype(dab_dtype(dtype), op, mapc, C.byref(out)))
+    return np.dtype(np.int64) if out.value == _lib.I64 else np_dtype(out.value)
+
+
+# ---- whole-array reductions ------------------------------------------------------------------------------------------------
+
+
+def _chunk_partials(d: DArray, op: int, mapc: int, param) -> Tuple[np.ndarray, np.dtype]:
+    """One kernel per local chunk, the chunk results of ALL workers on every rank (bytes, 16 per worker, worker order)."""
+    rt = d.rt
+    code = dab_dtype(d.dtype)
+    wpr = rt.workers_per_rank
+    slots = B200Array.empty(rt, (16 * wpr,), np.uint8)
+    pp = C.c_void_p(param.ctypes.data) if param is not None else None
+    try:
+        for pid, ch in d.chunks.items():
+            k = (pid - 1) % wpr
+            _lib.call("dab_reduce", rt.ctx, code, op, mapc, pp, C.c_void_p(ch.ptr), ch.size, C.c_void_p(slots.ptr + 16 * k))
+        if rt.world > 1:
+            allslots = B200Array.empty(rt, (16 * wpr * rt.world,), np.uint8)
+            _lib.call("dab_allgather", rt.ctx, C.c_void_p(slots.ptr), C.c_void_p(allslots.ptr), 16 * wpr)
+            host = allslots.to_numpy()
+            allslots.free()
+        else:
+            host = slots.to_numpy()
+    finally:
+        rt.sync()
+        slots.free()
+    return host.view(np.uint8), _result_dtype(d.dtype, op, mapc)
+
+
+def _fold(host: np.ndarray, pids: Sequence[int], rdt: np.dtype, op: int):
+    """``reduce(op, results)`` (src/mapreduce.jl:34): left fold in procs(d) order, in the result type."""
+    vals = np.empty(len(pids), dtype=rdt)
+    for i, pid in enumerate(pids):
+        vals[i] = host[16 * (pid - 1):16 * (pid - 1) + rdt.itemsize].view(rdt)[0]
+    out = np.zeros(1, dtype=rdt)
+    rcode = _lib.I64 if rdt == np.dtype(np.int64) else dab_dtype(rdt)
+    _lib.check(_lib.lib().dab_combine_ordered(rcode, op, C.c_void_p(vals.ctypes.data), len(pids), C.c_void_p(out.ctypes.data)))
+    return out[0], vals
+
+
+def _mapreduce_all(f, op, d: DArray, return_partials: bool = False):
+    opc = op if isinstance(op, int) else _op_code(op)
+    mapc, param, expr = classify_map(f, d.dtype)
+    src, tmp = d, None
+    if mapc is None:
+        # general f: materialise f.(d) with the SAME layout (one fused kernel per chunk), then reduce with identity
+        from ._broadcast import LocalArg, run_local
+        from ._darray import darray_like
+        out_dt = _NPT[expr.jt]
+        tmp = darray_like(lambda I: B200Array.empty(d.rt, shape_of(I), out_dt), d, dtype=out_dt)
+        for pid, out in tmp.chunks.items():
+            run_local(d.rt, expr, out, [LocalArg(d.chunks[pid], None, tag_of(d.dtype))])
+        src, mapc, param = tmp, (_lib.MAP_NONZERO if out_dt == np.dtype(np.bool_) else _lib.MAP_ID), None
+    if opc in (_lib.MAX, _lib.MIN):
+        for pid in src.layout.pids:
+            if int(np.prod(shape_of(src.layout.localindices(pid)))) == 0:
+                if tmp is not None:
+                    tmp.close()
+                raise _lib.ArgumentError(_lib.ERR_EMPTY, "reducing over an empty collection is not allowed")
+    rt = d.rt
+    try:
+        if rt.workers_per_rank == 1 and src.layout.pids == rt.workers() and not return_partials:
+            # production mapping, one chunk per GPU: kernel + NCCL all-gather + ordered fold in ONE C-ABI call
+            ch = src.chunks[rt.myid()]
+            rdt = _result_dtype(src.dtype, opc, mapc)
+            out = np.zeros(2, dtype=np.uint64)
+            _lib.call("dab_mapreduce_all", rt.ctx, dab_dtype(src.dtype), opc, mapc, C.c_void_p(param.ctypes.data) if param is not None else None,
+                      C.c_void_p(ch.ptr), ch.size, C.c_void_p(out.ctypes.data))
+            return out.view(np.uint8)[:rdt.itemsize].view(rdt)[0]
+        host, rdt = _chunk_partials(src, opc, mapc, param)
+        res, vals = _fold(host, src.layout.pids, rdt, opc)
+        return (res, vals) if return_partials else res
+    finally:
+        if tmp is not None:
+            tmp.close()
+
+
+def reduce(op, d: DArray, dims=None, init=None):
+    """``reduce(f, d::DArray)`` (reference src/mapreduce.jl:17-27); with ``dims`` the dimensional form."""
+    return mapreduce(None, op, d, dims=dims, init=init)
+
+
+def mapreduce(f: Optional[Callable], op, d: DArray, dims=None, init=None, _partials: bool = False):
+    """``mapreduce(f, op, d::DArray[; dims, init])`` (reference src/mapreduce.jl:29-35 and :42-94)."""
+    if dims is None:
+        if init is not None:
+            raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "mapreduce(f, op, d; init) without dims falls back to scalar iteration in the reference; not served")
+        return _mapreduce_all(f, op, d, _partials)
+    return mapreducedim(f, op, d, dims, init)
+
+
+def sum(d: DArray, f: Optional[Callable] = None, dims=None):  # noqa: A001 - mirrors Base.sum
+    return mapreduce(f, "+", d, dims=dims)
+
+
+def prod(d: DArray, f: Optional[Callable] = None, dims=None):
+    return mapreduce(f, "*", d, dims=dims)
+
+
+def maximum(d: DArray, f: Optional[Callable] = None, dims=None):
+    return mapreduce(f, "max", d, dims=dims)
+
+
+def minimum(d: DArray, f: Optional[Callable] = None, dims=None):
+    return mapreduce(f, "min", d, dims=dims)
+
+
+def _pred_reduce(opc: int, d: DArray, f: Optional[Callable]):
+    if f is None:
+        if d.dtype != np.dtype(np.bool_):
+            raise TypeError("TypeError: non-boolean used in boolean context")
+        return _mapreduce_all(None, opc, d)
+    mapc, param, e = classify_map(f, d.dtype)
+    if e is not None and e.jt != "bool":
+        raise TypeError("TypeError: non-boolean used in boolean context")
+    return _mapreduce_all(f, opc, d)
+
+
+def all(d: DArray, f: Optional[Callable] = None) -> bool:  # noqa: A001
+    """``Base._all(f, A::DArray, ::Colon)`` (reference src/mapreduce.jl:97-104)."""
+    return bool(_pred_reduce(_lib.ALL, d, f))
+
+
+def any(d: DArray, f: Optional[Callable] = None) -> bool:  # noqa: A001
+    """reference src/mapreduce.jl:106-113."""
+    return bool(_pred_reduce(_lib.ANY, d, f))
+
+
+def count(d: DArray, f: Optional[Callable] = None) -> int:
+    """reference src/mapreduce.jl:115-122."""
+    return int(_pred_reduce(_lib.COUNT, d, f))
+
+
+def extrema(d: DArray):
+    """reference src/mapreduce.jl:124-131: per-chunk (min, max), folded with (min, max)."""
+    return (_mapreduce_all(None, _lib.MIN, d), _mapreduce_all(None, _lib.MAX, d))
+
+
+# ---- dimensional reduction ------------------------------------------------------------------------------------------------------
+
+
+def _normalise_region(dims, ndim: int) -> Tuple[int, ...]:
+    if isinstance(dims, (int, np.integer)):
+        dims = (int(dims),)
+    dims = tuple(int(x) for x in dims)
+    for x in dims:
+        if x <= 0:  # Base.check_reducedims / reduced_indices: "region dimension(s) must be >= 1"
+            raise _lib.ArgumentError(_lib.ERR_ARG, f"ArgumentError: region dimension(s) must be ≥ 1, got {x}")
+    return tuple(sorted(set(dims)))
+
+
+def reduce_chunk_dims(rt, ch: B200Array, region_in: Sequence[int], op: int, mapc: int, out_dtype: np.dtype) -> B200Array:
+    """``mapreduce(f, op, localpart(A), dims=region)`` (reference src/mapreduce.jl:64) on one chunk.
+    Every maximal run of reduced dims is one (inner, reduce, outer) kernel pass, last run first."""
+    shape = list(ch.shape)
+    runs = collapse_for_region(shape, set(region_in))
+    cur, cur_dtype, cur_map, owned = ch, ch.dtype, mapc, False
+    # positions of runs: process reduced runs from the last to the first so `inner` stays the untouched prefix
+    ext = [e for _, e in runs]
+    for ri in range(len(runs) - 1, -1, -1):
+        if not runs[ri][0]:
+            continue
+        inner = int(np.prod(ext[:ri])) if ri else 1
+        red = ext[ri]
+        outer = int(np.prod(ext[ri + 1:])) if ri + 1 < len(ext) else 1
+        nxt = B200Array.empty(rt, (inner * outer,), out_dtype)
+        _lib.call("dab_reducedim", rt.ctx, dab_dtype(cur_dtype), op, cur_map, C.c_void_p(cur.ptr), inner, red, outer, C.c_void_p(nxt.ptr), 0)
+        if owned:
+            rt.sync()
+            cur.free()
+        cur, cur_dtype, cur_map, owned = nxt, out_dtype, _lib.MAP_ID, True
+        ext[ri] = 1
+    rshape = tuple(1 if (k + 1) in region_in else s for k, s in enumerate(ch.shape))
+    if not owned:  # nothing reduced (cannot happen when region_in is non-empty)
+        return ch
+    cur.shape = rshape
+    return cur
+
+
+def mapreducedim(f: Optional[Callable], op, d: DArray, dims, init=None) -> DArray:
+    """``mapreduce(f, op, d; dims[, init])`` -> DArray R (reference src/mapreduce.jl:42-94)."""
+    rt = d.rt
+    opc = _op_code(op)
+    N = d.ndim
+    region = _normalise_region(dims, N)
+    reg_in = tuple(r for r in region if r <= N)
+    mapc, param, expr = classify_map(f, d.dtype)
+    if param is not None:
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "predicate maps with dims are not served")
+    src, tmp = d, None
+    if mapc is None:
+        from ._broadcast import LocalArg, run_local
+        from ._darray import darray_like
+        out_dt = _NPT[expr.jt]
+        tmp = darray_like(lambda I: B200Array.empty(rt, shape_of(I), out_dt), d, dtype=out_dt)
+        for pid, out in tmp.chunks.items():
+            run_local(rt, expr, out, [LocalArg(d.chunks[pid], None, tag_of(d.dtype))])
+        src, mapc = tmp, _lib.MAP_ID
+    rdt = _result_dtype(src.dtype, opc, mapc)
+    L = src.layout
+    try:
+        if not reg_in or d.size == 0:
+            # ``isempty(region) -> copyto!(R, A)`` (src/mapreduce.jl:89-91; f and init are NOT applied there) and
+            # ``isempty(A) -> copy(R)`` (:85-87)
+            from ._darray import darray_like
+            R = darray_like(lambda I: B200Array.empty(rt, shape_of(I), rdt), d, dtype=rdt)
+            for pid, out in R.chunks.items():
+                if out.size:
+                    if d.dtype == rdt:
+                        _lib.call("dab_d2d", rt.ctx, C.c_void_p(out.ptr), C.c_void_p(d.chunks[pid].ptr), out.nbytes)
+                    else:
+                        from ._broadcast import LocalArg, run_local, Expr as _E
+                        run_local(rt, _E("arg", (), tag_of(d.dtype), 0), out, [LocalArg(d.chunks[pid], None, tag_of(d.dtype))])
+            return R
+        # ---- layout of R: pids[1:1 along region, : elsewhere] (src/mapreduce.jl:44)
+        Rgrid = tuple(1 if (k + 1) in reg_in else g for k, g in enumerate(L.grid))
+        nR = int(np.prod(Rgrid))
+        Rpids, Rindices, fibres = [], [], []
+        for rl in range(nR):
+            rc = unravel(rl, Rgrid)
+            owner_lin = ravel(rc, L.grid)
+            Rpids.append(L.pids[owner_lin])
+            Rindices.append(tuple((1, 1) if (k + 1) in reg_in else L.indices[owner_lin][k] for k in range(N)))
+            # fibre members in column-major order over the grid dims inside the region
+            sub = [L.grid[k] if (k + 1) in reg_in else 1 for k in range(N)]
+            members = []
+            for ml in range(int(np.prod(sub))):
+                mc = unravel(ml, sub)
+                members.append(ravel(tuple(mc[k] if (k + 1) in reg_in else rc[k] for k in range(N)), L.grid))
+            fibres.append(members)
+        Rdims = tuple(1 if (k + 1) in reg_in else s for k, s in enumerate(L.dims))
+        Rcuts = [[1, 2] if (k + 1) in reg_in else list(L.cuts[k]) for k in range(N)]
+        Rlayout = Layout(Rdims, Rgrid, Rpids, Rindices, Rcuts)
+        # ---- phase 1: mapreducedim_within (src/mapreduce.jl:54-66)
+        partial: Dict[int, B200Array] = {}
+        for pid, ch in src.chunks.items():
+            partial[pid] = reduce_chunk_dims(rt, ch, reg_in, opc, mapc, rdt)
+        # ---- phase 2: mapreducedim_between! (src/mapreduce.jl:71-81)
+        Rchunks: Dict[int, B200Array] = {}
+        stacks: Dict[int, Tuple[B200Array, int, int]] = {}
+        sends, recvs = [], []
+        for rl, members in enumerate(fibres):
+            owner = Rpids[rl]
+            plen = int(np.prod(shape_of(Rindices[rl])))
+            if rt.is_local(owner):
+                stack = B200Array.empty(rt, (plen * len(members),), rdt)
+                stacks[rl] = (stack, plen, len(members))
+                for slot, m in enumerate(members):
+                    mp = L.pids[m]
+                    dst = stack.ptr + slot * plen * rdt.itemsize
+                    if rt.is_local(mp):
+                        _lib.call("dab_d2d", rt.ctx, C.c_void_p(dst), C.c_void_p(partial[mp].ptr), plen * rdt.itemsize)
+                    else:
+                        recvs.append((dst, plen * rdt.itemsize, rt.rank_of(mp)))
+            else:
+                for m in members:
+                    mp = L.pids[m]
+                    if rt.is_local(mp):
+                        sends.append((partial[mp].ptr, plen * rdt.itemsize, rt.rank_of(owner)))
+        if sends or recvs:
+            _lib.call("dab_group_start", rt.ctx)
+            for ptr, nb, peer in sends:
+                _lib.call("dab_send", rt.ctx, C.c_void_p(ptr), nb, peer)
+            for ptr, nb, peer in recvs:
+                _lib.call("dab_recv", rt.ctx, C.c_void_p(ptr), nb, peer)
+            _lib.call("dab_group_end", rt.ctx)
+        for rl, (stack, plen, nm) in stacks.items():
+            owner = Rpids[rl]
+            Rch = B200Array.empty(rt, shape_of(Rindices[rl]), rdt)
+            acc = 0
+            if init is not None:
+                v = np.asarray(init, dtype=rdt)
+                _lib.call("dab_fill", rt.ctx, dab_dtype(rdt) if rdt != np.dtype(np.int64) else _lib.I64, C.c_void_p(Rch.ptr), Rch.size,
+                          C.c_void_p(v.ctypes.data))
+                acc = 1
+            # Base.mapreducedim!(identity, op, localpart(R), Bfull): accumulate the nm partial slabs, in grid order, onto R
+            _lib.call("dab_reducedim", rt.ctx, dab_dtype(rdt), opc, _lib.MAP_ID, C.c_void_p(stack.ptr), plen, nm, 1, C.c_void_p(Rch.ptr), acc)
+            Rchunks[owner] = Rch
+        rt.sync()
+        for stack, _, _ in stacks.values():
+            stack.free()
+        for p in partial.values():
+            p.free()
+        return DArray(Rlayout, rdt, Rchunks, rt)
+    finally:
+        if tmp is not None:
+            tmp.close()

@@ -1,0 +1,322 @@
+// dab_core.cu -- lifecycle, buffers, events, fill!, rand!  (C ABI: include/dab200.h)
+#include <cstdarg>
+#include <cstdlib>
+#include <mutex>
+#include <new>
+#include <unordered_map>
+
+#include "dab_common.cuh"
+
+thread_local char dab_tls_err[512] = "";
+
+int dab_resident_ctas(const void* kernel, int threads) {
+    static std::mutex mu;
+    static std::unordered_map<const void*, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(kernel);
+    if (it != cache.end()) return it->second;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = 1;
+    }
+    cache[kernel] = n;
+    return n;
+}
+
+int32_t dab_fail(dab_ctx* ctx, int32_t status, const char* fmt, ...) {
+    char* dst = ctx ? ctx->err : dab_tls_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    if (ctx) memcpy(dab_tls_err, dst, 512);
+    return status;
+}
+
+int32_t dab_fail_cuda(dab_ctx* ctx, cudaError_t e, const char* what, const char* file, int line) {
+    // clear the (non-sticky) error state so it does not leak into the next call
+    cudaGetLastError();
+    return dab_fail(ctx, e == cudaErrorMemoryAllocation ? DAB_ERR_NOMEM : DAB_ERR_CUDA, "CUDA error %d (%s) in %s at %s:%d",
+                    (int)e, cudaGetErrorString(e), what, file, line);
+}
+
+extern "C" {
+
+int32_t dab_abi_version(void) { return DAB_ABI_VERSION; }
+
+const char* dab_status_string(int32_t s) {
+    switch (s) {
+        case DAB_OK: return "ok";
+        case DAB_ERR_CUDA: return "CUDA error";
+        case DAB_ERR_ARG: return "ArgumentError";
+        case DAB_ERR_EMPTY: return "ArgumentError: reducing over an empty collection is not allowed";
+        case DAB_ERR_DIM_MISMATCH: return "DimensionMismatch";
+        case DAB_ERR_NCCL: return "NCCL error";
+        case DAB_ERR_UNSUPPORTED: return "unsupported op/dtype (no host fallback)";
+        case DAB_ERR_NVRTC: return "NVRTC error";
+        case DAB_ERR_NOMEM: return "out of device memory";
+        default: return "unknown status";
+    }
+}
+
+const char* dab_last_error(const dab_ctx* ctx) { return ctx ? ctx->err : dab_tls_err; }
+
+int32_t dab_device_count(int32_t* count) {
+    if (!count) return dab_fail(nullptr, DAB_ERR_ARG, "null count");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return dab_fail_cuda(nullptr, e, "cudaGetDeviceCount", __FILE__, __LINE__);
+    }
+    *count = n;
+    return DAB_OK;
+}
+
+int32_t dab_init(int32_t device, dab_ctx** out) {
+    if (!out) return dab_fail(nullptr, DAB_ERR_ARG, "null ctx out-pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return dab_fail_cuda(nullptr, e, "cudaGetDeviceCount", __FILE__, __LINE__);
+    if (device < 0 || device >= n) return dab_fail(nullptr, DAB_ERR_ARG, "device %d out of range (have %d)", device, n);
+    dab_ctx* ctx = new (std::nothrow) dab_ctx();
+    if (!ctx) return dab_fail(nullptr, DAB_ERR_NOMEM, "host allocation failed");
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    ctx->rank = 0;
+    ctx->nranks = 1;
+#define INIT_CUDA(call)                                                     \
+    do {                                                                    \
+        cudaError_t e__ = (call);                                           \
+        if (e__ != cudaSuccess) {                                           \
+            int32_t st = dab_fail_cuda(nullptr, e__, #call, __FILE__, __LINE__); \
+            delete ctx;                                                     \
+            return st;                                                      \
+        }                                                                   \
+    } while (0)
+    INIT_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    INIT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        delete ctx;
+        return dab_fail(nullptr, DAB_ERR_UNSUPPORTED, "device %d is sm_%d%d; libdab200 is built for sm_100a only", device,
+                        prop.major, prop.minor);
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    INIT_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    INIT_CUDA(cudaMalloc(&ctx->block_partials, (size_t)DAB_MAX_REDUCE_BLOCKS * 16));
+    INIT_CUDA(cudaMalloc((void**)&ctx->counter, 64));
+    INIT_CUDA(cudaMemsetAsync(ctx->counter, 0, 64, ctx->stream));
+    INIT_CUDA(cudaMalloc(&ctx->result_slot, DAB_SLOT_BYTES));
+    INIT_CUDA(cudaMalloc(&ctx->gather_slots, (size_t)DAB_MAX_RANKS * 16));
+    INIT_CUDA(cudaHostAlloc(&ctx->host_slot, (size_t)(DAB_MAX_RANKS + 2) * 16, cudaHostAllocDefault));
+    INIT_CUDA(cudaStreamSynchronize(ctx->stream));
+#undef INIT_CUDA
+    *out = ctx;
+    return DAB_OK;
+}
+
+int32_t dab_comm_destroy(dab_ctx* ctx);
+
+int32_t dab_shutdown(dab_ctx* ctx) {
+    if (!ctx) return DAB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) dab_comm_destroy(ctx);
+    cudaFree(ctx->block_partials);
+    cudaFree(ctx->counter);
+    cudaFree(ctx->result_slot);
+    cudaFree(ctx->gather_slots);
+    if (ctx->dim_scratch) cudaFree(ctx->dim_scratch);
+    cudaFreeHost(ctx->host_slot);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return DAB_OK;
+}
+
+int32_t dab_sync(dab_ctx* ctx) {
+    DAB_ENTER(ctx);
+    DAB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DAB_OK;
+}
+
+int32_t dab_device_info(dab_ctx* ctx, int32_t* device, int32_t* sm_count, size_t* free_bytes, size_t* total_bytes) {
+    DAB_ENTER(ctx);
+    size_t f = 0, t = 0;
+    DAB_CUDA(ctx, cudaMemGetInfo(&f, &t));
+    if (device) *device = ctx->device;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return DAB_OK;
+}
+
+int32_t dab_stream(dab_ctx* ctx, void** stream) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, stream, DAB_ERR_ARG, "null stream out-pointer");
+    *stream = (void*)ctx->stream;
+    return DAB_OK;
+}
+
+int32_t dab_launch_count(dab_ctx* ctx, uint64_t* launches) {
+    if (!ctx || !launches) return dab_fail(ctx, DAB_ERR_ARG, "null argument");
+    *launches = ctx->launches;
+    return DAB_OK;
+}
+
+// ---- events -----------------------------------------------------------------------------
+int32_t dab_event_create(dab_ctx* ctx, void** event) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, event, DAB_ERR_ARG, "null event out-pointer");
+    cudaEvent_t ev;
+    DAB_CUDA(ctx, cudaEventCreate(&ev));
+    *event = (void*)ev;
+    return DAB_OK;
+}
+int32_t dab_event_record(dab_ctx* ctx, void* event) {
+    DAB_ENTER(ctx);
+    DAB_CUDA(ctx, cudaEventRecord((cudaEvent_t)event, ctx->stream));
+    return DAB_OK;
+}
+int32_t dab_event_elapsed_ms(dab_ctx* ctx, void* start, void* stop, float* ms) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, ms, DAB_ERR_ARG, "null ms");
+    DAB_CUDA(ctx, cudaEventSynchronize((cudaEvent_t)stop));
+    DAB_CUDA(ctx, cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return DAB_OK;
+}
+int32_t dab_event_destroy(dab_ctx* ctx, void* event) {
+    DAB_ENTER(ctx);
+    DAB_CUDA(ctx, cudaEventDestroy((cudaEvent_t)event));
+    return DAB_OK;
+}
+
+// ---- buffers ----------------------------------------------------------------------------
+int32_t dab_alloc(dab_ctx* ctx, size_t nbytes, void** dptr) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, dptr, DAB_ERR_ARG, "null dptr out-pointer");
+    *dptr = nullptr;
+    if (nbytes == 0) nbytes = 16;  // empty localparts still get a valid, distinct address
+    DAB_CUDA(ctx, cudaMalloc(dptr, nbytes));
+    return DAB_OK;
+}
+int32_t dab_free(dab_ctx* ctx, void* dptr) {
+    DAB_ENTER(ctx);
+    if (dptr) DAB_CUDA(ctx, cudaFree(dptr));
+    return DAB_OK;
+}
+int32_t dab_host_alloc(dab_ctx* ctx, size_t nbytes, void** hptr) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, hptr, DAB_ERR_ARG, "null hptr out-pointer");
+    DAB_CUDA(ctx, cudaHostAlloc(hptr, nbytes ? nbytes : 16, cudaHostAllocDefault));
+    return DAB_OK;
+}
+int32_t dab_host_free(dab_ctx* ctx, void* hptr) {
+    DAB_ENTER(ctx);
+    if (hptr) DAB_CUDA(ctx, cudaFreeHost(hptr));
+    return DAB_OK;
+}
+int32_t dab_h2d(dab_ctx* ctx, void* dptr, const void* hptr, size_t nbytes) {
+    DAB_ENTER(ctx);
+    if (nbytes) DAB_CUDA(ctx, cudaMemcpyAsync(dptr, hptr, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    return DAB_OK;
+}
+int32_t dab_d2h(dab_ctx* ctx, void* hptr, const void* dptr, size_t nbytes) {
+    DAB_ENTER(ctx);
+    if (nbytes) DAB_CUDA(ctx, cudaMemcpyAsync(hptr, dptr, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return DAB_OK;
+}
+int32_t dab_d2d(dab_ctx* ctx, void* dst, const void* src, size_t nbytes) {
+    DAB_ENTER(ctx);
+    if (nbytes) DAB_CUDA(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return DAB_OK;
+}
+int32_t dab_h2d_2d(dab_ctx* ctx, void* dptr, size_t dpitch, const void* hptr, size_t hpitch, size_t row_bytes, size_t cols) {
+    DAB_ENTER(ctx);
+    if (row_bytes && cols)
+        DAB_CUDA(ctx, cudaMemcpy2DAsync(dptr, dpitch, hptr, hpitch, row_bytes, cols, cudaMemcpyHostToDevice, ctx->stream));
+    return DAB_OK;
+}
+int32_t dab_d2h_2d(dab_ctx* ctx, void* hptr, size_t hpitch, const void* dptr, size_t dpitch, size_t row_bytes, size_t cols) {
+    DAB_ENTER(ctx);
+    if (row_bytes && cols)
+        DAB_CUDA(ctx, cudaMemcpy2DAsync(hptr, hpitch, dptr, dpitch, row_bytes, cols, cudaMemcpyDeviceToHost, ctx->stream));
+    return DAB_OK;
+}
+
+}  // extern "C"
+
+// ---- fill! / rand! kernels ----------------------------------------------------------------
+// Write-only streams: 16-byte stores, grid = 8 CTAs/SM, grid-stride.  Alignment: the head (up to
+// 16/sizeof(T)-1 elements) and the tail are written as scalars by the last CTA.
+template <typename T, typename Gen>
+__global__ void __launch_bounds__(256) dab_generate_kernel(T* __restrict__ x, size_t n, Gen gen) {
+    constexpr int VPT = 16 / sizeof(T);
+    size_t head = ((16 - ((uintptr_t)x & 15)) & 15) / sizeof(T);
+    if (head > n) head = n;
+    size_t nvec = (n - head) / VPT;
+    int4* xv = reinterpret_cast<int4*>(x + head);
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        Pack<T> p;
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) p.v[k] = gen(head + i * VPT + k);
+        st_stream(xv + i, as_int4(p));
+    }
+    if (blockIdx.x == gridDim.x - 1) {
+        for (size_t i = threadIdx.x; i < head; i += blockDim.x) x[i] = gen(i);
+        for (size_t i = head + nvec * VPT + threadIdx.x; i < n; i += blockDim.x) x[i] = gen(i);
+    }
+}
+
+template <typename T>
+struct FillGen {
+    T v;
+    __device__ __forceinline__ T operator()(size_t) const { return v; }
+};
+template <typename T>
+struct RandGen {
+    uint64_t seed, off;
+    __device__ __forceinline__ T operator()(size_t i) const {
+        return (T)(dab_hash_u32(seed, off + i) >> 8) * (T)5.9604644775390625e-08;  // 2^-24
+    }
+};
+
+template <typename T, typename Gen>
+static int32_t launch_generate(dab_ctx* ctx, T* x, size_t n, Gen gen) {
+    if (n == 0) return DAB_OK;
+    size_t nvec = n / (16 / sizeof(T)) + 1;
+    int grid = dab_persistent_grid(ctx, dab_generate_kernel<T, Gen>, 256, (nvec + 255) / 256);
+    dab_generate_kernel<T, Gen><<<grid, 256, 0, ctx->stream>>>(x, n, gen);
+    DAB_LAUNCHED(ctx);
+    return DAB_OK;
+}
+
+extern "C" {
+
+int32_t dab_fill(dab_ctx* ctx, int32_t dtype, void* x, size_t n, const void* value) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, (x || n == 0) && value, DAB_ERR_ARG, "dab_fill: null pointer");
+    switch (dtype) {
+        case DAB_F32: return launch_generate(ctx, (float*)x, n, FillGen<float>{*(const float*)value});
+        case DAB_F64: return launch_generate(ctx, (double*)x, n, FillGen<double>{*(const double*)value});
+        case DAB_I32: return launch_generate(ctx, (int32_t*)x, n, FillGen<int32_t>{*(const int32_t*)value});
+        case DAB_I64: return launch_generate(ctx, (long long*)x, n, FillGen<long long>{*(const long long*)value});
+        case DAB_U8: return launch_generate(ctx, (uint8_t*)x, n, FillGen<uint8_t>{*(const uint8_t*)value});
+        default: return dab_fail(ctx, DAB_ERR_ARG, "dab_fill: bad dtype %d", dtype);
+    }
+}
+
+int32_t dab_rand_u01(dab_ctx* ctx, int32_t dtype, void* x, size_t n, uint64_t seed, uint64_t global_offset) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, x || n == 0, DAB_ERR_ARG, "dab_rand_u01: null pointer");
+    switch (dtype) {
+        case DAB_F32: return launch_generate(ctx, (float*)x, n, RandGen<float>{seed, global_offset});
+        case DAB_F64: return launch_generate(ctx, (double*)x, n, RandGen<double>{seed, global_offset});
+        default: return dab_fail(ctx, DAB_ERR_UNSUPPORTED, "dab_rand_u01: dtype %d (F32/F64 only)", dtype);
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,311 @@
+// dab_elementwise.cu -- K1-K3: the fused per-localpart broadcast / map! loop, as streaming sm_100a kernels.
+//
+// Replaces Base.Broadcast.copyto!(localpart(dest), lbc) (reference src/broadcast.jl:80), copy(lbc) (:96) and
+// map!(f, localpart(dest), makelocal(src, ...)) (src/mapreduce.jl:8).
+//
+// Roofline: HBM.  Algorithmic traffic = sizeof(T) * (inputs + 1) bytes / element (8 B/elem for y .= a.*x .+ b).
+// Design: every element is touched exactly once, so there is no reuse to stage in shared memory; the kernel is a
+// persistent grid (8 CTAs x 256 threads per SM), each CTA walking 16 KiB tiles with UNROLL independent 16-byte
+// evict-first loads in flight per thread before any store (>= 19 MB in flight chip-wide, vs ~5 MB needed by
+// Little's law at 7.7 TB/s x ~0.7 us).  Head/tail elements (unaligned views) are peeled by the last CTA.
+#include <type_traits>
+
+#include "dab_scalar_ops.cuh"
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+template <typename T, typename F, int UNROLL>
+__global__ void __launch_bounds__(EW_THREADS) ew1_kernel(T* y, const T* x, size_t n, size_t head, F f) {
+    constexpr int VPT = 16 / sizeof(T);
+    const size_t nvec = (n - head) / VPT;
+    const int4* xv = reinterpret_cast<const int4*>(x + head);
+    int4* yv = reinterpret_cast<int4*>(y + head);
+    constexpr size_t TILE = (size_t)EW_THREADS * UNROLL;
+    const size_t ntiles = nvec / TILE;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const size_t base = t * TILE + threadIdx.x;
+        int4 r[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) r[u] = ld_stream(xv + base + (size_t)u * EW_THREADS);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            Pack<T> p = as_pack<T>(r[u]);
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) p.v[k] = f(p.v[k]);
+            st_stream(yv + base + (size_t)u * EW_THREADS, as_int4(p));
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1) {  // remainder vectors + unaligned head + tail
+        for (size_t i = ntiles * TILE + threadIdx.x; i < nvec; i += EW_THREADS) {
+            Pack<T> p = as_pack<T>(ld_stream(xv + i));
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) p.v[k] = f(p.v[k]);
+            st_stream(yv + i, as_int4(p));
+        }
+        for (size_t i = threadIdx.x; i < head; i += EW_THREADS) y[i] = f(x[i]);
+        for (size_t i = head + nvec * VPT + threadIdx.x; i < n; i += EW_THREADS) y[i] = f(x[i]);
+    }
+}
+
+template <typename T, typename F, int UNROLL>
+__global__ void __launch_bounds__(EW_THREADS) ew2_kernel(T* z, const T* x, const T* y, size_t n, size_t head, F f) {
+    constexpr int VPT = 16 / sizeof(T);
+    const size_t nvec = (n - head) / VPT;
+    const int4* xv = reinterpret_cast<const int4*>(x + head);
+    const int4* yv = reinterpret_cast<const int4*>(y + head);
+    int4* zv = reinterpret_cast<int4*>(z + head);
+    constexpr size_t TILE = (size_t)EW_THREADS * UNROLL;
+    const size_t ntiles = nvec / TILE;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const size_t base = t * TILE + threadIdx.x;
+        int4 rx[UNROLL], ry[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            rx[u] = ld_stream(xv + base + (size_t)u * EW_THREADS);
+            ry[u] = ld_stream(yv + base + (size_t)u * EW_THREADS);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            Pack<T> p = as_pack<T>(rx[u]), q = as_pack<T>(ry[u]);
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) p.v[k] = f(p.v[k], q.v[k]);
+            st_stream(zv + base + (size_t)u * EW_THREADS, as_int4(p));
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1) {
+        for (size_t i = ntiles * TILE + threadIdx.x; i < nvec; i += EW_THREADS) {
+            Pack<T> p = as_pack<T>(ld_stream(xv + i)), q = as_pack<T>(ld_stream(yv + i));
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) p.v[k] = f(p.v[k], q.v[k]);
+            st_stream(zv + i, as_int4(p));
+        }
+        for (size_t i = threadIdx.x; i < head; i += EW_THREADS) z[i] = f(x[i], y[i]);
+        for (size_t i = head + nvec * VPT + threadIdx.x; i < n; i += EW_THREADS) z[i] = f(x[i], y[i]);
+    }
+}
+
+// pointers whose 16-byte misalignments differ: plain coalesced 4/8-byte accesses
+template <typename T, typename F>
+__global__ void __launch_bounds__(EW_THREADS) ew1_scalar_kernel(T* y, const T* x, size_t n, F f) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = f(x[i]);
+}
+template <typename T, typename F>
+__global__ void __launch_bounds__(EW_THREADS) ew2_scalar_kernel(T* z, const T* x, const T* y, size_t n, F f) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) z[i] = f(x[i], y[i]);
+}
+
+template <typename T>
+inline size_t head_of(const void* p, size_t n) {
+    size_t h = ((16 - ((uintptr_t)p & 15)) & 15) / sizeof(T);
+    return h > n ? n : h;
+}
+
+template <typename T, typename F>
+int32_t launch_ew1(dab_ctx* ctx, T* y, const T* x, size_t n, F f) {
+    if (n == 0) return DAB_OK;
+    if ((((uintptr_t)x) & 15) == (((uintptr_t)y) & 15) && (((uintptr_t)x) % sizeof(T)) == 0) {
+        constexpr int UNROLL = 4;
+        size_t tiles = n / ((16 / sizeof(T)) * (size_t)EW_THREADS * UNROLL);
+        int grid = dab_persistent_grid(ctx, ew1_kernel<T, F, UNROLL>, EW_THREADS, tiles);
+        ew1_kernel<T, F, UNROLL><<<grid, EW_THREADS, 0, ctx->stream>>>(y, x, n, head_of<T>(x, n), f);
+    } else {
+        int grid = dab_persistent_grid(ctx, ew1_scalar_kernel<T, F>, EW_THREADS, (n + EW_THREADS - 1) / EW_THREADS);
+        ew1_scalar_kernel<T, F><<<grid, EW_THREADS, 0, ctx->stream>>>(y, x, n, f);
+    }
+    DAB_LAUNCHED(ctx);
+    return DAB_OK;
+}
+
+template <typename T, typename F>
+int32_t launch_ew2(dab_ctx* ctx, T* z, const T* x, const T* y, size_t n, F f) {
+    if (n == 0) return DAB_OK;
+    uintptr_t mx = (uintptr_t)x & 15, my = (uintptr_t)y & 15, mz = (uintptr_t)z & 15;
+    if (mx == my && mx == mz && (((uintptr_t)x) % sizeof(T)) == 0) {
+        constexpr int UNROLL = 2;
+        size_t tiles = n / ((16 / sizeof(T)) * (size_t)EW_THREADS * UNROLL);
+        int grid = dab_persistent_grid(ctx, ew2_kernel<T, F, UNROLL>, EW_THREADS, tiles);
+        ew2_kernel<T, F, UNROLL><<<grid, EW_THREADS, 0, ctx->stream>>>(z, x, y, n, head_of<T>(x, n), f);
+    } else {
+        int grid = dab_persistent_grid(ctx, ew2_scalar_kernel<T, F>, EW_THREADS, (n + EW_THREADS - 1) / EW_THREADS);
+        ew2_scalar_kernel<T, F><<<grid, EW_THREADS, 0, ctx->stream>>>(z, x, y, n, f);
+    }
+    DAB_LAUNCHED(ctx);
+    return DAB_OK;
+}
+
+// ---- functors --------------------------------------------------------------------------------
+template <typename T>
+struct AffineF {  // a*x + b, two roundings (Julia never contracts; src/broadcast.jl:80 runs Base's loop)
+    T a, b;
+    __device__ __forceinline__ T operator()(T x) const { return jl::add(jl::mul(a, x), b); }
+};
+
+template <typename T, int FN>
+struct UnaryF {
+    __device__ __forceinline__ T operator()(T x) const {
+        if constexpr (FN == DAB_MAP_ID) return x;
+        else if constexpr (FN == DAB_MAP_ABS) return jl::abs(x);
+        else if constexpr (FN == DAB_MAP_ABS2) return jl::mul(x, x);
+        else if constexpr (FN == DAB_MAP_NEG) return jl::neg(x);
+        else if constexpr (FN == DAB_MAP_SIGN) return jl::sign(x);
+        else if constexpr (std::is_floating_point<T>::value) {
+            if constexpr (FN == DAB_MAP_SQRT) return jl::sqrt(x);
+            else if constexpr (FN == DAB_MAP_INV) return jl::inv(x);
+            else if constexpr (FN == DAB_MAP_FLOOR) return floor(x);
+            else if constexpr (FN == DAB_MAP_CEIL) return ceil(x);
+            else return x;
+        } else return x;  // floor/ceil of an integer is the integer
+    }
+};
+
+template <typename T, int OP>
+struct BinOp {
+    __device__ __forceinline__ T operator()(T a, T b) const {
+        if constexpr (OP == DAB_ADD) return jl::add(a, b);
+        else if constexpr (OP == DAB_SUB) return jl::sub(a, b);
+        else if constexpr (OP == DAB_MUL) return jl::mul(a, b);
+        else if constexpr (OP == DAB_REM) return jl::rem(a, b);
+        else if constexpr (OP == DAB_MOD) return jl::mod(a, b);
+        else if constexpr (OP == DAB_BMAX) return jl::max(a, b);
+        else if constexpr (OP == DAB_BMIN) return jl::min(a, b);
+        else if constexpr (std::is_floating_point<T>::value) {
+            if constexpr (OP == DAB_DIV) return jl::div(a, b);
+            else return a;
+        } else {
+            if constexpr (OP == DAB_IDIV) return jl::idiv(a, b);
+            else if constexpr (OP == DAB_AND) return a & b;
+            else if constexpr (OP == DAB_OR) return a | b;
+            else if constexpr (OP == DAB_XOR) return a ^ b;
+            else return a;
+        }
+    }
+};
+
+template <typename T, int OP, bool LEFT>
+struct BinScalarF {
+    T s;
+    __device__ __forceinline__ T operator()(T x) const { return LEFT ? BinOp<T, OP>()(s, x) : BinOp<T, OP>()(x, s); }
+};
+
+template <typename T>
+constexpr bool op_ok(int op) {
+    if (std::is_floating_point<T>::value) return op == DAB_ADD || op == DAB_SUB || op == DAB_MUL || op == DAB_DIV || op == DAB_REM ||
+                                                 op == DAB_BMAX || op == DAB_BMIN || op == DAB_MOD;
+    return op == DAB_ADD || op == DAB_SUB || op == DAB_MUL || op == DAB_REM || op == DAB_BMAX || op == DAB_BMIN || op == DAB_MOD ||
+           op == DAB_IDIV || op == DAB_AND || op == DAB_OR || op == DAB_XOR;
+}
+
+template <typename T>
+int32_t unary_t(dab_ctx* ctx, int32_t fn, T* y, const T* x, size_t n) {
+    switch (fn) {
+#define C(FN) \
+    case FN: return launch_ew1(ctx, y, x, n, UnaryF<T, FN>())
+        C(DAB_MAP_ID);
+        C(DAB_MAP_ABS);
+        C(DAB_MAP_ABS2);
+        C(DAB_MAP_NEG);
+        C(DAB_MAP_SIGN);
+        C(DAB_MAP_FLOOR);
+        C(DAB_MAP_CEIL);
+#undef C
+        case DAB_MAP_SQRT:
+            if (std::is_floating_point<T>::value) return launch_ew1(ctx, y, x, n, UnaryF<T, DAB_MAP_SQRT>());
+            break;
+        case DAB_MAP_INV:
+            if (std::is_floating_point<T>::value) return launch_ew1(ctx, y, x, n, UnaryF<T, DAB_MAP_INV>());
+            break;
+        default: break;
+    }
+    return dab_fail(ctx, DAB_ERR_UNSUPPORTED, "dab_unary: fn %d not served for this dtype (no host fallback)", fn);
+}
+
+template <typename T, int OP>
+int32_t binary_dispatch(dab_ctx* ctx, T* z, const T* x, const T* y, const T* s, int mode, size_t n) {
+    if (mode == 0) return launch_ew2(ctx, z, x, y, n, BinOp<T, OP>());
+    if (mode == 1) return launch_ew1(ctx, z, x, n, BinScalarF<T, OP, false>{*s});
+    return launch_ew1(ctx, z, x, n, BinScalarF<T, OP, true>{*s});
+}
+
+template <typename T>
+int32_t binary_t(dab_ctx* ctx, int32_t op, T* z, const T* x, const T* y, const T* s, int mode, size_t n) {
+    if (!op_ok<T>(op)) return dab_fail(ctx, DAB_ERR_UNSUPPORTED, "binary op %d not served for this dtype (no host fallback)", op);
+    switch (op) {
+#define C(OP) \
+    case OP: return binary_dispatch<T, OP>(ctx, z, x, y, s, mode, n)
+        C(DAB_ADD);
+        C(DAB_SUB);
+        C(DAB_MUL);
+        C(DAB_DIV);
+        C(DAB_REM);
+        C(DAB_BMAX);
+        C(DAB_BMIN);
+        C(DAB_MOD);
+        C(DAB_IDIV);
+        C(DAB_AND);
+        C(DAB_OR);
+        C(DAB_XOR);
+#undef C
+        default: return dab_fail(ctx, DAB_ERR_ARG, "bad binary op %d", op);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t dab_affine(dab_ctx* ctx, int32_t dtype, void* y, const void* x, const void* a, const void* b, size_t n) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, ((x && y) || n == 0) && a && b, DAB_ERR_ARG, "dab_affine: null pointer");
+    switch (dtype) {
+        case DAB_F32: return launch_ew1(ctx, (float*)y, (const float*)x, n, AffineF<float>{*(const float*)a, *(const float*)b});
+        case DAB_F64: return launch_ew1(ctx, (double*)y, (const double*)x, n, AffineF<double>{*(const double*)a, *(const double*)b});
+        case DAB_I32: return launch_ew1(ctx, (int32_t*)y, (const int32_t*)x, n, AffineF<int32_t>{*(const int32_t*)a, *(const int32_t*)b});
+        case DAB_I64:
+            return launch_ew1(ctx, (long long*)y, (const long long*)x, n, AffineF<long long>{*(const long long*)a, *(const long long*)b});
+        default: return dab_fail(ctx, DAB_ERR_ARG, "dab_affine: bad dtype %d", dtype);
+    }
+}
+
+int32_t dab_unary(dab_ctx* ctx, int32_t dtype, int32_t fn, void* y, const void* x, size_t n) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, (x && y) || n == 0, DAB_ERR_ARG, "dab_unary: null pointer");
+    switch (dtype) {
+        case DAB_F32: return unary_t(ctx, fn, (float*)y, (const float*)x, n);
+        case DAB_F64: return unary_t(ctx, fn, (double*)y, (const double*)x, n);
+        case DAB_I32: return unary_t(ctx, fn, (int32_t*)y, (const int32_t*)x, n);
+        case DAB_I64: return unary_t(ctx, fn, (long long*)y, (const long long*)x, n);
+        default: return dab_fail(ctx, DAB_ERR_ARG, "dab_unary: bad dtype %d", dtype);
+    }
+}
+
+int32_t dab_binary(dab_ctx* ctx, int32_t dtype, int32_t op, void* z, const void* x, const void* y, size_t n) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, (x && y && z) || n == 0, DAB_ERR_ARG, "dab_binary: null pointer");
+    switch (dtype) {
+        case DAB_F32: return binary_t<float>(ctx, op, (float*)z, (const float*)x, (const float*)y, nullptr, 0, n);
+        case DAB_F64: return binary_t<double>(ctx, op, (double*)z, (const double*)x, (const double*)y, nullptr, 0, n);
+        case DAB_I32: return binary_t<int32_t>(ctx, op, (int32_t*)z, (const int32_t*)x, (const int32_t*)y, nullptr, 0, n);
+        case DAB_I64: return binary_t<long long>(ctx, op, (long long*)z, (const long long*)x, (const long long*)y, nullptr, 0, n);
+        default: return dab_fail(ctx, DAB_ERR_ARG, "dab_binary: bad dtype %d", dtype);
+    }
+}
+
+int32_t dab_binary_scalar(dab_ctx* ctx, int32_t dtype, int32_t op, void* z, const void* x, const void* s, int32_t scalar_left,
+                          size_t n) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, ((x && z) || n == 0) && s, DAB_ERR_ARG, "dab_binary_scalar: null pointer");
+    int mode = scalar_left ? 2 : 1;
+    switch (dtype) {
+        case DAB_F32: return binary_t<float>(ctx, op, (float*)z, (const float*)x, nullptr, (const float*)s, mode, n);
+        case DAB_F64: return binary_t<double>(ctx, op, (double*)z, (const double*)x, nullptr, (const double*)s, mode, n);
+        case DAB_I32: return binary_t<int32_t>(ctx, op, (int32_t*)z, (const int32_t*)x, nullptr, (const int32_t*)s, mode, n);
+        case DAB_I64: return binary_t<long long>(ctx, op, (long long*)z, (const long long*)x, nullptr, (const long long*)s, mode, n);
+        default: return dab_fail(ctx, DAB_ERR_ARG, "dab_binary_scalar: bad dtype %d", dtype);
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,454 @@
+// dab_jit.cu -- general fused broadcast: ONE kernel per localpart for an arbitrary expression tree, compiled at run time.
+//
+// Replaces what Julia's JIT does for  copyto!(localpart(dest), lbc::Broadcasted)  (reference src/broadcast.jl:80) and
+// copy(lbc) (:96): the whole tree  f.(args...)  is fused into a single pass over the chunk -- N-ary, nested, with size-1
+// ("extruded", src/broadcast.jl:112-113) dims and mixed element types.  The host runtime (distributedarrays.jl_b200/
+// _broadcast.py) traces the user's function into C source for ONE element (Julia promotion already applied); this file
+// wraps it into two sm_100a kernels with NVRTC (-fmad=false: no FMA contraction, Julia semantics):
+//   dab_bc_linear  : every array argument is dense and has the destination's shape -> 4 consecutive elements per thread,
+//                    16/32-byte vector loads and stores, grid-stride (HBM roofline: sum of element sizes per element);
+//   dab_bc_general : per-argument strides (0 = extruded dim), coalesced along dim 0.
+// Kernels are cached per (device, expression, element types, argument kinds).  NVRTC and the driver entry points are
+// resolved at run time (dlopen / cudaGetDriverEntryPoint), so libdab200.so loads on a machine without a GPU.
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "dab_common.cuh"
+
+namespace {
+
+const char* kPrelude = R"PRELUDE(
+typedef unsigned long long u64;
+typedef long long i64;
+#define DEV __device__ __forceinline__
+// ---- Julia scalar semantics: one IEEE rounding per operation, never contracted ----
+DEV float jl_add(float a, float b) { return __fadd_rn(a, b); }
+DEV float jl_sub(float a, float b) { return __fsub_rn(a, b); }
+DEV float jl_mul(float a, float b) { return __fmul_rn(a, b); }
+DEV float jl_div(float a, float b) { return __fdiv_rn(a, b); }
+DEV double jl_add(double a, double b) { return __dadd_rn(a, b); }
+DEV double jl_sub(double a, double b) { return __dsub_rn(a, b); }
+DEV double jl_mul(double a, double b) { return __dmul_rn(a, b); }
+DEV double jl_div(double a, double b) { return __ddiv_rn(a, b); }
+DEV int jl_add(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
+DEV int jl_sub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
+DEV int jl_mul(int a, int b) { return (int)((unsigned)a * (unsigned)b); }
+DEV i64 jl_add(i64 a, i64 b) { return (i64)((u64)a + (u64)b); }
+DEV i64 jl_sub(i64 a, i64 b) { return (i64)((u64)a - (u64)b); }
+DEV i64 jl_mul(i64 a, i64 b) { return (i64)((u64)a * (u64)b); }
+DEV float jl_max(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+DEV float jl_min(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+DEV double jl_max(double a, double b) {
+    if (a != a || b != b) return __longlong_as_double(0x7ff8000000000000ll);
+    if (a == b) return (__double_as_longlong(a) < 0) ? b : a;
+    return a > b ? a : b;
+}
+DEV double jl_min(double a, double b) {
+    if (a != a || b != b) return __longlong_as_double(0x7ff8000000000000ll);
+    if (a == b) return (__double_as_longlong(a) < 0) ? a : b;
+    return a < b ? a : b;
+}
+DEV int jl_max(int a, int b) { return a > b ? a : b; }
+DEV int jl_min(int a, int b) { return a < b ? a : b; }
+DEV i64 jl_max(i64 a, i64 b) { return a > b ? a : b; }
+DEV i64 jl_min(i64 a, i64 b) { return a < b ? a : b; }
+DEV bool jl_max(bool a, bool b) { return a || b; }
+DEV bool jl_min(bool a, bool b) { return a && b; }
+DEV float jl_rem(float a, float b) { return fmodf(a, b); }
+DEV double jl_rem(double a, double b) { return fmod(a, b); }
+DEV int jl_rem(int a, int b) { return (b == 0 || b == -1) ? 0 : a % b; }
+DEV i64 jl_rem(i64 a, i64 b) { return (b == 0 || b == -1) ? 0 : a % b; }
+DEV float jl_mod(float x, float y) { float r = fmodf(x, y); if (r == 0.f) return copysignf(r, y); return ((r > 0.f) != (y > 0.f)) ? __fadd_rn(r, y) : r; }
+DEV double jl_mod(double x, double y) { double r = fmod(x, y); if (r == 0.0) return copysign(r, y); return ((r > 0.0) != (y > 0.0)) ? __dadd_rn(r, y) : r; }
+DEV int jl_mod(int a, int b) { if (b == 0 || b == -1) return 0; int r = a % b; return (r != 0 && ((r < 0) != (b < 0))) ? r + b : r; }
+DEV i64 jl_mod(i64 a, i64 b) { if (b == 0 || b == -1) return 0; i64 r = a % b; return (r != 0 && ((r < 0) != (b < 0))) ? r + b : r; }
+DEV int jl_idiv(int a, int b) { if (b == 0) return 0; if (b == -1) return (int)(0u - (unsigned)a); return a / b; }
+DEV i64 jl_idiv(i64 a, i64 b) { if (b == 0) return 0; if (b == -1) return (i64)(0ull - (u64)a); return a / b; }
+DEV float jl_pow(float a, float b) { return powf(a, b); }
+DEV double jl_pow(double a, double b) { return pow(a, b); }
+DEV int jl_and(int a, int b) { return a & b; }
+DEV int jl_or(int a, int b) { return a | b; }
+DEV int jl_xor(int a, int b) { return a ^ b; }
+DEV i64 jl_and(i64 a, i64 b) { return a & b; }
+DEV i64 jl_or(i64 a, i64 b) { return a | b; }
+DEV i64 jl_xor(i64 a, i64 b) { return a ^ b; }
+DEV bool jl_and(bool a, bool b) { return a && b; }
+DEV bool jl_or(bool a, bool b) { return a || b; }
+DEV bool jl_xor(bool a, bool b) { return a != b; }
+template <typename T> DEV bool jl_lt(T a, T b) { return a < b; }
+template <typename T> DEV bool jl_le(T a, T b) { return a <= b; }
+template <typename T> DEV bool jl_gt(T a, T b) { return a > b; }
+template <typename T> DEV bool jl_ge(T a, T b) { return a >= b; }
+template <typename T> DEV bool jl_eq(T a, T b) { return a == b; }
+template <typename T> DEV bool jl_ne(T a, T b) { return a != b; }
+DEV float jl_neg(float a) { return -a; }
+DEV double jl_neg(double a) { return -a; }
+DEV int jl_neg(int a) { return (int)(0u - (unsigned)a); }
+DEV i64 jl_neg(i64 a) { return (i64)(0ull - (u64)a); }
+DEV float jl_abs(float a) { return fabsf(a); }
+DEV double jl_abs(double a) { return fabs(a); }
+DEV int jl_abs(int a) { return a < 0 ? (int)(0u - (unsigned)a) : a; }
+DEV i64 jl_abs(i64 a) { return a < 0 ? (i64)(0ull - (u64)a) : a; }
+template <typename T> DEV T jl_abs2(T a) { return jl_mul(a, a); }
+DEV float jl_sqrt(float a) { return __fsqrt_rn(a); }
+DEV double jl_sqrt(double a) { return __dsqrt_rn(a); }
+DEV float jl_inv(float a) { return __fdiv_rn(1.0f, a); }
+DEV double jl_inv(double a) { return __ddiv_rn(1.0, a); }
+DEV float jl_floor(float a) { return floorf(a); }
+DEV double jl_floor(double a) { return floor(a); }
+DEV float jl_ceil(float a) { return ceilf(a); }
+DEV double jl_ceil(double a) { return ceil(a); }
+template <typename T> DEV T jl_floor(T a) { return a; }
+template <typename T> DEV T jl_ceil(T a) { return a; }
+template <typename T> DEV T jl_sign(T a) { return a > (T)0 ? (T)1 : (a < (T)0 ? (T)(-1) : a); }
+template <typename T> DEV bool jl_isnan(T a) { return a != a; }
+template <typename T> DEV bool jl_isinf(T a) { return (a == a) && ((a - a) != (a - a)); }
+template <typename T> DEV bool jl_isfinite(T a) { return (a - a) == (a - a); }
+// transcendental functions: CUDA's libdevice (<= 1-2 ulp); NOT bit-identical to Julia's openlibm-derived kernels
+#define JL_F1(name, ff, fd) DEV float jl_##name(float a) { return ff(a); } DEV double jl_##name(double a) { return fd(a); }
+JL_F1(sin, sinf, sin) JL_F1(cos, cosf, cos) JL_F1(tan, tanf, tan) JL_F1(exp, expf, exp) JL_F1(exp2, exp2f, exp2)
+JL_F1(log, logf, log) JL_F1(log2, log2f, log2) JL_F1(log10, log10f, log10) JL_F1(tanh, tanhf, tanh) JL_F1(sinh, sinhf, sinh)
+JL_F1(cosh, coshf, cosh) JL_F1(atan, atanf, atan) JL_F1(asin, asinf, asin) JL_F1(acos, acosf, acos) JL_F1(expm1, expm1f, expm1)
+JL_F1(log1p, log1pf, log1p) JL_F1(cbrt, cbrtf, cbrt)
+
+struct BcParams {
+    void* out;
+    u64 shape[4];
+    i64 ostr[4];
+    const void* ptr[8];
+    i64 str[8][4];
+    u64 scalar[8];
+};
+template <typename T, int N> struct __align__(sizeof(T) * N) VecN { T v[N]; };
+template <typename T> DEV T bits_as(u64 b) { T r; memcpy(&r, &b, sizeof(T)); return r; }
+)PRELUDE";
+
+const char* ctype_of(int32_t dt) {
+    switch (dt) {
+        case DAB_F32: return "float";
+        case DAB_F64: return "double";
+        case DAB_I32: return "int";
+        case DAB_I64: return "long long";
+        case DAB_U8: return "bool";
+        default: return nullptr;
+    }
+}
+
+struct BcParamsHost {
+    void* out;
+    unsigned long long shape[4];
+    long long ostr[4];
+    const void* ptr[8];
+    long long str[8][4];
+    unsigned long long scalar[8];
+};
+
+struct Nvrtc {
+    void* h = nullptr;
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    const char* (*GetErrorString)(nvrtcResult) = nullptr;
+    bool ok = false;
+    char why[256] = "";
+};
+
+Nvrtc& nvrtc() {
+    static Nvrtc api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", nullptr};
+    for (int i = 0; names[i] && !api.h; ++i) api.h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!api.h) {
+        snprintf(api.why, sizeof(api.why), "dlopen(libnvrtc.so.12) failed: %s", dlerror());
+        return api;
+    }
+#define SYM(f, n)                                                                  \
+    do {                                                                           \
+        *(void**)(&api.f) = dlsym(api.h, n);                                       \
+        if (!api.f) {                                                              \
+            snprintf(api.why, sizeof(api.why), "libnvrtc lacks symbol %s", n);     \
+            return api;                                                            \
+        }                                                                          \
+    } while (0)
+    SYM(CreateProgram, "nvrtcCreateProgram");
+    SYM(CompileProgram, "nvrtcCompileProgram");
+    SYM(GetCUBINSize, "nvrtcGetCUBINSize");
+    SYM(GetCUBIN, "nvrtcGetCUBIN");
+    SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+    SYM(GetProgramLog, "nvrtcGetProgramLog");
+    SYM(DestroyProgram, "nvrtcDestroyProgram");
+    SYM(GetErrorString, "nvrtcGetErrorString");
+#undef SYM
+    api.ok = true;
+    return api;
+}
+
+struct Driver {
+    CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+    CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    bool ok = false;
+    char why[256] = "";
+};
+
+Driver& driver() {
+    static Driver d;
+    static bool tried = false;
+    if (tried) return d;
+    tried = true;
+#define ENTRY(f, n)                                                                                       \
+    do {                                                                                                  \
+        cudaDriverEntryPointQueryResult qr;                                                               \
+        if (cudaGetDriverEntryPoint(n, (void**)&d.f, cudaEnableDefault, &qr) != cudaSuccess || !d.f) {    \
+            cudaGetLastError();                                                                           \
+            snprintf(d.why, sizeof(d.why), "driver entry point %s unavailable", n);                       \
+            return d;                                                                                     \
+        }                                                                                                 \
+    } while (0)
+    ENTRY(ModuleLoadData, "cuModuleLoadData");
+    ENTRY(ModuleGetFunction, "cuModuleGetFunction");
+    ENTRY(LaunchKernel, "cuLaunchKernel");
+    ENTRY(OccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+    ENTRY(GetErrorString, "cuGetErrorString");
+#undef ENTRY
+    d.ok = true;
+    return d;
+}
+
+struct Compiled {
+    CUfunction linear = nullptr, general = nullptr;
+    int occ_linear = 1, occ_general = 1;
+};
+
+std::mutex g_mu;
+std::unordered_map<std::string, Compiled> g_cache;
+
+std::string build_source(const char* expr, int32_t out_dt, int nargs, const int32_t* dts, const bool* is_arr) {
+    std::string s = kPrelude;
+    s += "typedef ";
+    s += ctype_of(out_dt);
+    s += " OUT_T;\n";
+    for (int k = 0; k < nargs; ++k) s += std::string("typedef ") + ctype_of(dts[k]) + " T" + std::to_string(k) + ";\n";
+    s += "#define DAB_EXPR (";
+    s += expr;
+    s += ")\n";
+    // ---- linear kernel
+    s += "extern \"C\" __global__ void __launch_bounds__(256) dab_bc_linear(BcParams p) {\n"
+         "  const u64 n = p.shape[0] * p.shape[1] * p.shape[2] * p.shape[3];\n"
+         "  const u64 nv = n / 4;\n"
+         "  OUT_T* o = (OUT_T*)p.out;\n";
+    for (int k = 0; k < nargs; ++k) {
+        std::string K = std::to_string(k);
+        if (is_arr[k]) s += "  const T" + K + "* q" + K + " = (const T" + K + "*)p.ptr[" + K + "];\n";
+        else s += "  const T" + K + " a" + K + " = bits_as<T" + K + ">(p.scalar[" + K + "]);\n";
+    }
+    s += "  const u64 stride = (u64)gridDim.x * blockDim.x;\n"
+         "  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {\n";
+    for (int k = 0; k < nargs; ++k)
+        if (is_arr[k]) {
+            std::string K = std::to_string(k);
+            s += "    const VecN<T" + K + ", 4> v" + K + " = *(const VecN<T" + K + ", 4>*)(q" + K + " + 4 * i);\n";
+        }
+    s += "    VecN<OUT_T, 4> r;\n"
+         "#pragma unroll\n"
+         "    for (int j = 0; j < 4; ++j) {\n";
+    for (int k = 0; k < nargs; ++k)
+        if (is_arr[k]) {
+            std::string K = std::to_string(k);
+            s += "      const T" + K + " a" + K + " = v" + K + ".v[j];\n";
+        }
+    s += "      r.v[j] = (OUT_T)DAB_EXPR;\n"
+         "    }\n"
+         "    *(VecN<OUT_T, 4>*)(o + 4 * i) = r;\n"
+         "  }\n"
+         "  if (blockIdx.x == gridDim.x - 1) {\n"
+         "    for (u64 i = nv * 4 + threadIdx.x; i < n; i += blockDim.x) {\n";
+    for (int k = 0; k < nargs; ++k)
+        if (is_arr[k]) {
+            std::string K = std::to_string(k);
+            s += "      const T" + K + " a" + K + " = q" + K + "[i];\n";
+        }
+    s += "      o[i] = (OUT_T)DAB_EXPR;\n"
+         "    }\n"
+         "  }\n"
+         "}\n";
+    // ---- general (strided / extruded) kernel
+    s += "extern \"C\" __global__ void __launch_bounds__(256) dab_bc_general(BcParams p) {\n"
+         "  const u64 n0 = p.shape[0], n1 = p.shape[1], n2 = p.shape[2];\n"
+         "  const u64 n = n0 * n1 * n2 * p.shape[3];\n"
+         "  OUT_T* o = (OUT_T*)p.out;\n";
+    for (int k = 0; k < nargs; ++k) {
+        std::string K = std::to_string(k);
+        if (is_arr[k]) s += "  const T" + K + "* q" + K + " = (const T" + K + "*)p.ptr[" + K + "];\n";
+        else s += "  const T" + K + " a" + K + " = bits_as<T" + K + ">(p.scalar[" + K + "]);\n";
+    }
+    s += "  const u64 stride = (u64)gridDim.x * blockDim.x;\n"
+         "  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {\n"
+         "    const u64 i0 = i % n0, t0 = i / n0, i1 = t0 % n1, t1 = t0 / n1, i2 = t1 % n2, i3 = t1 / n2;\n";
+    for (int k = 0; k < nargs; ++k)
+        if (is_arr[k]) {
+            std::string K = std::to_string(k);
+            s += "    const T" + K + " a" + K + " = q" + K + "[(i64)i0 * p.str[" + K + "][0] + (i64)i1 * p.str[" + K + "][1] + (i64)i2 * p.str[" + K +
+                 "][2] + (i64)i3 * p.str[" + K + "][3]];\n";
+        }
+    s += "    o[(i64)i0 * p.ostr[0] + (i64)i1 * p.ostr[1] + (i64)i2 * p.ostr[2] + (i64)i3 * p.ostr[3]] = (OUT_T)DAB_EXPR;\n"
+         "  }\n"
+         "}\n";
+    return s;
+}
+
+int32_t compile_cubin(dab_ctx* ctx, const std::string& src, std::vector<char>* cubin_out) {
+    Nvrtc& rt = nvrtc();
+    if (!rt.ok) return dab_fail(ctx, DAB_ERR_NVRTC, "NVRTC unavailable: %s", rt.why);
+    nvrtcProgram prog;
+    nvrtcResult r = rt.CreateProgram(&prog, src.c_str(), "dab_broadcast.cu", 0, nullptr, nullptr);
+    if (r != NVRTC_SUCCESS) return dab_fail(ctx, DAB_ERR_NVRTC, "nvrtcCreateProgram: %s", rt.GetErrorString(r));
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-fmad=false", "--std=c++17", "-lineinfo", "-default-device"};
+    r = rt.CompileProgram(prog, 5, opts);
+    if (r != NVRTC_SUCCESS) {
+        size_t ls = 0;
+        rt.GetProgramLogSize(prog, &ls);
+        std::string log(ls + 1, '\0');
+        if (ls) rt.GetProgramLog(prog, &log[0]);
+        rt.DestroyProgram(&prog);
+        if (log.size() > 400) log.resize(400);
+        return dab_fail(ctx, DAB_ERR_NVRTC, "NVRTC compile failed (%s): %s", rt.GetErrorString(r), log.c_str());
+    }
+    size_t cs = 0;
+    rt.GetCUBINSize(prog, &cs);
+    cubin_out->resize(cs);
+    rt.GetCUBIN(prog, cubin_out->data());
+    rt.DestroyProgram(&prog);
+    return DAB_OK;
+}
+
+int32_t compile(dab_ctx* ctx, const std::string& src, Compiled* out) {
+    Driver& drv = driver();
+    if (!drv.ok) return dab_fail(ctx, DAB_ERR_NVRTC, "CUDA driver API unavailable: %s", drv.why);
+    std::vector<char> cubin;
+    int32_t st = compile_cubin(ctx, src, &cubin);
+    if (st != DAB_OK) return st;
+    CUmodule mod;
+    CUresult cr = drv.ModuleLoadData(&mod, cubin.data());
+    if (cr != CUDA_SUCCESS) {
+        const char* es = "?";
+        drv.GetErrorString(cr, &es);
+        return dab_fail(ctx, DAB_ERR_NVRTC, "cuModuleLoadData failed: %s", es);
+    }
+    if (drv.ModuleGetFunction(&out->linear, mod, "dab_bc_linear") != CUDA_SUCCESS ||
+        drv.ModuleGetFunction(&out->general, mod, "dab_bc_general") != CUDA_SUCCESS)
+        return dab_fail(ctx, DAB_ERR_NVRTC, "cuModuleGetFunction failed");
+    if (drv.OccupancyMaxActiveBlocksPerMultiprocessor(&out->occ_linear, out->linear, 256, 0) != CUDA_SUCCESS || out->occ_linear < 1)
+        out->occ_linear = 1;
+    if (drv.OccupancyMaxActiveBlocksPerMultiprocessor(&out->occ_general, out->general, 256, 0) != CUDA_SUCCESS || out->occ_general < 1)
+        out->occ_general = 1;
+    return DAB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Diagnostic (no GPU needed): run the same source generation + NVRTC compilation as dab_broadcast_expr and report the size
+// of the sm_100a cubin.  Lets the host-side tests validate the tracer's code generation on a CPU-only machine.
+int32_t dab_jit_compile_check(const char* expr, int32_t out_dtype, int32_t nargs, const int32_t* arg_dtypes,
+                              const int32_t* arg_is_array, size_t* cubin_bytes) {
+    if (!expr || !ctype_of(out_dtype) || nargs < 0 || nargs > 8 || (nargs && (!arg_dtypes || !arg_is_array)))
+        return dab_fail(nullptr, DAB_ERR_ARG, "dab_jit_compile_check: bad argument");
+    bool is_arr[8] = {false};
+    for (int k = 0; k < nargs; ++k) {
+        if (!ctype_of(arg_dtypes[k])) return dab_fail(nullptr, DAB_ERR_ARG, "dab_jit_compile_check: bad dtype of arg %d", k);
+        is_arr[k] = arg_is_array[k] != 0;
+    }
+    std::vector<char> cubin;
+    int32_t st = compile_cubin(nullptr, build_source(expr, out_dtype, nargs, arg_dtypes, is_arr), &cubin);
+    if (st != DAB_OK) return st;
+    if (cubin_bytes) *cubin_bytes = cubin.size();
+    return DAB_OK;
+}
+
+int32_t dab_broadcast_expr(dab_ctx* ctx, const char* expr, int32_t out_dtype, void* out, const size_t shape[4],
+                           const size_t out_strides[4], int32_t nargs, const int32_t* arg_dtypes, const void* const* arg_ptrs,
+                           const size_t* arg_strides, const uint64_t* arg_scalars) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, expr && out && shape && out_strides, DAB_ERR_ARG, "dab_broadcast_expr: null pointer");
+    DAB_REQUIRE(ctx, nargs >= 0 && nargs <= 8, DAB_ERR_ARG, "dab_broadcast_expr: nargs %d (max 8)", nargs);
+    DAB_REQUIRE(ctx, ctype_of(out_dtype), DAB_ERR_ARG, "dab_broadcast_expr: bad out dtype %d", out_dtype);
+    DAB_REQUIRE(ctx, nargs == 0 || (arg_dtypes && arg_ptrs && arg_strides && arg_scalars), DAB_ERR_ARG, "dab_broadcast_expr: null arg table");
+    size_t n = shape[0] * shape[1] * shape[2] * shape[3];
+    if (n == 0) return DAB_OK;
+    bool is_arr[8] = {false};
+    std::string key = std::to_string(ctx->device) + "|" + std::to_string(out_dtype) + "|";
+    for (int k = 0; k < nargs; ++k) {
+        DAB_REQUIRE(ctx, ctype_of(arg_dtypes[k]), DAB_ERR_ARG, "dab_broadcast_expr: bad dtype of arg %d", k);
+        is_arr[k] = arg_ptrs[k] != nullptr;
+        key += std::to_string(arg_dtypes[k]) + (is_arr[k] ? "a" : "s");
+    }
+    key += "|";
+    key += expr;
+    Compiled comp;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_cache.find(key);
+        if (it == g_cache.end()) {
+            DAB_CUDA(ctx, cudaFree(0));  // make sure the primary context is current for the driver calls
+            int32_t st = compile(ctx, build_source(expr, out_dtype, nargs, arg_dtypes, is_arr), &comp);
+            if (st != DAB_OK) return st;
+            g_cache[key] = comp;
+        } else {
+            comp = it->second;
+        }
+    }
+    BcParamsHost p;
+    memset(&p, 0, sizeof(p));
+    p.out = out;
+    size_t dense[4], acc = 1;
+    for (int d = 0; d < 4; ++d) {
+        p.shape[d] = shape[d];
+        p.ostr[d] = (long long)out_strides[d];
+        dense[d] = acc;
+        acc *= shape[d];
+    }
+    bool linear = true;
+    for (int d = 0; d < 4; ++d)
+        if (shape[d] > 1 && out_strides[d] != dense[d]) linear = false;
+    if ((uintptr_t)out % (4 * dab_dtype_size(out_dtype))) linear = false;
+    for (int k = 0; k < nargs; ++k) {
+        p.ptr[k] = arg_ptrs[k];
+        p.scalar[k] = arg_scalars[k];
+        for (int d = 0; d < 4; ++d) {
+            p.str[k][d] = (long long)arg_strides[4 * k + d];
+            if (is_arr[k] && shape[d] > 1 && arg_strides[4 * k + d] != dense[d]) linear = false;
+        }
+        if (is_arr[k] && ((uintptr_t)arg_ptrs[k] % (4 * dab_dtype_size(arg_dtypes[k])))) linear = false;
+    }
+    Driver& drv = driver();
+    void* args[] = {&p};
+    CUfunction fn = linear ? comp.linear : comp.general;
+    size_t work = linear ? (n / 4 + 255) / 256 : (n + 255) / 256;
+    int grid = dab_grid_for(ctx, work, linear ? comp.occ_linear : comp.occ_general);
+    CUresult cr = drv.LaunchKernel(fn, (unsigned)grid, 1, 1, 256, 1, 1, 0, (CUstream)ctx->stream, args, nullptr);
+    if (cr != CUDA_SUCCESS) {
+        const char* es = "?";
+        drv.GetErrorString(cr, &es);
+        return dab_fail(ctx, DAB_ERR_CUDA, "cuLaunchKernel failed: %s", es);
+    }
+    ctx->launches++;
+    return DAB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,316 @@
+// dab_reducedim.cu -- K5 / K6: mapreduce(f, op, localpart(A), dims=region) as streaming sm_100a kernels.
+//
+// Replaces the per-worker Base.mapreducedim! at reference src/mapreduce.jl:64 (phase 1, mapreducedim_within) and :77
+// (phase 2, accumulation of the gathered partials onto localpart(R) in mapreducedim_between!).
+//
+// The chunk is collapsed to the column-major shape (inner, reduce, outer):  out[i + inner*o] = op_r f(x[i + inner*(r + reduce*o)]).
+// Roofline: HBM, sizeof(T) bytes read per element + one output element per (i, o).
+//   * inner == 1  ("leading dims", e.g. sum(A, dims=1)): every output is a CONTIGUOUS run of `reduce` elements.
+//       - long runs : one CTA per (run, split); 16-byte evict-first loads, 4 in flight per thread, per-run head/tail peel
+//         (run starts are not 16-byte aligned when reduce % (16/sizeof T) != 0); runs are split across CTAs when there are too
+//         few of them to fill 148 SMs, and a tiny second kernel folds the splits in order (deterministic, no atomics).
+//       - short runs: one warp per run, lanes strided (coalesced 128 B per warp load).
+//   * inner  > 1  (reduce over a non-leading dim): threads map along i (coalesced), each walks r with 8 independent loads in
+//     flight; r is split across CTAs when inner*outer alone cannot fill the machine, then folded in order.
+// Accumulators are wide (fp64 / int64) exactly as in dab_reduce.cu; float results are rounded once at the end.
+#include "dab_reduce_traits.cuh"
+
+namespace {
+
+template <typename A, typename Out>
+__device__ __forceinline__ Out narrow(A a) {
+    return (Out)a;
+}
+
+// ---- leading-dims, long runs: one CTA per (run, split) -----------------------------------------------------------------
+template <typename T, typename Map, typename R, typename Out>
+__global__ void __launch_bounds__(RD_THREADS) rdim_lead_cta_kernel(const T* __restrict__ x, size_t red, size_t outer, int nsplit,
+                                                                    Map map, typename R::A* __restrict__ partials,
+                                                                    Out* __restrict__ out, int accumulate) {
+    using A = typename R::A;
+    using V = typename Map::V;
+    constexpr int VPT = 16 / sizeof(T);
+    constexpr int UNROLL = 4;
+    __shared__ A smem[RD_THREADS / 32];
+    const size_t work = outer * (size_t)nsplit;
+    const size_t split_len = (red + nsplit - 1) / nsplit;
+    for (size_t w = blockIdx.x; w < work; w += gridDim.x) {
+        const size_t seg = w / nsplit;
+        const size_t sp = w % nsplit;
+        size_t lo = sp * split_len, hi = lo + split_len;
+        if (hi > red) hi = red;
+        A acc = R::identity();
+        if (lo < hi) {
+            const T* p = x + seg * red + lo;
+            const size_t n = hi - lo;
+            size_t head = ((16 - ((uintptr_t)p & 15)) & 15) / sizeof(T);
+            if (head > n) head = n;
+            const size_t nvec = (n - head) / VPT;
+            const int4* pv = reinterpret_cast<const int4*>(p + head);
+            size_t i = threadIdx.x;
+            for (; i + (size_t)(UNROLL - 1) * RD_THREADS < nvec; i += (size_t)UNROLL * RD_THREADS) {
+                int4 r[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) r[u] = ld_stream(pv + i + (size_t)u * RD_THREADS);
+                V tv[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    Pack<T> pk = as_pack<T>(r[u]);
+                    V m[VPT];
+#pragma unroll
+                    for (int k = 0; k < VPT; ++k) m[k] = map(pk.v[k]);
+#pragma unroll
+                    for (int ww = VPT; ww > 1; ww >>= 1)
+#pragma unroll
+                        for (int k = 0; k < ww / 2; ++k) m[k] = R::tile(m[k], m[k + ww / 2]);
+                    tv[u] = m[0];
+                }
+#pragma unroll
+                for (int ww = UNROLL; ww > 1; ww >>= 1)
+#pragma unroll
+                    for (int k = 0; k < ww / 2; ++k) tv[k] = R::tile(tv[k], tv[k + ww / 2]);
+                acc = R::comb(acc, R::lift(tv[0]));
+            }
+            for (; i < nvec; i += RD_THREADS) {
+                Pack<T> pk = as_pack<T>(ld_stream(pv + i));
+                V m = map(pk.v[0]);
+#pragma unroll
+                for (int k = 1; k < VPT; ++k) m = R::tile(m, map(pk.v[k]));
+                acc = R::comb(acc, R::lift(m));
+            }
+            for (size_t j = threadIdx.x; j < head; j += RD_THREADS) acc = R::comb(acc, R::lift(map(p[j])));
+            for (size_t j = head + nvec * VPT + threadIdx.x; j < n; j += RD_THREADS) acc = R::comb(acc, R::lift(map(p[j])));
+        }
+        acc = block_reduce<R>(acc, smem);
+        if (threadIdx.x == 0) {
+            if (nsplit == 1) {
+                if (accumulate) acc = R::comb((A)out[seg], acc);
+                out[seg] = narrow<A, Out>(acc);
+            } else {
+                partials[seg * nsplit + sp] = acc;
+            }
+        }
+    }
+}
+
+// ---- leading-dims, short runs: one warp per run ----------------------------------------------------------------------------
+template <typename T, typename Map, typename R, typename Out>
+__global__ void __launch_bounds__(RD_THREADS) rdim_lead_warp_kernel(const T* __restrict__ x, size_t red, size_t outer, Map map,
+                                                                     Out* __restrict__ out, int accumulate) {
+    using A = typename R::A;
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * RD_THREADS + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * RD_THREADS) >> 5;
+    for (size_t seg = warp; seg < outer; seg += nwarps) {
+        const T* p = x + seg * red;
+        A acc = R::identity();
+        size_t j = lane;
+        for (; j + 96 < red; j += 128) {  // 4 independent loads in flight
+            T a0 = p[j], a1 = p[j + 32], a2 = p[j + 64], a3 = p[j + 96];
+            auto t = R::tile(R::tile(map(a0), map(a1)), R::tile(map(a2), map(a3)));
+            acc = R::comb(acc, R::lift(t));
+        }
+        for (; j < red; j += 32) acc = R::comb(acc, R::lift(map(p[j])));
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc = R::comb(acc, shfl_down<A>(acc, d));
+        if (lane == 0) {
+            if (accumulate) acc = R::comb((A)out[seg], acc);
+            out[seg] = narrow<A, Out>(acc);
+        }
+    }
+}
+
+// ---- non-leading dim: threads along i, loop over r --------------------------------------------------------------------------
+template <typename T, typename Map, typename R, typename Out>
+__global__ void __launch_bounds__(RD_THREADS) rdim_strided_kernel(const T* __restrict__ x, size_t inner, size_t red, size_t outer,
+                                                                   int nsplit, Map map, typename R::A* __restrict__ partials,
+                                                                   Out* __restrict__ out, int accumulate) {
+    using A = typename R::A;
+    constexpr int UNROLL = 8;
+    const size_t iblocks = (inner + RD_THREADS - 1) / RD_THREADS;
+    const size_t work = iblocks * outer * (size_t)nsplit;
+    const size_t split_len = (red + nsplit - 1) / nsplit;
+    for (size_t w = blockIdx.x; w < work; w += gridDim.x) {
+        const size_t ib = w % iblocks;
+        const size_t rest = w / iblocks;
+        const size_t sp = rest % nsplit;
+        const size_t o = rest / nsplit;
+        const size_t i = ib * RD_THREADS + threadIdx.x;
+        if (i >= inner) continue;
+        size_t lo = sp * split_len, hi = lo + split_len;
+        if (hi > red) hi = red;
+        const T* p = x + i + inner * (o * red);
+        A acc = R::identity();
+        size_t r = lo;
+        for (; r + UNROLL <= hi; r += UNROLL) {
+            T v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) v[u] = __ldcs(p + (r + u) * inner);
+            typename Map::V m[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) m[u] = map(v[u]);
+#pragma unroll
+            for (int ww = UNROLL; ww > 1; ww >>= 1)
+#pragma unroll
+                for (int k = 0; k < ww / 2; ++k) m[k] = R::tile(m[k], m[k + ww / 2]);
+            acc = R::comb(acc, R::lift(m[0]));
+        }
+        for (; r < hi; ++r) acc = R::comb(acc, R::lift(map(__ldcs(p + r * inner))));
+        if (nsplit == 1) {
+            const size_t oi = i + inner * o;
+            if (accumulate) acc = R::comb((A)out[oi], acc);
+            out[oi] = narrow<A, Out>(acc);
+        } else {
+            partials[(sp * outer + o) * inner + i] = acc;
+        }
+    }
+}
+
+// ---- ordered fold of the split partials: thread per output -----------------------------------------------------------------
+template <typename R, typename Out>
+__global__ void __launch_bounds__(RD_THREADS) rdim_finish_kernel(const typename R::A* __restrict__ partials, size_t nout, int nsplit,
+                                                                  size_t stride_out, size_t stride_split, Out* __restrict__ out,
+                                                                  int accumulate) {
+    using A = typename R::A;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < nout; k += stride) {
+        A acc = accumulate ? (A)out[k] : R::identity();
+        for (int s = 0; s < nsplit; ++s) acc = R::comb(acc, partials[k * stride_out + (size_t)s * stride_split]);
+        out[k] = (Out)acc;
+    }
+}
+
+int32_t ensure_scratch(dab_ctx* ctx, size_t bytes) {
+    if (ctx->dim_scratch_bytes >= bytes) return DAB_OK;
+    if (ctx->dim_scratch) {
+        DAB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        DAB_CUDA(ctx, cudaFree(ctx->dim_scratch));
+        ctx->dim_scratch = nullptr;
+        ctx->dim_scratch_bytes = 0;
+    }
+    DAB_CUDA(ctx, cudaMalloc(&ctx->dim_scratch, bytes));
+    ctx->dim_scratch_bytes = bytes;
+    return DAB_OK;
+}
+
+template <typename T, typename Map, typename R, typename Out>
+int32_t launch_rdim(dab_ctx* ctx, const T* x, size_t inner, size_t red, size_t outer, Map map, Out* out, int accumulate) {
+    using A = typename R::A;
+    const size_t target_ctas = (size_t)ctx->sm_count * 8;
+    if (inner == 1) {
+        if (red < 2048 && outer >= (size_t)ctx->sm_count) {
+            size_t warps_needed = outer;
+            int grid = dab_persistent_grid(ctx, rdim_lead_warp_kernel<T, Map, R, Out>, RD_THREADS, (warps_needed + 7) / 8);
+            rdim_lead_warp_kernel<T, Map, R, Out><<<grid, RD_THREADS, 0, ctx->stream>>>(x, red, outer, map, out, accumulate);
+            DAB_LAUNCHED(ctx);
+            return DAB_OK;
+        }
+        // split long runs when there are too few of them; keep every split >= 16 KiB of input
+        size_t max_split = red * sizeof(T) / 16384;
+        if (max_split < 1) max_split = 1;
+        size_t want = outer >= target_ctas ? 1 : (target_ctas + outer - 1) / outer;
+        int nsplit = (int)(want < max_split ? want : max_split);
+        if (nsplit > 1024) nsplit = 1024;
+        A* partials = nullptr;
+        if (nsplit > 1) {
+            int32_t st = ensure_scratch(ctx, outer * (size_t)nsplit * sizeof(A));
+            if (st != DAB_OK) return st;
+            partials = (A*)ctx->dim_scratch;
+        }
+        int grid = dab_persistent_grid(ctx, rdim_lead_cta_kernel<T, Map, R, Out>, RD_THREADS, outer * (size_t)nsplit);
+        rdim_lead_cta_kernel<T, Map, R, Out><<<grid, RD_THREADS, 0, ctx->stream>>>(x, red, outer, nsplit, map, partials, out, accumulate);
+        DAB_LAUNCHED(ctx);
+        if (nsplit > 1) {
+            int g2 = dab_grid_for(ctx, (outer + RD_THREADS - 1) / RD_THREADS, 8);
+            rdim_finish_kernel<R, Out><<<g2, RD_THREADS, 0, ctx->stream>>>(partials, outer, nsplit, (size_t)nsplit, 1, out, accumulate);
+            DAB_LAUNCHED(ctx);
+        }
+        return DAB_OK;
+    }
+    const size_t iblocks = (inner + RD_THREADS - 1) / RD_THREADS;
+    size_t base_ctas = iblocks * outer;
+    size_t max_split = red / 64;
+    if (max_split < 1) max_split = 1;
+    size_t want = base_ctas >= target_ctas ? 1 : (target_ctas + base_ctas - 1) / base_ctas;
+    int nsplit = (int)(want < max_split ? want : max_split);
+    if (nsplit > 1024) nsplit = 1024;
+    A* partials = nullptr;
+    if (nsplit > 1) {
+        int32_t st = ensure_scratch(ctx, inner * outer * (size_t)nsplit * sizeof(A));
+        if (st != DAB_OK) return st;
+        partials = (A*)ctx->dim_scratch;
+    }
+    int grid = dab_persistent_grid(ctx, rdim_strided_kernel<T, Map, R, Out>, RD_THREADS, base_ctas * (size_t)nsplit);
+    rdim_strided_kernel<T, Map, R, Out><<<grid, RD_THREADS, 0, ctx->stream>>>(x, inner, red, outer, nsplit, map, partials, out, accumulate);
+    DAB_LAUNCHED(ctx);
+    if (nsplit > 1) {
+        size_t nout = inner * outer;
+        int g2 = dab_grid_for(ctx, (nout + RD_THREADS - 1) / RD_THREADS, 8);
+        rdim_finish_kernel<R, Out><<<g2, RD_THREADS, 0, ctx->stream>>>(partials, nout, nsplit, 1, nout, out, accumulate);
+        DAB_LAUNCHED(ctx);
+    }
+    return DAB_OK;
+}
+
+template <typename T>
+using ResultOfSum = typename std::conditional<std::is_floating_point<T>::value, T, long long>::type;
+
+template <typename T, int FN>
+int32_t rdim_map(dab_ctx* ctx, int32_t op, const T* x, size_t inner, size_t red, size_t outer, void* out, int accumulate) {
+    MapF<T, FN> map{(T)0};
+    switch (op) {
+        case DAB_SUM:
+            return launch_rdim<T, MapF<T, FN>, SumTraits<T>, ResultOfSum<T>>(ctx, x, inner, red, outer, map, (ResultOfSum<T>*)out, accumulate);
+        case DAB_PROD:
+            return launch_rdim<T, MapF<T, FN>, ProdTraits<T>, ResultOfSum<T>>(ctx, x, inner, red, outer, map, (ResultOfSum<T>*)out, accumulate);
+        case DAB_MAX: return launch_rdim<T, MapF<T, FN>, MaxTraits<T>, T>(ctx, x, inner, red, outer, map, (T*)out, accumulate);
+        case DAB_MIN: return launch_rdim<T, MapF<T, FN>, MinTraits<T>, T>(ctx, x, inner, red, outer, map, (T*)out, accumulate);
+        default: return dab_fail(ctx, DAB_ERR_UNSUPPORTED, "dab_reducedim: op %d not served (no host fallback)", op);
+    }
+}
+
+template <typename T>
+int32_t rdim_t(dab_ctx* ctx, int32_t op, int32_t map, const T* x, size_t inner, size_t red, size_t outer, void* out, int accumulate) {
+    switch (map) {
+        case DAB_MAP_ID: return rdim_map<T, DAB_MAP_ID>(ctx, op, x, inner, red, outer, out, accumulate);
+        case DAB_MAP_ABS: return rdim_map<T, DAB_MAP_ABS>(ctx, op, x, inner, red, outer, out, accumulate);
+        case DAB_MAP_ABS2: return rdim_map<T, DAB_MAP_ABS2>(ctx, op, x, inner, red, outer, out, accumulate);
+        case DAB_MAP_NEG: return rdim_map<T, DAB_MAP_NEG>(ctx, op, x, inner, red, outer, out, accumulate);
+        default: return dab_fail(ctx, DAB_ERR_UNSUPPORTED, "dab_reducedim: map %d not served (no host fallback)", map);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t dab_reducedim(dab_ctx* ctx, int32_t dtype, int32_t op, int32_t map, const void* x, size_t inner, size_t reduce, size_t outer,
+                      void* out, int32_t accumulate) {
+    DAB_ENTER(ctx);
+    const size_t nout = inner * outer;
+    if (nout == 0) return DAB_OK;
+    DAB_REQUIRE(ctx, out && (x || reduce == 0), DAB_ERR_ARG, "dab_reducedim: null pointer");
+    if (reduce == 0) {
+        // reducing over an empty dimension: SUM/PROD give the identity, MAX/MIN throw (Base semantics)
+        if (accumulate) return DAB_OK;
+        if (op != DAB_SUM && op != DAB_PROD) return dab_fail(ctx, DAB_ERR_EMPTY, "reducing over an empty collection is not allowed");
+        int32_t rdt;
+        dab_reduce_result_dtype(dtype, op, map, &rdt);
+        unsigned char v[8] = {0};
+        if (op == DAB_PROD) {
+            if (rdt == DAB_F32) { float o = 1.f; memcpy(v, &o, 4); }
+            else if (rdt == DAB_F64) { double o = 1.0; memcpy(v, &o, 8); }
+            else { long long o = 1; memcpy(v, &o, 8); }
+        }
+        return dab_fill(ctx, rdt, out, nout, v);
+    }
+    switch (dtype) {
+        case DAB_F32: return rdim_t<float>(ctx, op, map, (const float*)x, inner, reduce, outer, out, accumulate);
+        case DAB_F64: return rdim_t<double>(ctx, op, map, (const double*)x, inner, reduce, outer, out, accumulate);
+        case DAB_I32: return rdim_t<int32_t>(ctx, op, map, (const int32_t*)x, inner, reduce, outer, out, accumulate);
+        case DAB_I64: return rdim_t<long long>(ctx, op, map, (const long long*)x, inner, reduce, outer, out, accumulate);
+        default: return dab_fail(ctx, DAB_ERR_ARG, "dab_reducedim: bad dtype %d", dtype);
+    }
+}
+
+}  // extern "C"

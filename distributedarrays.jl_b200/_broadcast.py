@@ -61,6 +61,9 @@ class Expr:
     """Symbolic scalar.  ``op``: 'arg' | 'const' | unary name | binary name; ``jt``: Julia type tag of the value."""
 
     __slots__ = ("op", "args", "jt", "val", "weak")
+    # NumPy scalars must defer to our reflected operators (np.float32(1.5) * x has to stay a Float32 constant; without this
+    # NumPy would coerce itself to a Python float -- a Float64 literal in Julia terms -- before calling __rmul__).
+    __array_ufunc__ = None
 
     def __init__(self, op, args=(), jt="f64", val=None, weak=False):
         self.op, self.args, self.jt, self.val, self.weak = op, tuple(args), jt, val, weak
@@ -335,6 +338,7 @@ def run_local(rt, expr: Expr, out: B200Array, largs: List[LocalArg]):
     same = all(a.arr.shape == out.shape or a.arr.size == n and _squeeze(a.arr.shape) == _squeeze(out.shape) for a in full)
     ctx = rt.ctx
     code = dab_dtype(out.dtype)
+    rt.last_kernel = "fixed"
     # ---- hand-written kernels when the tree is one of the fixed shapes
     if same and expr.jt == out_tag and out_tag != "bool":
         x0 = largs[0] if largs and largs[0].arr is not None and largs[0].tag == out_tag else None
@@ -345,6 +349,7 @@ def run_local(rt, expr: Expr, out: B200Array, largs: List[LocalArg]):
                 b = np.asarray(ab[1], dtype=out.dtype)
                 _lib.call("dab_affine", ctx, code, C.c_void_p(out.ptr), C.c_void_p(x0.arr.ptr), C.c_void_p(a.ctypes.data),
                           C.c_void_p(b.ctypes.data), n)
+                rt.last_kernel = "dab_affine"
                 return
             if expr.op in _UN and _is_arg(expr.args[0], 0):
                 _lib.call("dab_unary", ctx, code, _UN[expr.op], C.c_void_p(out.ptr), C.c_void_p(x0.arr.ptr), n)
@@ -383,6 +388,7 @@ def run_local(rt, expr: Expr, out: B200Array, largs: List[LocalArg]):
         _lib.call("dab_fill", ctx, code, C.c_void_p(out.ptr), n, C.c_void_p(v.ctypes.data))
         return
     # ---- general fused kernel (NVRTC)
+    rt.last_kernel = "dab_broadcast_expr"
     src = codegen(convert(expr, out_tag)).encode()
     oshape = _pad4(out.shape)
     nargs = len(largs)

@@ -54,7 +54,7 @@ def classify_map(f: Optional[Callable], dtype) -> Tuple[Optional[int], Optional[
         code = {"abs": _lib.MAP_ABS, "abs2": _lib.MAP_ABS2, "neg": _lib.MAP_NEG}.get(e.op)
         if code is not None:
             return code, None, e
-    if e.op == "mul" and e.jt == tag and all(a.op == "arg" for a in e.args):  # x*x == abs2 for reals
+    if e.op == "mul" and e.jt == tag and builtins.all(a.op == "arg" for a in e.args):  # x*x == abs2 for reals
         return _lib.MAP_ABS2, None, e
     if e.op in _CMPMAP:
         l, r = e.args

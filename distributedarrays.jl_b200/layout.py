@@ -66,7 +66,8 @@ def chunk_idxs(dims: Sequence[int], grid: Sequence[int]):
     idx = []
     for lin in range(int(np.prod(grid)) if len(grid) else 1):
         c = unravel(lin, grid)
-        idx.append(tuple((cuts[k][c[k]], cuts[k][c[k] + 1] - 1) for k in range(len(dims))))
+        # Julia normalises an empty UnitRange a:b (b < a-1) to a:a-1
+        idx.append(tuple((cuts[k][c[k]], max(cuts[k][c[k]] - 1, cuts[k][c[k] + 1] - 1)) for k in range(len(dims))))
     return idx, cuts
 
 

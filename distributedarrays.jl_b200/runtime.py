@@ -39,6 +39,7 @@ class Runtime:
         self.ctx = ctx
         self.dist = None
         self._ipc_cache = {}
+        self.last_kernel = None  # which entry point served the last local broadcast launch (diagnostics)
         if use_dist is None:
             use_dist = self.world > 1
         if use_dist and self.world > 1:

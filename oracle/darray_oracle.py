@@ -110,7 +110,8 @@ def chunk_idxs(dims: Sequence[int], chunks: Sequence[int]):
     cuts = [defaultdist_cuts(d, c) for d, c in zip(dims, chunks)]
     idxs = {}
     for cidx in grid_iter(chunks):
-        idxs[cidx] = tuple((cuts[i][cidx[i] - 1], cuts[i][cidx[i]] - 1) for i in range(len(dims)))
+        # an empty UnitRange a:b with b < a-1 is normalised to a:a-1 by Julia's UnitRange constructor
+        idxs[cidx] = tuple((cuts[i][cidx[i] - 1], max(cuts[i][cidx[i] - 1] - 1, cuts[i][cidx[i]] - 1)) for i in range(len(dims)))
     return idxs, cuts
 
 

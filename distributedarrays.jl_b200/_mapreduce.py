@@ -250,6 +250,59 @@ def reduce_chunk_dims(rt, ch: B200Array, region_in: Sequence[int], op: int, mapc
     return cur
 
 
+def plan_reducedim(L: Layout, reg_in: Sequence[int]):
+    """Pure layout logic of the dimensional reduction (reference src/mapreduce.jl:42-81).
+
+    Returns ``(Rlayout, fibres)``: the layout of the result R -- ``pids[1:1 along region, : elsewhere]`` (:44), region dims
+    collapsed to index 1:1 with cuts [1, 2] (:59-62) -- and, per chunk of R, the 0-based chunk numbers of A whose partial slabs
+    are accumulated onto it, in column-major grid order along the reduced dims (the order ``Bfull`` is laid out in, :74-77)."""
+    N = len(L.dims)
+    Rgrid = tuple(1 if (k + 1) in reg_in else g for k, g in enumerate(L.grid))
+    Rpids, Rindices, fibres = [], [], []
+    for rl in range(int(np.prod(Rgrid))):
+        rc = unravel(rl, Rgrid)
+        owner_lin = ravel(rc, L.grid)
+        Rpids.append(L.pids[owner_lin])
+        Rindices.append(tuple((1, 1) if (k + 1) in reg_in else L.indices[owner_lin][k] for k in range(N)))
+        sub = [L.grid[k] if (k + 1) in reg_in else 1 for k in range(N)]
+        members = []
+        for ml in range(int(np.prod(sub))):
+            mc = unravel(ml, sub)
+            members.append(ravel(tuple(mc[k] if (k + 1) in reg_in else rc[k] for k in range(N)), L.grid))
+        fibres.append(members)
+    Rdims = tuple(1 if (k + 1) in reg_in else s for k, s in enumerate(L.dims))
+    Rcuts = [[1, 2] if (k + 1) in reg_in else list(L.cuts[k]) for k in range(N)]
+    return Layout(Rdims, Rgrid, Rpids, Rindices, Rcuts), fibres
+
+
+def exchange_plan(L: Layout, Rlayout: Layout, fibres, rank_of: Callable[[int], int], my_rank: int):
+    """Who sends which partial slab to whom in ``mapreducedim_between!`` (reference src/mapreduce.jl:71-81), from the point of
+    view of ``my_rank``.  Pure function of the layouts; every rank computes the same global plan, so the sends of one rank are
+    exactly the receives of its peers (tests/test_dist_gloo.py executes it over gloo).
+
+      owned : R chunk numbers whose owner lives on my rank
+      local : (R chunk, slot in the fibre, member pid)            -- member partial already on my rank: device copy
+      recvs : (R chunk, slot, member pid, source rank)            -- grouped ncclRecv, in this order
+      sends : (member pid, destination rank, R chunk)             -- grouped ncclSend, in this order
+    """
+    owned, local, recvs, sends = [], [], [], []
+    for rl, members in enumerate(fibres):
+        owner = Rlayout.pids[rl]
+        orank = rank_of(owner)
+        if orank == my_rank:
+            owned.append(rl)
+        for slot, m in enumerate(members):
+            mp = L.pids[m]
+            mrank = rank_of(mp)
+            if orank == my_rank and mrank == my_rank:
+                local.append((rl, slot, mp))
+            elif orank == my_rank:
+                recvs.append((rl, slot, mp, mrank))
+            elif mrank == my_rank:
+                sends.append((mp, orank, rl))
+    return {"owned": owned, "local": local, "recvs": recvs, "sends": sends}
+
+
 def mapreducedim(f: Optional[Callable], op, d: DArray, dims, init=None) -> DArray:
     """``mapreduce(f, op, d; dims[, init])`` -> DArray R (reference src/mapreduce.jl:42-94)."""
     rt = d.rt
@@ -285,25 +338,8 @@ def mapreducedim(f: Optional[Callable], op, d: DArray, dims, init=None) -> DArra
                         from ._broadcast import LocalArg, run_local, Expr as _E
                         run_local(rt, _E("arg", (), tag_of(d.dtype), 0), out, [LocalArg(d.chunks[pid], None, tag_of(d.dtype))])
             return R
-        # ---- layout of R: pids[1:1 along region, : elsewhere] (src/mapreduce.jl:44)
-        Rgrid = tuple(1 if (k + 1) in reg_in else g for k, g in enumerate(L.grid))
-        nR = int(np.prod(Rgrid))
-        Rpids, Rindices, fibres = [], [], []
-        for rl in range(nR):
-            rc = unravel(rl, Rgrid)
-            owner_lin = ravel(rc, L.grid)
-            Rpids.append(L.pids[owner_lin])
-            Rindices.append(tuple((1, 1) if (k + 1) in reg_in else L.indices[owner_lin][k] for k in range(N)))
-            # fibre members in column-major order over the grid dims inside the region
-            sub = [L.grid[k] if (k + 1) in reg_in else 1 for k in range(N)]
-            members = []
-            for ml in range(int(np.prod(sub))):
-                mc = unravel(ml, sub)
-                members.append(ravel(tuple(mc[k] if (k + 1) in reg_in else rc[k] for k in range(N)), L.grid))
-            fibres.append(members)
-        Rdims = tuple(1 if (k + 1) in reg_in else s for k, s in enumerate(L.dims))
-        Rcuts = [[1, 2] if (k + 1) in reg_in else list(L.cuts[k]) for k in range(N)]
-        Rlayout = Layout(Rdims, Rgrid, Rpids, Rindices, Rcuts)
+        Rlayout, fibres = plan_reducedim(L, reg_in)
+        Rpids, Rindices = Rlayout.pids, Rlayout.indices
         # ---- phase 1: mapreducedim_within (src/mapreduce.jl:54-66)
         partial: Dict[int, B200Array] = {}
         for pid, ch in src.chunks.items():
@@ -311,25 +347,18 @@ def mapreducedim(f: Optional[Callable], op, d: DArray, dims, init=None) -> DArra
         # ---- phase 2: mapreducedim_between! (src/mapreduce.jl:71-81)
         Rchunks: Dict[int, B200Array] = {}
         stacks: Dict[int, Tuple[B200Array, int, int]] = {}
-        sends, recvs = [], []
-        for rl, members in enumerate(fibres):
-            owner = Rpids[rl]
+        xp = exchange_plan(L, Rlayout, fibres, rt.rank_of, rt.rank)
+        for rl in xp["owned"]:
             plen = int(np.prod(shape_of(Rindices[rl])))
-            if rt.is_local(owner):
-                stack = B200Array.empty(rt, (plen * len(members),), rdt)
-                stacks[rl] = (stack, plen, len(members))
-                for slot, m in enumerate(members):
-                    mp = L.pids[m]
-                    dst = stack.ptr + slot * plen * rdt.itemsize
-                    if rt.is_local(mp):
-                        _lib.call("dab_d2d", rt.ctx, C.c_void_p(dst), C.c_void_p(partial[mp].ptr), plen * rdt.itemsize)
-                    else:
-                        recvs.append((dst, plen * rdt.itemsize, rt.rank_of(mp)))
-            else:
-                for m in members:
-                    mp = L.pids[m]
-                    if rt.is_local(mp):
-                        sends.append((partial[mp].ptr, plen * rdt.itemsize, rt.rank_of(owner)))
+            stacks[rl] = (B200Array.empty(rt, (plen * len(fibres[rl]),), rdt), plen, len(fibres[rl]))
+        for rl, slot, mp in xp["local"]:
+            stack, plen, _ = stacks[rl]
+            _lib.call("dab_d2d", rt.ctx, C.c_void_p(stack.ptr + slot * plen * rdt.itemsize), C.c_void_p(partial[mp].ptr), plen * rdt.itemsize)
+        sends = [(partial[mp].ptr, partial[mp].size * rdt.itemsize, peer) for mp, peer, _ in xp["sends"]]
+        recvs = []
+        for rl, slot, _, peer in xp["recvs"]:
+            stack, plen, _ = stacks[rl]
+            recvs.append((stack.ptr + slot * plen * rdt.itemsize, plen * rdt.itemsize, peer))
         if sends or recvs:
             _lib.call("dab_group_start", rt.ctx)
             for ptr, nb, peer in sends:

@@ -8,7 +8,7 @@
 
 #include "../../include/dab200.h"
 
-#define DAB_MAX_REDUCE_BLOCKS 4096
+#define DAB_MAX_REDUCE_BLOCKS 262144
 #define DAB_SLOT_BYTES 64
 #define DAB_MAX_RANKS 64
 

@@ -106,9 +106,9 @@ int32_t dab_init(int32_t device, dab_ctx** out) {
     }
     ctx->sm_count = prop.multiProcessorCount;
     INIT_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    INIT_CUDA(cudaMalloc(&ctx->block_partials, (size_t)DAB_MAX_REDUCE_BLOCKS * 16));
-    INIT_CUDA(cudaMalloc((void**)&ctx->counter, 64));
-    INIT_CUDA(cudaMemsetAsync(ctx->counter, 0, 64, ctx->stream));
+    INIT_CUDA(cudaMalloc(&ctx->block_partials, ((size_t)DAB_MAX_REDUCE_BLOCKS + DAB_MAX_REDUCE_BLOCKS / 256 + 16) * 8));
+    INIT_CUDA(cudaMalloc((void**)&ctx->counter, (DAB_MAX_REDUCE_BLOCKS / 256 + 16) * 4));
+    INIT_CUDA(cudaMemsetAsync(ctx->counter, 0, (DAB_MAX_REDUCE_BLOCKS / 256 + 16) * 4, ctx->stream));
     INIT_CUDA(cudaMalloc(&ctx->result_slot, DAB_SLOT_BYTES));
     INIT_CUDA(cudaMalloc(&ctx->gather_slots, (size_t)DAB_MAX_RANKS * 16));
     INIT_CUDA(cudaHostAlloc(&ctx->host_slot, (size_t)(DAB_MAX_RANKS + 2) * 16, cudaHostAllocDefault));

@@ -4,10 +4,10 @@
 // map!(f, localpart(dest), makelocal(src, ...)) (src/mapreduce.jl:8).
 //
 // Roofline: HBM.  Algorithmic traffic = sizeof(T) * (inputs + 1) bytes / element (8 B/elem for y .= a.*x .+ b).
-// Design: every element is touched exactly once, so there is no reuse to stage in shared memory; the kernel is a
-// persistent grid (8 CTAs x 256 threads per SM), each CTA walking 16 KiB tiles with UNROLL independent 16-byte
-// evict-first loads in flight per thread before any store (>= 19 MB in flight chip-wide, vs ~5 MB needed by
-// Little's law at 7.7 TB/s x ~0.7 us).  Head/tail elements (unaligned views) are peeled by the last CTA.
+// Design: every element is touched exactly once, so there is no reuse to stage in shared memory (a TMA-staged ring was
+// measured and is slower, see the note on ew1_kernel).  One CTA of 256 threads per 8 KiB tile, 2 independent 16-byte
+// evict-first loads in flight per thread before any store, 8 CTAs resident per SM (~9.7 MB in flight chip-wide, vs ~5 MB
+// needed by Little's law at 7.7 TB/s x ~0.7 us).  Head/tail elements (unaligned views) are peeled by one extra CTA.
 #include <type_traits>
 
 #include "dab_scalar_ops.cuh"
@@ -16,6 +16,11 @@ namespace {
 
 constexpr int EW_THREADS = 256;
 
+// One CTA per 256*UNROLL-vector tile ("flat" grid): the hardware block scheduler hands tiles out in address order as CTAs
+// retire, so the set of concurrently open DRAM pages stays a compact sliding window.  Measured on B200 (tools/sweep_stream.cu,
+// profiles/sweep_r1.txt): 6.94 TB/s for y = a*x+b at 2^30 and 2^31 floats, vs 5.95 TB/s for a persistent grid-stride loop whose
+// CTAs drift apart, 6.65 TB/s for a TMA (cp.async.bulk + mbarrier) ring and 6.6 TB/s for cudaMemcpy D2D.
+// The extra last CTA handles the remainder vectors and the unaligned head / tail elements.
 template <typename T, typename F, int UNROLL>
 __global__ void __launch_bounds__(EW_THREADS) ew1_kernel(T* y, const T* x, size_t n, size_t head, F f) {
     constexpr int VPT = 16 / sizeof(T);
@@ -24,7 +29,8 @@ __global__ void __launch_bounds__(EW_THREADS) ew1_kernel(T* y, const T* x, size_
     int4* yv = reinterpret_cast<int4*>(y + head);
     constexpr size_t TILE = (size_t)EW_THREADS * UNROLL;
     const size_t ntiles = nvec / TILE;
-    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const size_t t = blockIdx.x;
+    if (t < ntiles) {
         const size_t base = t * TILE + threadIdx.x;
         int4 r[UNROLL];
 #pragma unroll
@@ -36,8 +42,7 @@ __global__ void __launch_bounds__(EW_THREADS) ew1_kernel(T* y, const T* x, size_
             for (int k = 0; k < VPT; ++k) p.v[k] = f(p.v[k]);
             st_stream(yv + base + (size_t)u * EW_THREADS, as_int4(p));
         }
-    }
-    if (blockIdx.x == gridDim.x - 1) {  // remainder vectors + unaligned head + tail
+    } else {  // remainder vectors + unaligned head + tail
         for (size_t i = ntiles * TILE + threadIdx.x; i < nvec; i += EW_THREADS) {
             Pack<T> p = as_pack<T>(ld_stream(xv + i));
 #pragma unroll
@@ -58,7 +63,8 @@ __global__ void __launch_bounds__(EW_THREADS) ew2_kernel(T* z, const T* x, const
     int4* zv = reinterpret_cast<int4*>(z + head);
     constexpr size_t TILE = (size_t)EW_THREADS * UNROLL;
     const size_t ntiles = nvec / TILE;
-    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const size_t t = blockIdx.x;
+    if (t < ntiles) {
         const size_t base = t * TILE + threadIdx.x;
         int4 rx[UNROLL], ry[UNROLL];
 #pragma unroll
@@ -73,8 +79,7 @@ __global__ void __launch_bounds__(EW_THREADS) ew2_kernel(T* z, const T* x, const
             for (int k = 0; k < VPT; ++k) p.v[k] = f(p.v[k], q.v[k]);
             st_stream(zv + base + (size_t)u * EW_THREADS, as_int4(p));
         }
-    }
-    if (blockIdx.x == gridDim.x - 1) {
+    } else {
         for (size_t i = ntiles * TILE + threadIdx.x; i < nvec; i += EW_THREADS) {
             Pack<T> p = as_pack<T>(ld_stream(xv + i)), q = as_pack<T>(ld_stream(yv + i));
 #pragma unroll
@@ -108,10 +113,11 @@ template <typename T, typename F>
 int32_t launch_ew1(dab_ctx* ctx, T* y, const T* x, size_t n, F f) {
     if (n == 0) return DAB_OK;
     if ((((uintptr_t)x) & 15) == (((uintptr_t)y) & 15) && (((uintptr_t)x) % sizeof(T)) == 0) {
-        constexpr int UNROLL = 4;
-        size_t tiles = n / ((16 / sizeof(T)) * (size_t)EW_THREADS * UNROLL);
-        int grid = dab_persistent_grid(ctx, ew1_kernel<T, F, UNROLL>, EW_THREADS, tiles);
-        ew1_kernel<T, F, UNROLL><<<grid, EW_THREADS, 0, ctx->stream>>>(y, x, n, head_of<T>(x, n), f);
+        constexpr int UNROLL = 2;
+        const size_t head = head_of<T>(x, n);
+        const size_t tiles = ((n - head) / (16 / sizeof(T))) / ((size_t)EW_THREADS * UNROLL);
+        if (tiles + 1 > 0x7fffffffull) return dab_fail(ctx, DAB_ERR_ARG, "array too large for one launch");
+        ew1_kernel<T, F, UNROLL><<<(unsigned)(tiles + 1), EW_THREADS, 0, ctx->stream>>>(y, x, n, head, f);
     } else {
         int grid = dab_persistent_grid(ctx, ew1_scalar_kernel<T, F>, EW_THREADS, (n + EW_THREADS - 1) / EW_THREADS);
         ew1_scalar_kernel<T, F><<<grid, EW_THREADS, 0, ctx->stream>>>(y, x, n, f);
@@ -126,9 +132,10 @@ int32_t launch_ew2(dab_ctx* ctx, T* z, const T* x, const T* y, size_t n, F f) {
     uintptr_t mx = (uintptr_t)x & 15, my = (uintptr_t)y & 15, mz = (uintptr_t)z & 15;
     if (mx == my && mx == mz && (((uintptr_t)x) % sizeof(T)) == 0) {
         constexpr int UNROLL = 2;
-        size_t tiles = n / ((16 / sizeof(T)) * (size_t)EW_THREADS * UNROLL);
-        int grid = dab_persistent_grid(ctx, ew2_kernel<T, F, UNROLL>, EW_THREADS, tiles);
-        ew2_kernel<T, F, UNROLL><<<grid, EW_THREADS, 0, ctx->stream>>>(z, x, y, n, head_of<T>(x, n), f);
+        const size_t head = head_of<T>(x, n);
+        const size_t tiles = ((n - head) / (16 / sizeof(T))) / ((size_t)EW_THREADS * UNROLL);
+        if (tiles + 1 > 0x7fffffffull) return dab_fail(ctx, DAB_ERR_ARG, "array too large for one launch");
+        ew2_kernel<T, F, UNROLL><<<(unsigned)(tiles + 1), EW_THREADS, 0, ctx->stream>>>(z, x, y, n, head, f);
     } else {
         int grid = dab_persistent_grid(ctx, ew2_scalar_kernel<T, F>, EW_THREADS, (n + EW_THREADS - 1) / EW_THREADS);
         ew2_scalar_kernel<T, F><<<grid, EW_THREADS, 0, ctx->stream>>>(z, x, y, n, f);

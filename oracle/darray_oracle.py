@@ -532,11 +532,18 @@ def julia_mapreducedim(f, op: str, A: np.ndarray, region: Sequence[int], R: np.n
         return R
     lanes, inter = simd if simd is not None else default_simd(v.dtype)
     k = len(region)
-    leading = region == list(range(1, k + 1))
-    lsiz = int(np.prod(A.shape[:k])) if leading and k > 0 else 0
     if k == 0:
         return fn(R, v)
-    if leading and lsiz > 16:
+    # Base.check_reducedims: a dim counts as reduced when size(R, i) == 1; lsiz = product of the leading reduced extents,
+    # 0 as soon as a reduced dim (of extent > 1) follows a kept one.
+    lsiz, had_nonreduc = 1, False
+    for i in range(N):
+        if rshape[i] == 1:
+            if A.shape[i] > 1:
+                lsiz = 0 if had_nonreduc else lsiz * A.shape[i]
+        else:
+            had_nonreduc = True
+    if lsiz > 16:
         flat = v.reshape((lsiz, -1), order="F")           # column = one contiguous slice
         s = _pairwise(fn, np.ascontiguousarray(flat.T), lanes, inter)
         return fn(R, s.reshape(rshape, order="F"))

@@ -1,0 +1,230 @@
+"""CPU-only tests (run with -m "not gpu"): the C-ABI library loads and exports every declared symbol, host-side logic of the
+product (layout math, tracer / promotion / lowering, ordered combine, NVRTC code generation) and the C oracle vs the NumPy
+oracle.  No kernel is launched here.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import core as ocore
+from oracle import darray_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_library_exports_every_declared_symbol(dab):
+    from darray_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "dab200.h")).read()
+    declared = set(re.findall(r"\b(dab_[a-z0-9_]+)\s*\(", hdr)) - {"dab_ctx"}
+    L = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"libdab200.so does not export {name}"
+    assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
+    assert L.dab_abi_version() == 1
+    assert L.dab_status_string(_lib.ERR_EMPTY).decode().startswith("ArgumentError")
+
+
+def test_no_gpu_means_loud_failure_not_fallback(dab):
+    """Without a GPU the product must raise, never compute on the host."""
+    from darray_b200 import _lib
+
+    n = C.c_int32(-1)
+    st = _lib.lib().dab_device_count(C.byref(n))
+    if st == _lib.OK and n.value > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(_lib.DabError):
+        dab.Runtime(use_dist=False)
+
+
+def test_combine_ordered_is_a_left_fold_in_the_result_type(dab):
+    """dab_combine_ordered == reduce(op, results) (reference src/mapreduce.jl:34): host-only entry point."""
+    from darray_b200 import _lib
+
+    L = _lib.lib()
+    v = np.array([1e8, 1.0, -1e8, 1.0, 3.0], dtype=np.float32)
+    out = np.zeros(1, dtype=np.float32)
+    _lib.check(L.dab_combine_ordered(_lib.F32, _lib.SUM, C.c_void_p(v.ctypes.data), v.size, C.c_void_p(out.ctypes.data)))
+    fold = v[0]
+    for x in v[1:]:
+        fold = np.float32(fold + x)
+    assert out[0] == fold == ocore.lib().orc_fold_sum_f32(v.ctypes.data_as(C.POINTER(C.c_float)), v.size)
+    for op, vals, want in [(_lib.MAX, [1.0, np.nan, 3.0], np.nan), (_lib.MAX, [-0.0, 0.0], 0.0), (_lib.MIN, [0.0, -0.0], -0.0),
+                           (_lib.MIN, [2.0, -1.0, 5.0], -1.0), (_lib.PROD, [2.0, 3.0, 0.5], 3.0)]:
+        a = np.array(vals, dtype=np.float32)
+        _lib.check(L.dab_combine_ordered(_lib.F32, op, C.c_void_p(a.ctypes.data), a.size, C.c_void_p(out.ctypes.data)))
+        assert (np.isnan(out[0]) and np.isnan(want)) or (out[0] == want and np.signbit(out[0]) == np.signbit(np.float32(want)))
+    iv = np.array([2**62, 2**62, 5], dtype=np.int64)
+    io = np.zeros(1, dtype=np.int64)
+    _lib.check(L.dab_combine_ordered(_lib.I64, _lib.SUM, C.c_void_p(iv.ctypes.data), 3, C.c_void_p(io.ctypes.data)))
+    assert io[0] == np.int64(-2**63 + 5)  # wraps like Julia Int64
+    assert L.dab_combine_ordered(_lib.F32, _lib.SUM, C.c_void_p(v.ctypes.data), 0, C.c_void_p(out.ctypes.data)) == _lib.ERR_EMPTY
+    dt = C.c_int32()
+    for (d, op, m, want) in [(_lib.F32, _lib.SUM, _lib.MAP_ID, _lib.F32), (_lib.I32, _lib.SUM, _lib.MAP_ID, _lib.I64),
+                             (_lib.I32, _lib.MAX, _lib.MAP_ID, _lib.I32), (_lib.F64, _lib.COUNT, _lib.MAP_GT, _lib.I64),
+                             (_lib.F32, _lib.SUM, _lib.MAP_GT, _lib.I64), (_lib.F64, _lib.PROD, _lib.MAP_ABS, _lib.F64)]:
+        assert L.dab_reduce_result_dtype(d, op, m, C.byref(dt)) == 0 and dt.value == want
+
+
+# ------------------------------------------------------------------------------------------------ layout (product) vs oracle
+def test_layout_matches_oracle_exhaustively(dab):
+    rng = np.random.default_rng(0)
+    cases = [((50,), 4), ((3,), 2), ((1024, 1024), 2), ((1 << 33,), 8), ((65536, 65536), 8), ((73, 73), 2), ((20, 20, 20), 8), ((7, 1), 8), ((1, 9), 8),
+             ((2, 3, 5, 4), 8), ((100, 100), 6), ((5, 5), 7), ((2, 2), 8), ((1,), 3)]
+    for _ in range(200):
+        nd = int(rng.integers(1, 5))
+        cases.append((tuple(int(x) for x in rng.integers(1, 40, nd)), int(rng.integers(1, 17))))
+    for dims, nw in cases:
+        procs = list(range(1, orc.default_nprocs(dims, nw) + 1))
+        assert dab.layout.default_procs(dims, list(range(1, nw + 1))) == procs
+        lay, od = dab.make_layout(dims, procs), orc.make_layout(dims, procs)
+        assert lay.grid == tuple(od.grid) and lay.pids == od.pids and lay.indices == od.indices and lay.cuts == od.cuts, (dims, nw)
+        assert dab.defaultdist(dims, len(procs)) == tuple(orc.defaultdist_grid(dims, len(procs)))
+    assert dab.cuts_for(50, 4) == [1, 14, 27, 39, 51]                    # reference test/darray.jl:66
+    with pytest.raises(ValueError):
+        dab.make_layout((4, 4), [])
+    lay = dab.make_layout((200, 200), [1, 2])
+    assert lay.locate(1, 101) == (1, 2) and lay.locate(200, 100) == (1, 1)
+    with pytest.raises(ValueError):
+        lay.locate(1, 201)
+    l2 = dab.layout.layout_from_chunk_shapes([(3, 10), (7, 10)], (2, 1), [1, 2])
+    o2 = orc.from_chunks([np.zeros((3, 10)), np.zeros((7, 10))], (2, 1), [1, 2])
+    assert l2.dims == o2.dims and l2.indices == o2.indices and l2.cuts == o2.cuts
+
+
+def test_slab_plan_matches_oracle(dab):
+    rng = np.random.default_rng(1)
+    for _ in range(100):
+        nd = int(rng.integers(1, 4))
+        dims = tuple(int(x) for x in rng.integers(2, 30, nd))
+        procs = list(range(1, orc.default_nprocs(dims, 8) + 1))
+        lay, od = dab.make_layout(dims, procs), orc.make_layout(dims, procs)
+        J = []
+        for s in dims:
+            lo = int(rng.integers(1, s + 1))
+            J.append((lo, int(rng.integers(lo, s + 1))))
+        got = [(p.chunk, p.src, p.dst, p.whole_chunk) for p in dab.slab_plan(lay, J)]
+        assert got == [tuple(x) for x in orc.slab_plan(od, J)]
+
+
+def test_collapse_for_region(dab):
+    c = dab.layout.collapse_for_region
+    assert c((32768, 16384), {1}) == [(True, 32768), (False, 16384)]
+    assert c((4, 5, 6), {1, 2}) == [(True, 20), (False, 6)]
+    assert c((4, 5, 6), {1, 3}) == [(True, 4), (False, 5), (True, 6)]
+    assert c((4, 5, 6), {2}) == [(False, 4), (True, 5), (False, 6)]
+
+
+# ------------------------------------------------------------------------------------------------ tracer / promotion / lowering
+def test_tracer_promotion_follows_julia():
+    from darray_b200 import abs2, ifelse, sqrt
+    from darray_b200._broadcast import codegen, convert, match_affine, trace
+
+    f32 = np.float32
+    e = trace(lambda x: 2 * x + 1, ["f32"])                                   # map!(x->2x+1): Int literals adopt Float32
+    assert e.jt == "f32" and match_affine(e) == (2.0, 1.0)
+    assert match_affine(trace(lambda x: f32(1.5) * x + f32(0.25), ["f32"])) == (1.5, 0.25)
+    assert match_affine(trace(lambda x: f32(0.25) + x * f32(1.5), ["f32"])) == (1.5, 0.25)
+    assert match_affine(trace(lambda x: x + 3, ["i64"])) == (1, 3)
+    assert trace(lambda x: 1.5 * x, ["f32"]).jt == "f64"                       # Float64 literal * Float32 -> Float64
+    assert trace(lambda x: f32(1.5) * x, ["f32"]).jt == "f32"
+    assert trace(lambda x: x + 1, ["i32"]).jt == "i64"                         # Int32 + (Int64 literal) -> Int64
+    assert trace(lambda x: x / 2, ["i64"]).jt == "f64"                         # Int / Int -> Float64
+    assert trace(lambda x: x > 1.0, ["f64"]).jt == "bool"
+    assert trace(lambda x, y: x * y, ["f32", "f64"]).jt == "f64"
+    assert trace(lambda x: sqrt(x), ["i64"]).jt == "f64"
+    assert trace(lambda x: x ** 2, ["i64"]).key() == "mul:i64(a0:i64,a0:i64)"   # literal_pow
+    assert trace(lambda x: 1, ["f64"]).op == "const"                           # map(x->1, D)
+    src = codegen(convert(trace(lambda a, m, c: a - m * abs2(c), ["f64", "f64", "f64"]), "f64"))
+    assert src == "jl_sub(a0, jl_mul(a1, jl_abs2(a2)))"
+    assert "?" in codegen(trace(lambda x, y: ifelse(x < y, x, y), ["f32", "f32"]))
+    with pytest.raises(TypeError):
+        trace(lambda x: x if x > 0 else -x, ["f32"])                            # data-dependent Python control flow
+
+
+def test_classify_map_for_reductions():
+    from darray_b200 import _lib, abs2
+    from darray_b200._mapreduce import classify_map
+
+    assert classify_map(None, np.float32)[0] == _lib.MAP_ID
+    assert classify_map(lambda x: x, np.float32)[0] == _lib.MAP_ID
+    assert classify_map(abs, np.int64)[0] == _lib.MAP_ABS
+    assert classify_map(abs2, np.float32)[0] == _lib.MAP_ABS2
+    assert classify_map(lambda t: t * t, np.float64)[0] == _lib.MAP_ABS2
+    code, p, _ = classify_map(lambda x: x > 1.0, np.float64)
+    assert code == _lib.MAP_GT and p == 1.0
+    code, p, _ = classify_map(lambda x: 2.0 == x, np.float64)
+    assert code == _lib.MAP_EQ and p == 2.0
+    code, p, _ = classify_map(lambda x: 3 < x, np.int64)
+    assert code == _lib.MAP_GT and p == 3
+    assert classify_map(lambda x: 2 * x, np.int64)[0] is None                 # general f -> fused map kernel + identity reduce
+
+
+def test_nvrtc_codegen_compiles_for_sm100a(dab):
+    """The exact source dab_broadcast_expr would JIT, compiled with NVRTC for sm_100a on this CPU-only box."""
+    from darray_b200 import _lib, abs2, ifelse, jl_max, mod, sin, sqrt
+    from darray_b200._broadcast import codegen, convert, trace
+
+    L = _lib.lib()
+    code = {"f32": 0, "f64": 1, "i32": 2, "i64": 3, "bool": 4}
+    cases = [(lambda a, m, c: a - m * sin(c), ["f64", "f64", "f64"], "f64"), (lambda z: 3 + abs2(z), ["f64"], "f64"),
+             (lambda x, y: x % y, ["f32", "f32"], "f32"), (lambda x: x > 1.0, ["f64"], "bool"), (lambda x: 2 * x * x - 1, ["i64"], "i64"),
+             (lambda x, y: ifelse(x < y, jl_max(x, y), sqrt(x)), ["f32", "f32"], "f32"), (lambda x, y: mod(x, y) // 3, ["i32", "i32"], "i64"),
+             (lambda x, s: x * s + 1, ["f32", "f64"], "f64")]
+    for f, tags, out in cases:
+        e = trace(f, tags)
+        src = codegen(convert(e, out)).encode()
+        n = len(tags)
+        dts = (C.c_int32 * n)(*[code[t] for t in tags])
+        arr = (C.c_int32 * n)(*([1] * (n - 1) + [0 if n > 1 else 1]))
+        sz = C.c_size_t()
+        st = L.dab_jit_compile_check(src, code[out], n, dts, arr, C.byref(sz))
+        assert st == 0, L.dab_last_error(None)
+        assert sz.value > 1000
+    sz = C.c_size_t()
+    bad = L.dab_jit_compile_check(b"a0 +* 1", 0, 1, (C.c_int32 * 1)(0), (C.c_int32 * 1)(1), C.byref(sz))
+    assert bad == _lib.ERR_NVRTC and b"error" in L.dab_last_error(None)
+
+
+# ------------------------------------------------------------------------------------------------ C oracle == NumPy oracle
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 33, 34, 1023, 1024, 1025, 1026, 2049, 5000, 100003])
+def test_c_oracle_matches_numpy_model_bit_for_bit(n):
+    x = ocore.rand_u01_f32(1234, 7, n)
+    assert np.array_equal(x, orc.rand_u01(1234, 7, n))
+    assert ocore.rand_ksum(1234, 7, n) == orc.rand_u01_ksum(1234, 7, n) == ocore.ksum_f32(x)
+    for simd in [(8, 4), (1, 1), (4, 2)]:
+        assert ocore.sum_f32(x, *simd) == orc.julia_mapreduce(None, "+", x, simd=simd)
+    x64 = x.astype(np.float64) * 1.1
+    assert ocore.sum_f64(x64) == orc.julia_mapreduce(None, "+", x64)
+    assert np.array_equal(ocore.affine_f32(x, 1.5, 0.25), orc.affine_unfused(1.5, x, 0.25))
+    y = x - np.float32(0.5)
+    if n > 3:
+        y[n // 2] = -0.0
+    assert ocore.max_f32(y) == orc.julia_mapreduce(None, "max", y) and ocore.min_f32(y) == orc.julia_mapreduce(None, "min", y)
+
+
+def test_c_oracle_sumdim_matches_numpy_model():
+    for inner, red, outer in [(1, 5000, 7), (1, 20, 9), (1, 12, 3), (6, 33, 4), (16, 4, 1)]:
+        x = orc.rand_u01(3, 0, inner * red * outer)
+        got = ocore.sumdim_f32(x, inner, red, outer)
+        A = x.reshape((inner, red, outer), order="F")
+        want = orc.julia_mapreducedim(None, "+", A, [2]).ravel(order="F")
+        assert np.array_equal(got, want), (inner, red, outer)
+    with pytest.raises(ValueError):
+        ocore.max_f32(np.zeros(0, dtype=np.float32))
+
+
+def test_workers_run_cpu_baseline_smoke():
+    best, mean, res = ocore.workers_run(3, 2, 1 << 16, 1234, 1.5, 0.25, 1, 2)
+    assert best > 0 and mean >= best
+    # two map! passes were warm-up + 2 timed = 3 applications of a*x+b in place, then the sum of the last state
+    x0 = orc.rand_u01(1234, 0, 1 << 16)
+    x1 = orc.rand_u01(1234, 1 << 16, 1 << 16)
+    for _ in range(3):
+        x0, x1 = orc.affine_unfused(1.5, x0, 0.25), orc.affine_unfused(1.5, x1, 0.25)
+    want = np.float32(ocore.sum_f32(x0) + ocore.sum_f32(x1))
+    assert res == want

@@ -242,8 +242,11 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "l2": "inputs (4 GiB/GPU) >> 126 MB L2, no flush needed", "grid": list(x.layout.grid),
                        "combine": "NCCL all-gather of the P chunk results + ordered left fold" if world > 1 else "single chunk"},
-            "roofline": {"bound": "hbm", "kernel": "ew1_kernel<float, AffineF<float>, 4>", "entry": bc_entry, "achieved": bc_gbs, "peak": peak,
-                         "peak_kind": peak_kind, "unit": "GB/s", "frac": bc_gbs / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "ew1_kernel<float, AffineF<float>, 2>", "entry": bc_entry, "achieved": bc_gbs, "peak": peak,
+                         "peak_kind": peak_kind, "unit": "GB/s", "frac": bc_gbs / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 2^30 elements, ncu --set full capture
+                         # profiles/r1_ncu_full_affine_reduce.txt (4.295 + 4.243 GB); null for other sizes
+                         "traffic": 8.538e9 if args.log2n == 30 else None,
                          "algorithmic_bytes_per_launch": 8 * n_per},
             "kernels": {"broadcast_GBs_per_gpu": bc_gbs, "sum_GBs_per_gpu": sum_gbs, "maximum_GBs_per_gpu": max_gbs,
                         "broadcast_frac": bc_gbs / peak, "sum_frac": sum_gbs / peak, "maximum_frac": max_gbs / peak,

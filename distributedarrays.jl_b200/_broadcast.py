@@ -488,6 +488,20 @@ def _localise(rt, a, I, pid) -> LocalArg:
     return LocalArg(None, e.val, e.jt)
 
 
+def _prepare_remote_reads(dest_layout, rt, args):
+    """Collective: when a DArray argument's layout differs from the destination's, some rank will have to halo-fetch non-owned
+    data (makelocal's non-local branch, reference src/darray.jl:361-366).  Every rank takes the same decision from the layouts
+    alone, shares the CUDA-IPC handles and fences the producers' streams before the one-sided peer reads."""
+    if rt.world == 1:
+        return
+    need = [a for a in args if isinstance(a, DArray) and not (a.layout.pids == dest_layout.pids and a.layout.indices == dest_layout.indices)]
+    for a in need:
+        if a._handles is None:
+            a.share()
+    if need:
+        rt.barrier()
+
+
 def broadcast_into(dest: DArray, f: Callable, *args) -> DArray:
     """``dest .= f.(args...)``: ``Base.copyto!(dest::DArray, bc::Broadcasted{Nothing})`` (reference src/broadcast.jl:65-85)."""
     shapes = [a.dims if isinstance(a, DArray) else (a.shape if isinstance(a, np.ndarray) else ()) for a in args]
@@ -495,6 +509,7 @@ def broadcast_into(dest: DArray, f: Callable, *args) -> DArray:
         raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"destination axes {dest.dims} are not compatible with source axes {_bc_shape(shapes)}")
     expr = trace(f, [_arg_tag(a) for a in args])
     rt = dest.rt
+    _prepare_remote_reads(dest.layout, rt, args)
     for pid, out in dest.chunks.items():
         I = dest.layout.localindices(pid)
         largs = [_localise(rt, a, I, pid) for a in args]
@@ -515,6 +530,7 @@ def broadcast(f: Callable, *args, rt=None) -> DArray:
     expr = trace(f, [_arg_tag(a) for a in args])
     out_dt = _NPT[expr.jt]
     dest = darray(lambda I: B200Array.empty(rt, shape_of(I), out_dt), dims, dtype=out_dt, rt=rt)
+    _prepare_remote_reads(dest.layout, rt, args)
     for pid, out in dest.chunks.items():
         I = dest.layout.localindices(pid)
         largs = [_localise(rt, a, I, pid) for a in args]
@@ -536,6 +552,7 @@ def map_inplace(f: Callable, dest: DArray, src: DArray) -> DArray:
     ``map!(f, localpart(dest), makelocal(src, localindices(dest)...))``."""
     expr = trace(f, [tag_of(src.dtype)])
     rt = dest.rt
+    _prepare_remote_reads(dest.layout, rt, [src])
     for pid, out in dest.chunks.items():
         I = dest.layout.localindices(pid)
         arr = makelocal(src, I, pid)

@@ -283,8 +283,17 @@ class SubDArray:
         """Dense device copy of the view on the calling rank's GPU: the halo read (src/darray.jl:584-602, 798-820)."""
         d = self.parent
         rt = rt or d.rt
+        out = B200Array.empty(rt, tuple(rlen(j) for j in self.J), d.dtype)
+        return self.copy_to(out)
+
+    def copy_to(self, out: B200Array) -> B200Array:
+        """``copyto!(a, s::SubDArray)`` into an existing dense device array (reference src/darray.jl:598-602, 798-820): one
+        peer-load copy kernel per intersecting chunk, asynchronous on the ctx stream."""
+        d = self.parent
+        rt = out.rt
         full_shape = tuple(rlen(j) for j in self.J)
-        out = B200Array.empty(rt, full_shape, d.dtype)
+        if out.size != int(np.prod(full_shape)) or out.dtype != d.dtype:
+            raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"destination {out.shape}/{out.dtype} vs view {full_shape}/{d.dtype}")
         for piece in slab_plan(d.layout, self.J):
             pid = d.layout.pids[piece.chunk]
             src_ptr = d.peer_ptr(pid)

@@ -98,6 +98,9 @@ _SIGS = {
     "dab_send": (_i32, [_vp, _vp, _sz, _i32]),
     "dab_recv": (_i32, [_vp, _vp, _sz, _i32]),
     "dab_mapreduce_all": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "dab_mailbox_create": (_i32, [_vp, _vp]),
+    "dab_mailbox_attach": (_i32, [_vp, _vp, _i32, _i32]),
+    "dab_mailbox_detach": (_i32, [_vp]),
     "dab_ipc_get_handle": (_i32, [_vp, _vp, _vp]),
     "dab_ipc_open": (_i32, [_vp, _vp, _pvp]),
     "dab_ipc_close": (_i32, [_vp, _vp]),

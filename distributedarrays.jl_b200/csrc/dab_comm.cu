@@ -199,6 +199,20 @@ int32_t dab_mapreduce_all(dab_ctx* ctx, int32_t dtype, int32_t op, int32_t map, 
     DAB_REQUIRE(ctx, out_host, DAB_ERR_ARG, "dab_mapreduce_all: null out");
     int32_t rdt;
     if (dab_reduce_result_dtype(dtype, op, map, &rdt) != DAB_OK) return dab_fail(ctx, DAB_ERR_ARG, "bad dtype/op");
+    if (ctx->mbox_ranks > 1 && n > 0) {
+        // fused path: ONE kernel = chunk reduce + peer-memory all-gather + ordered fold + scalar into pinned host memory
+        ctx->fuse_op = op;
+        int32_t st = dab_reduce(ctx, dtype, op, map, map_param, x, n, ctx->result_slot);
+        ctx->fuse_op = -1;
+        if (st != DAB_OK) return st;
+        DAB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const volatile unsigned long long* h = (const volatile unsigned long long*)ctx->host_slot;
+        if (h[1] != 0) return dab_fail(ctx, DAB_ERR_NCCL, "fused combine timed out waiting for a peer's chunk result (did every rank call?)");
+        unsigned long long bits = h[0];
+        memset(out_host, 0, 8);
+        memcpy(out_host, &bits, dab_dtype_size(rdt));
+        return DAB_OK;
+    }
     int32_t st = dab_reduce(ctx, dtype, op, map, map_param, x, n, ctx->result_slot);
     if (st != DAB_OK) return st;
     const int P = ctx->comm ? ctx->nranks : 1;
@@ -219,6 +233,56 @@ int32_t dab_mapreduce_all(dab_ctx* ctx, int32_t dtype, int32_t op, int32_t map, 
     if (st != DAB_OK) return dab_fail(ctx, st, "%s", dab_last_error(nullptr));
     memset(out_host, 0, 8);
     memcpy(out_host, res, es);
+    return DAB_OK;
+}
+
+// ---- mailboxes for the fused reduce + combine kernel ---------------------------------------------------------
+int32_t dab_mailbox_create(dab_ctx* ctx, void* handle64) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, handle64, DAB_ERR_ARG, "dab_mailbox_create: null handle");
+    if (!ctx->mailbox) {
+        DAB_CUDA(ctx, cudaMalloc(&ctx->mailbox, DAB_MBOX_BYTES));
+        DAB_CUDA(ctx, cudaMemset(ctx->mailbox, 0, DAB_MBOX_BYTES));
+    }
+    cudaIpcMemHandle_t h;
+    DAB_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->mailbox));
+    memcpy(handle64, &h, 64);
+    return DAB_OK;
+}
+
+int32_t dab_mailbox_attach(dab_ctx* ctx, const void* handles, int32_t rank, int32_t nranks) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, handles && nranks >= 1 && nranks <= DAB_MAX_RANKS && rank >= 0 && rank < nranks, DAB_ERR_ARG, "dab_mailbox_attach: bad arguments");
+    DAB_REQUIRE(ctx, ctx->mailbox, DAB_ERR_ARG, "dab_mailbox_attach: call dab_mailbox_create first");
+    DAB_REQUIRE(ctx, ctx->mbox_ranks == 0, DAB_ERR_ARG, "mailboxes already attached");
+    for (int j = 0; j < nranks; ++j) {
+        if (j == rank) {
+            ctx->peer_mbox_host[j] = ctx->mailbox;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)j * 64, 64);
+        DAB_CUDA(ctx, cudaIpcOpenMemHandle(&ctx->peer_mbox_host[j], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    DAB_CUDA(ctx, cudaMalloc((void**)&ctx->peer_mbox_dev, sizeof(void*) * DAB_MAX_RANKS));
+    DAB_CUDA(ctx, cudaMemcpy(ctx->peer_mbox_dev, ctx->peer_mbox_host, sizeof(void*) * nranks, cudaMemcpyHostToDevice));
+    ctx->rank = rank;
+    ctx->mbox_ranks = nranks;
+    ctx->mbox_seq = 0;
+    return DAB_OK;
+}
+
+int32_t dab_mailbox_detach(dab_ctx* ctx) {
+    if (!ctx) return DAB_OK;
+    cudaSetDevice(ctx->device);
+    for (int j = 0; j < ctx->mbox_ranks; ++j)
+        if (j != ctx->rank && ctx->peer_mbox_host[j]) cudaIpcCloseMemHandle(ctx->peer_mbox_host[j]);
+    if (ctx->peer_mbox_dev) cudaFree(ctx->peer_mbox_dev);
+    if (ctx->mailbox) cudaFree(ctx->mailbox);
+    ctx->peer_mbox_dev = nullptr;
+    ctx->mailbox = nullptr;
+    ctx->mbox_ranks = 0;
+    cudaGetLastError();
     return DAB_OK;
 }
 

@@ -28,6 +28,13 @@ struct dab_ctx {
     // NCCL
     void* comm;
     int rank, nranks;
+    // fused reduce + all-gather + ordered fold over peer memory (dab_mailbox_*; dab_reduce.cu)
+    void* mailbox;          // this rank's mailbox (device, cudaMalloc'ed, IPC-exported)
+    void** peer_mbox_dev;   // device array [nranks] of mailbox addresses as mapped in THIS process
+    void* peer_mbox_host[DAB_MAX_RANKS];
+    int mbox_ranks;         // 0 = not attached
+    unsigned long long mbox_seq;
+    int fuse_op;            // >= 0: the next launch_reduce appends the cross-rank combine for this DAB_* op
     char err[512];
 };
 
@@ -70,6 +77,16 @@ static inline size_t dab_dtype_size(int32_t dt) {
         default: return 0;
     }
 }
+
+// Cross-rank combine fused into the reduce kernel's last CTA (see reduce_kernel): nranks == 0 disables it.
+#define DAB_MBOX_SLOT 32                                   /* [0,8) result  [8,16) wide carrier  [16,24) sequence flag */
+#define DAB_MBOX_BYTES (2 * DAB_MAX_RANKS * DAB_MBOX_SLOT) /* two parities */
+struct FusedComm {
+    void* const* peers;        // device array of the nranks mailboxes
+    void* host_out;            // pinned host slot: [0,8) folded result, [8,16) status (0 ok, 1 timed out)
+    unsigned long long seq;
+    int rank, nranks, op;
+};
 
 // ---- device helpers --------------------------------------------------------------------
 // 16-byte streaming load/store (evict-first: every element of the hot path is touched once).

@@ -87,6 +87,7 @@ int32_t dab_init(int32_t device, dab_ctx** out) {
     ctx->device = device;
     ctx->rank = 0;
     ctx->nranks = 1;
+    ctx->fuse_op = -1;
 #define INIT_CUDA(call)                                                     \
     do {                                                                    \
         cudaError_t e__ = (call);                                           \
@@ -119,6 +120,7 @@ int32_t dab_init(int32_t device, dab_ctx** out) {
 }
 
 int32_t dab_comm_destroy(dab_ctx* ctx);
+int32_t dab_mailbox_detach(dab_ctx* ctx);
 
 int32_t dab_shutdown(dab_ctx* ctx) {
     if (!ctx) return DAB_OK;
@@ -130,6 +132,7 @@ int32_t dab_shutdown(dab_ctx* ctx) {
     cudaFree(ctx->result_slot);
     cudaFree(ctx->gather_slots);
     if (ctx->dim_scratch) cudaFree(ctx->dim_scratch);
+    dab_mailbox_detach(ctx);
     cudaFreeHost(ctx->host_slot);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

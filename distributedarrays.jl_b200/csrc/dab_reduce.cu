@@ -25,7 +25,8 @@ constexpr int RD_UNROLL = 4;
 template <typename T, typename Map, typename R, typename Out>
 __global__ void __launch_bounds__(RD_THREADS) reduce_kernel(const T* __restrict__ x, size_t n, size_t head, Map map,
                                                              typename R::A* __restrict__ partials, unsigned int* counter,
-                                                             void* out, int finalize_mode, long long n_for_all, int tiles_per_cta) {
+                                                             void* out, int finalize_mode, long long n_for_all, int tiles_per_cta,
+                                                             FusedComm fc) {
     using A = typename R::A;
     using V = typename Map::V;
     constexpr int VPT = 16 / sizeof(T);
@@ -122,6 +123,64 @@ __global__ void __launch_bounds__(RD_THREADS) reduce_kernel(const T* __restrict_
         memcpy((char*)out + 8, &wide, sizeof(A));
         if (sizeof(A) < 8) memset((char*)out + 8 + sizeof(A), 0, 8 - sizeof(A));
     }
+    if (fc.nranks <= 1) return;
+    // ---- fused cross-worker combine over NVLink peer memory (replaces remotecall_fetch + reduce(op, results), reference
+    // src/mapreduce.jl:30-34, and an ncclAllGather + D2H copy): thread j of this last CTA PUSHES this rank's chunk result into
+    // rank j's mailbox (16-byte payload, system fence, then the sequence flag), then polls its own mailbox slot j until rank j's
+    // result for this call has landed; thread 0 folds the P results LEFT TO RIGHT in rank (= procs(d)) order in the result type
+    // and writes the scalar straight into pinned host memory.  Two parity banks: a fast rank can be at most one call ahead.
+    __shared__ unsigned long long pay[2];
+    __shared__ unsigned long long got[DAB_MAX_RANKS];
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) {
+        memcpy(&pay[0], out, 8);
+        memcpy(&pay[1], (char*)out + 8, 8);
+        timed_out = 0;
+    }
+    __syncthreads();
+    const size_t bank = (size_t)(fc.seq & 1ull) * DAB_MAX_RANKS * DAB_MBOX_SLOT;
+    if (threadIdx.x < (unsigned)fc.nranks) {
+        volatile unsigned long long* dst =
+            reinterpret_cast<volatile unsigned long long*>((char*)fc.peers[threadIdx.x] + bank + (size_t)fc.rank * DAB_MBOX_SLOT);
+        dst[0] = pay[0];
+        dst[1] = pay[1];
+        __threadfence_system();
+        dst[2] = fc.seq;
+        volatile unsigned long long* src =
+            reinterpret_cast<volatile unsigned long long*>((char*)fc.peers[fc.rank] + bank + (size_t)threadIdx.x * DAB_MBOX_SLOT);
+        const long long t0 = clock64();
+        while (src[2] != fc.seq) {
+            if (clock64() - t0 > 6000000000ll) {  // ~3 s at 1.9 GHz: a peer never called -> report instead of hanging the GPU
+                timed_out = 1;
+                break;
+            }
+        }
+        __threadfence_system();
+        got[threadIdx.x] = src[0];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Out a;
+        memcpy(&a, &got[0], sizeof(Out));
+        for (int j = 1; j < fc.nranks; ++j) {
+            Out b;
+            memcpy(&b, &got[j], sizeof(Out));
+            switch (fc.op) {
+                case DAB_SUM: case DAB_COUNT: a = jl::add(a, b); break;
+                case DAB_PROD: a = jl::mul(a, b); break;
+                case DAB_MAX: a = jl::max(a, b); break;
+                case DAB_MIN: a = jl::min(a, b); break;
+                case DAB_ALL: a = (Out)(a != (Out)0 && b != (Out)0); break;
+                default: a = (Out)(a != (Out)0 || b != (Out)0); break;  // ANY
+            }
+        }
+        unsigned long long bits = 0;
+        memcpy(&bits, &a, sizeof(Out));
+        volatile unsigned long long* h = reinterpret_cast<volatile unsigned long long*>(fc.host_out);
+        h[0] = bits;
+        h[1] = (unsigned long long)timed_out;
+        __threadfence_system();
+    }
 }
 
 template <typename T, typename Map, typename R, typename Out>
@@ -134,8 +193,18 @@ int32_t launch_reduce(dab_ctx* ctx, const T* x, size_t n, Map map, void* out, in
     if ((tiles + k - 1) / k > (size_t)DAB_MAX_REDUCE_BLOCKS) k = (tiles + DAB_MAX_REDUCE_BLOCKS - 1) / DAB_MAX_REDUCE_BLOCKS;
     size_t grid = (tiles + k - 1) / k;
     if (grid < 1) grid = 1;
+    FusedComm fc;
+    memset(&fc, 0, sizeof(fc));
+    if (ctx->fuse_op >= 0 && ctx->mbox_ranks > 1) {
+        fc.peers = ctx->peer_mbox_dev;
+        fc.host_out = ctx->host_slot;
+        fc.seq = ++ctx->mbox_seq;
+        fc.rank = ctx->rank;
+        fc.nranks = ctx->mbox_ranks;
+        fc.op = ctx->fuse_op;
+    }
     reduce_kernel<T, Map, R, Out><<<(unsigned)grid, RD_THREADS, 0, ctx->stream>>>(x, n, head, map, (typename R::A*)ctx->block_partials,
-                                                                                  ctx->counter, out, finalize_mode, (long long)n, (int)k);
+                                                                                  ctx->counter, out, finalize_mode, (long long)n, (int)k, fc);
     DAB_LAUNCHED(ctx);
     return DAB_OK;
 }

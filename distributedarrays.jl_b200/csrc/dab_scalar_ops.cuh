@@ -22,6 +22,9 @@ __device__ __forceinline__ long long add(long long a, long long b) { return (lon
 __device__ __forceinline__ long long sub(long long a, long long b) { return (long long)((unsigned long long)a - (unsigned long long)b); }
 __device__ __forceinline__ long long mul(long long a, long long b) { return (long long)((unsigned long long)a * (unsigned long long)b); }
 
+__device__ __forceinline__ uint8_t add(uint8_t a, uint8_t b) { return (uint8_t)(a + b); }
+__device__ __forceinline__ uint8_t mul(uint8_t a, uint8_t b) { return (uint8_t)(a * b); }
+
 // ---- max / min ----------------------------------------------------------------------------
 // PTX max.NaN.f32: NaN if either input is NaN; +0.0 > -0.0 (PTX ISA "max": -0.0 < +0.0).
 __device__ __forceinline__ float max(float a, float b) {

@@ -40,6 +40,7 @@ class Runtime:
         self.dist = None
         self._ipc_cache = {}
         self.last_kernel = None  # which entry point served the last local broadcast launch (diagnostics)
+        self.fused_combine = False
         if use_dist is None:
             use_dist = self.world > 1
         if use_dist and self.world > 1:
@@ -61,6 +62,16 @@ class Runtime:
         dist.broadcast_object_list(box, src=0)
         buf = C.create_string_buffer(box[0], 128)
         _lib.call("dab_comm_init_rank", self.ctx, buf, self.rank, self.world)
+        # mailboxes for the fused reduce + combine kernel (peer stores over NVLink instead of ncclAllGather + D2H);
+        # DAB_FUSED_COMBINE=0 keeps the NCCL path (A/B measurements, debugging)
+        if os.environ.get("DAB_FUSED_COMBINE", "1") != "0":
+            h = C.create_string_buffer(64)
+            _lib.call("dab_mailbox_create", self.ctx, h)
+            allh = [None] * self.world
+            dist.all_gather_object(allh, h.raw)
+            _lib.call("dab_mailbox_attach", self.ctx, C.create_string_buffer(b"".join(allh), 64 * self.world), self.rank, self.world)
+            self.fused_combine = True
+            dist.barrier()
 
     def barrier(self):
         """Stream sync + host barrier: the fence before one-sided (peer) reads of other workers' chunks."""

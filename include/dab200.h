@@ -235,6 +235,16 @@ int32_t dab_recv(dab_ctx* ctx, void* recv_dev, size_t nbytes, int32_t peer);
 int32_t dab_mapreduce_all(dab_ctx* ctx, int32_t dtype, int32_t op, int32_t map, const void* map_param, const void* x,
                           size_t n, void* out_host);
 
+/* Fused reduce + combine over NVLink peer memory.  After every rank has created its mailbox (dab_mailbox_create returns the
+ * 64-byte CUDA IPC handle), exchanged the handles through the host runtime and attached them (handles = nranks * 64 bytes, in
+ * rank order), dab_mapreduce_all runs as ONE kernel: the last CTA of the chunk reduction pushes the chunk result into every
+ * peer's mailbox with peer stores, waits for the P results, folds them left to right in rank order and writes the scalar into
+ * pinned host memory -- no NCCL call, no D2H copy.  A rank that never calls makes the others time out (~3 s) with DAB_ERR_NCCL
+ * instead of hanging the GPU.  All ranks must call dab_mapreduce_all in the same order (as with any collective). */
+int32_t dab_mailbox_create(dab_ctx* ctx, void* handle64);
+int32_t dab_mailbox_attach(dab_ctx* ctx, const void* handles, int32_t rank, int32_t nranks);
+int32_t dab_mailbox_detach(dab_ctx* ctx);
+
 /* ==== peer memory (one process per GPU): CUDA IPC handles, shipped by the host runtime ==== */
 int32_t dab_ipc_get_handle(dab_ctx* ctx, const void* dptr, void* handle64);
 int32_t dab_ipc_open(dab_ctx* ctx, const void* handle64, void** dptr);

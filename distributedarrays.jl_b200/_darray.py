@@ -52,17 +52,20 @@ def allowscalar(flag: bool = True):
 class B200Array:
     """A dense column-major array in one GPU's HBM: the chunk type ``A`` of ``DArray{T,N,A}``."""
 
-    __slots__ = ("rt", "ptr", "shape", "dtype", "_own", "_keep")
+    __slots__ = ("rt", "ptr", "shape", "dtype", "_own", "_keep", "_temp")
 
-    def __init__(self, rt: Runtime, ptr: int, shape: Sequence[int], dtype, own: bool = True, keep=None):
+    def __init__(self, rt: Runtime, ptr: int, shape: Sequence[int], dtype, own: bool = True, keep=None, temp: bool = False):
         self.rt, self.ptr, self.shape, self.dtype = rt, int(ptr), tuple(int(s) for s in shape), np.dtype(dtype)
-        self._own, self._keep = own, keep
+        self._own, self._keep, self._temp = own, keep, temp
 
     @classmethod
-    def empty(cls, rt: Runtime, shape: Sequence[int], dtype) -> "B200Array":
+    def empty(cls, rt: Runtime, shape: Sequence[int], dtype, temp: bool = False) -> "B200Array":
+        """``temp=True``: stream-ordered pool allocation for short-lived scratch (partials, gather stacks); such arrays cannot be
+        shared over CUDA IPC, so localparts always use the default."""
         dtype = np.dtype(dtype)
         n = int(np.prod(shape)) if len(shape) else 1
-        return cls(rt, rt.alloc(n * dtype.itemsize), shape, dtype)
+        ptr = rt.alloc_temp(n * dtype.itemsize) if temp else rt.alloc(n * dtype.itemsize)
+        return cls(rt, ptr, shape, dtype, temp=temp)
 
     @classmethod
     def from_numpy(cls, rt: Runtime, a: np.ndarray) -> "B200Array":
@@ -112,7 +115,10 @@ class B200Array:
 
     def free(self):
         if self._own and self.ptr:
-            self.rt.free(self.ptr)
+            if self._temp:
+                self.rt.free_temp(self.ptr)
+            else:
+                self.rt.free(self.ptr)
         self.ptr = 0
 
     def __repr__(self):

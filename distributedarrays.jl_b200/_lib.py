@@ -66,6 +66,8 @@ _SIGS = {
     "dab_event_destroy": (_i32, [_vp, _vp]),
     "dab_alloc": (_i32, [_vp, _sz, _pvp]),
     "dab_free": (_i32, [_vp, _vp]),
+    "dab_alloc_async": (_i32, [_vp, _sz, _pvp]),
+    "dab_free_async": (_i32, [_vp, _vp]),
     "dab_host_alloc": (_i32, [_vp, _sz, _pvp]),
     "dab_host_free": (_i32, [_vp, _vp]),
     "dab_h2d": (_i32, [_vp, _vp, _vp, _sz]),

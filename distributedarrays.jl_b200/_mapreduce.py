@@ -81,14 +81,14 @@ def _chunk_partials(d: DArray, op: int, mapc: int, param) -> Tuple[np.ndarray, n
     rt = d.rt
     code = dab_dtype(d.dtype)
     wpr = rt.workers_per_rank
-    slots = B200Array.empty(rt, (16 * wpr,), np.uint8)
+    slots = B200Array.empty(rt, (16 * wpr,), np.uint8, temp=True)
     pp = C.c_void_p(param.ctypes.data) if param is not None else None
     try:
         for pid, ch in d.chunks.items():
             k = (pid - 1) % wpr
             _lib.call("dab_reduce", rt.ctx, code, op, mapc, pp, C.c_void_p(ch.ptr), ch.size, C.c_void_p(slots.ptr + 16 * k))
         if rt.world > 1:
-            allslots = B200Array.empty(rt, (16 * wpr * rt.world,), np.uint8)
+            allslots = B200Array.empty(rt, (16 * wpr * rt.world,), np.uint8, temp=True)
             _lib.call("dab_allgather", rt.ctx, C.c_void_p(slots.ptr), C.c_void_p(allslots.ptr), 16 * wpr)
             host = allslots.to_numpy()
             allslots.free()
@@ -236,11 +236,10 @@ def reduce_chunk_dims(rt, ch: B200Array, region_in: Sequence[int], op: int, mapc
         inner = int(np.prod(ext[:ri])) if ri else 1
         red = ext[ri]
         outer = int(np.prod(ext[ri + 1:])) if ri + 1 < len(ext) else 1
-        nxt = B200Array.empty(rt, (inner * outer,), out_dtype)
+        nxt = B200Array.empty(rt, (inner * outer,), out_dtype, temp=True)
         _lib.call("dab_reducedim", rt.ctx, dab_dtype(cur_dtype), op, cur_map, C.c_void_p(cur.ptr), inner, red, outer, C.c_void_p(nxt.ptr), 0)
         if owned:
-            rt.sync()
-            cur.free()
+            cur.free()  # stream-ordered: no host sync needed
         cur, cur_dtype, cur_map, owned = nxt, out_dtype, _lib.MAP_ID, True
         ext[ri] = 1
     rshape = tuple(1 if (k + 1) in region_in else s for k, s in enumerate(ch.shape))
@@ -350,7 +349,7 @@ def mapreducedim(f: Optional[Callable], op, d: DArray, dims, init=None) -> DArra
         xp = exchange_plan(L, Rlayout, fibres, rt.rank_of, rt.rank)
         for rl in xp["owned"]:
             plen = int(np.prod(shape_of(Rindices[rl])))
-            stacks[rl] = (B200Array.empty(rt, (plen * len(fibres[rl]),), rdt), plen, len(fibres[rl]))
+            stacks[rl] = (B200Array.empty(rt, (plen * len(fibres[rl]),), rdt, temp=True), plen, len(fibres[rl]))
         for rl, slot, mp in xp["local"]:
             stack, plen, _ = stacks[rl]
             _lib.call("dab_d2d", rt.ctx, C.c_void_p(stack.ptr + slot * plen * rdt.itemsize), C.c_void_p(partial[mp].ptr), plen * rdt.itemsize)
@@ -378,8 +377,7 @@ def mapreducedim(f: Optional[Callable], op, d: DArray, dims, init=None) -> DArra
             # Base.mapreducedim!(identity, op, localpart(R), Bfull): accumulate the nm partial slabs, in grid order, onto R
             _lib.call("dab_reducedim", rt.ctx, dab_dtype(rdt), opc, _lib.MAP_ID, C.c_void_p(stack.ptr), plen, nm, 1, C.c_void_p(Rch.ptr), acc)
             Rchunks[owner] = Rch
-        rt.sync()
-        for stack, _, _ in stacks.values():
+        for stack, _, _ in stacks.values():  # temporaries are freed in stream order
             stack.free()
         for p in partial.values():
             p.free()

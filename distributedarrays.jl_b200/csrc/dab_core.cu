@@ -107,6 +107,12 @@ int32_t dab_init(int32_t device, dab_ctx** out) {
     }
     ctx->sm_count = prop.multiProcessorCount;
     INIT_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {
+        cudaMemPool_t pool;
+        INIT_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;
+        INIT_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     INIT_CUDA(cudaMalloc(&ctx->block_partials, ((size_t)DAB_MAX_REDUCE_BLOCKS + DAB_MAX_REDUCE_BLOCKS / 256 + 16) * 8));
     INIT_CUDA(cudaMalloc((void**)&ctx->counter, (DAB_MAX_REDUCE_BLOCKS / 256 + 16) * 4));
     INIT_CUDA(cudaMemsetAsync(ctx->counter, 0, (DAB_MAX_REDUCE_BLOCKS / 256 + 16) * 4, ctx->stream));
@@ -208,6 +214,22 @@ int32_t dab_alloc(dab_ctx* ctx, size_t nbytes, void** dptr) {
 int32_t dab_free(dab_ctx* ctx, void* dptr) {
     DAB_ENTER(ctx);
     if (dptr) DAB_CUDA(ctx, cudaFree(dptr));
+    return DAB_OK;
+}
+// Stream-ordered temporaries (partial slabs, gather stacks, result slots): cudaMallocAsync from the device's default pool with
+// an unlimited release threshold, so steady-state calls cost ~1 us and never synchronise.  NOT exportable over CUDA IPC: chunks
+// that peers read must come from dab_alloc.
+int32_t dab_alloc_async(dab_ctx* ctx, size_t nbytes, void** dptr) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, dptr, DAB_ERR_ARG, "null dptr out-pointer");
+    *dptr = nullptr;
+    if (nbytes == 0) nbytes = 16;
+    DAB_CUDA(ctx, cudaMallocAsync(dptr, nbytes, ctx->stream));
+    return DAB_OK;
+}
+int32_t dab_free_async(dab_ctx* ctx, void* dptr) {
+    DAB_ENTER(ctx);
+    if (dptr) DAB_CUDA(ctx, cudaFreeAsync(dptr, ctx->stream));
     return DAB_OK;
 }
 int32_t dab_host_alloc(dab_ctx* ctx, size_t nbytes, void** hptr) {

@@ -23,7 +23,7 @@ constexpr int RD_UNROLL = 4;
 // Result slot layout (16 bytes at `out`): [0..8) the result in its result dtype, [8..16) the wide accumulator (fp64 for
 // float SUM/PROD -- lets the host see the un-rounded carrier; tests use it).
 template <typename T, typename Map, typename R, typename Out>
-__global__ void __launch_bounds__(RD_THREADS) reduce_kernel(const T* __restrict__ x, size_t n, size_t head, Map map,
+__global__ void __launch_bounds__(RD_THREADS, 8) reduce_kernel(const T* __restrict__ x, size_t n, size_t head, Map map,
                                                              typename R::A* __restrict__ partials, unsigned int* counter,
                                                              void* out, int finalize_mode, long long n_for_all, int tiles_per_cta,
                                                              FusedComm fc) {

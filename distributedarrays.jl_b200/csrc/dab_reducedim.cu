@@ -127,16 +127,18 @@ __global__ void __launch_bounds__(RD_THREADS) rdim_strided_kernel(const T* __res
                                                                    Out* __restrict__ out, int accumulate) {
     using A = typename R::A;
     constexpr int UNROLL = 8;
-    const size_t iblocks = (inner + RD_THREADS - 1) / RD_THREADS;
-    const size_t work = iblocks * outer * (size_t)nsplit;
+    // threads cover the flattened output index k = i + inner*o (i fastest): full CTAs even when `inner` is small
+    const size_t nout = inner * outer;
+    const size_t kblocks = (nout + RD_THREADS - 1) / RD_THREADS;
+    const size_t work = kblocks * (size_t)nsplit;
     const size_t split_len = (red + nsplit - 1) / nsplit;
     for (size_t w = blockIdx.x; w < work; w += gridDim.x) {
-        const size_t ib = w % iblocks;
-        const size_t rest = w / iblocks;
-        const size_t sp = rest % nsplit;
-        const size_t o = rest / nsplit;
-        const size_t i = ib * RD_THREADS + threadIdx.x;
-        if (i >= inner) continue;
+        const size_t kb = w % kblocks;
+        const size_t sp = w / kblocks;
+        const size_t k = kb * RD_THREADS + threadIdx.x;
+        if (k >= nout) continue;
+        const size_t o = k / inner;
+        const size_t i = k - o * inner;
         size_t lo = sp * split_len, hi = lo + split_len;
         if (hi > red) hi = red;
         const T* p = x + i + inner * (o * red);
@@ -152,16 +154,15 @@ __global__ void __launch_bounds__(RD_THREADS) rdim_strided_kernel(const T* __res
 #pragma unroll
             for (int ww = UNROLL; ww > 1; ww >>= 1)
 #pragma unroll
-                for (int k = 0; k < ww / 2; ++k) m[k] = R::tile(m[k], m[k + ww / 2]);
+                for (int q = 0; q < ww / 2; ++q) m[q] = R::tile(m[q], m[q + ww / 2]);
             acc = R::comb(acc, R::lift(m[0]));
         }
         for (; r < hi; ++r) acc = R::comb(acc, R::lift(map(__ldcs(p + r * inner))));
         if (nsplit == 1) {
-            const size_t oi = i + inner * o;
-            if (accumulate) acc = R::comb((A)out[oi], acc);
-            out[oi] = narrow<A, Out>(acc);
+            if (accumulate) acc = R::comb((A)out[k], acc);
+            out[k] = narrow<A, Out>(acc);
         } else {
-            partials[(sp * outer + o) * inner + i] = acc;
+            partials[sp * nout + k] = acc;
         }
     }
 }
@@ -227,8 +228,7 @@ int32_t launch_rdim(dab_ctx* ctx, const T* x, size_t inner, size_t red, size_t o
         }
         return DAB_OK;
     }
-    const size_t iblocks = (inner + RD_THREADS - 1) / RD_THREADS;
-    size_t base_ctas = iblocks * outer;
+    size_t base_ctas = (inner * outer + RD_THREADS - 1) / RD_THREADS;
     size_t max_split = red / 64;
     if (max_split < 1) max_split = 1;
     size_t want = base_ctas >= target_ctas ? 1 : (target_ctas + base_ctas - 1) / base_ctas;
@@ -250,6 +250,23 @@ int32_t launch_rdim(dab_ctx* ctx, const T* x, size_t inner, size_t red, size_t o
         DAB_LAUNCHED(ctx);
     }
     return DAB_OK;
+}
+
+// out[0] (op)= slot[0]: lands the result of the flat whole-chunk reduce kernel when the "dimensional" reduction is really a
+// full reduction (inner == outer == 1)
+template <typename Out>
+__global__ void scalar_into_kernel(const Out* __restrict__ slot, Out* __restrict__ out, int accumulate, int op) {
+    Out v = *slot;
+    if (accumulate) {
+        Out o = *out;
+        switch (op) {
+            case DAB_SUM: v = jl::add(o, v); break;
+            case DAB_PROD: v = jl::mul(o, v); break;
+            case DAB_MAX: v = jl::max(o, v); break;
+            default: v = jl::min(o, v); break;
+        }
+    }
+    *out = v;
 }
 
 template <typename T>
@@ -303,6 +320,22 @@ int32_t dab_reducedim(dab_ctx* ctx, int32_t dtype, int32_t op, int32_t map, cons
             else { long long o = 1; memcpy(v, &o, 8); }
         }
         return dab_fill(ctx, rdt, out, nout, v);
+    }
+    if (inner == 1 && outer == 1 && reduce >= (1u << 16) && (map == DAB_MAP_ID || map == DAB_MAP_ABS || map == DAB_MAP_ABS2 || map == DAB_MAP_NEG) &&
+        op <= DAB_MIN) {
+        // a full reduction in disguise (e.g. sum(v, dims=1) of a vector, dims=(1,2) of a matrix): use the flat streaming kernel
+        int32_t st = dab_reduce(ctx, dtype, op, map, nullptr, x, reduce, ctx->result_slot);
+        if (st != DAB_OK) return st;
+        int32_t rdt;
+        dab_reduce_result_dtype(dtype, op, map, &rdt);
+        switch (rdt) {
+            case DAB_F32: scalar_into_kernel<float><<<1, 1, 0, ctx->stream>>>((const float*)ctx->result_slot, (float*)out, accumulate, op); break;
+            case DAB_F64: scalar_into_kernel<double><<<1, 1, 0, ctx->stream>>>((const double*)ctx->result_slot, (double*)out, accumulate, op); break;
+            case DAB_I32: scalar_into_kernel<int32_t><<<1, 1, 0, ctx->stream>>>((const int32_t*)ctx->result_slot, (int32_t*)out, accumulate, op); break;
+            default: scalar_into_kernel<long long><<<1, 1, 0, ctx->stream>>>((const long long*)ctx->result_slot, (long long*)out, accumulate, op); break;
+        }
+        DAB_LAUNCHED(ctx);
+        return DAB_OK;
     }
     switch (dtype) {
         case DAB_F32: return rdim_t<float>(ctx, op, map, (const float*)x, inner, reduce, outer, out, accumulate);

@@ -3,66 +3,154 @@
 // Replaces, per intersecting chunk, the owner-side  localpart(d)[idxs...]  + Julia serialisation + TCP + a[idxs...] = ...
 // of setindex!(a::Array, s::SubDArray, I...) (reference src/darray.jl:798-820), chunk(d, pid) (:458) and the non-local branch
 // of makelocal (:361-366).  The reference's read is pull-style and one-sided from the reader's point of view; so is this:
-// the READER launches the kernel and loads straight from the owner's HBM (peer mapping / CUDA IPC) over NVLink 5 with the
-// widest vector the box geometry allows (16-byte LDG when base, pitches and row length are 16-byte multiples), 4 loads in
-// flight per thread, and stores into its own HBM.  Roofline: NVLink (peer) or HBM (local): elem_bytes moved once per element.
+// the READER launches the kernel and loads straight from the owner's HBM (peer mapping / CUDA IPC) over NVLink 5, UNROLL
+// independent loads in flight per thread, and stores into its own HBM.  Roofline: NVLink (peer) or HBM (local): elem_bytes moved
+// once per element.
+//
+// Vector width: loads are the scarce resource on the peer path (NVLink request rate), so the LOAD unit is made as wide as the
+// source geometry allows (16 B when source base / pitches / row length are 16-byte multiples); when the destination is less
+// aligned than the source the value is stored in smaller pieces (local HBM stores are cheap).  A contiguous slab whose source
+// start is not 16-byte aligned is split on the host into head (< 16 B) + 16-byte-aligned body + tail.
+#include <cstdlib>
+
 #include "dab_common.cuh"
 
 namespace {
 
 struct BoxGeom {
-    // all in units of `vec` bytes along dim 0, elements of pitch along dims 1..3 (bytes)
-    unsigned long long upr;        // units per row
-    unsigned long long e1, e2, e3; // rows along dims 1..3
-    long long sp1, sp2, sp3;       // src pitches in bytes
-    long long dp1, dp2, dp3;       // dst pitches in bytes
+    unsigned long long upr;         // load units per row
+    unsigned long long e1, e2, e3;  // rows along dims 1..3
+    long long sp1, sp2, sp3;        // src pitches in bytes
+    long long dp1, dp2, dp3;        // dst pitches in bytes
 };
 
-template <typename U, typename I>
+template <typename U, typename S>
+__device__ __forceinline__ void store_as(char* dst, const U& v) {
+    constexpr int N = sizeof(U) / sizeof(S);
+    const S* p = reinterpret_cast<const S*>(&v);
+#pragma unroll
+    for (int k = 0; k < N; ++k) reinterpret_cast<S*>(dst)[k] = p[k];
+}
+
+// U = load unit, S = store unit (sizeof(S) <= sizeof(U)), I = index type
+template <typename U, typename S, typename I, int UNROLL>
 __global__ void __launch_bounds__(256) copy_box_kernel(char* __restrict__ dst, const char* __restrict__ src, BoxGeom g, I total) {
-    constexpr int UNROLL = 4;
     const I stride = (I)gridDim.x * blockDim.x;
     I idx = (I)blockIdx.x * blockDim.x + threadIdx.x;
     const I upr = (I)g.upr, e1 = (I)g.e1, e2 = (I)g.e2;
+    const bool flat = (g.e1 == 1 && g.e2 == 1 && g.e3 == 1);
     for (; idx + (UNROLL - 1) * stride < total; idx += UNROLL * stride) {
         U v[UNROLL];
         size_t doff[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             I id = idx + u * stride;
-            I row = id / upr, col = id - row * upr;
-            I j = row % e1, t = row / e1;
-            I k = t % e2, l = t / e2;
-            size_t soff = (size_t)col * sizeof(U) + (size_t)j * g.sp1 + (size_t)k * g.sp2 + (size_t)l * g.sp3;
-            doff[u] = (size_t)col * sizeof(U) + (size_t)j * g.dp1 + (size_t)k * g.dp2 + (size_t)l * g.dp3;
+            size_t soff;
+            if (flat) {
+                soff = doff[u] = (size_t)id * sizeof(U);
+            } else {
+                I row = id / upr, col = id - row * upr;
+                I j = row % e1, t = row / e1;
+                I k = t % e2, l = t / e2;
+                soff = (size_t)col * sizeof(U) + (size_t)j * g.sp1 + (size_t)k * g.sp2 + (size_t)l * g.sp3;
+                doff[u] = (size_t)col * sizeof(U) + (size_t)j * g.dp1 + (size_t)k * g.dp2 + (size_t)l * g.dp3;
+            }
             v[u] = *reinterpret_cast<const U*>(src + soff);
         }
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) *reinterpret_cast<U*>(dst + doff[u]) = v[u];
+        for (int u = 0; u < UNROLL; ++u) store_as<U, S>(dst + doff[u], v[u]);
     }
     for (; idx < total; idx += stride) {
-        I row = idx / upr, col = idx - row * upr;
-        I j = row % e1, t = row / e1;
-        I k = t % e2, l = t / e2;
-        size_t soff = (size_t)col * sizeof(U) + (size_t)j * g.sp1 + (size_t)k * g.sp2 + (size_t)l * g.sp3;
-        size_t doff = (size_t)col * sizeof(U) + (size_t)j * g.dp1 + (size_t)k * g.dp2 + (size_t)l * g.dp3;
-        *reinterpret_cast<U*>(dst + doff) = *reinterpret_cast<const U*>(src + soff);
+        size_t soff, doff;
+        if (flat) {
+            soff = doff = (size_t)idx * sizeof(U);
+        } else {
+            I row = idx / upr, col = idx - row * upr;
+            I j = row % e1, t = row / e1;
+            I k = t % e2, l = t / e2;
+            soff = (size_t)col * sizeof(U) + (size_t)j * g.sp1 + (size_t)k * g.sp2 + (size_t)l * g.sp3;
+            doff = (size_t)col * sizeof(U) + (size_t)j * g.dp1 + (size_t)k * g.dp2 + (size_t)l * g.dp3;
+        }
+        U v = *reinterpret_cast<const U*>(src + soff);
+        store_as<U, S>(dst + doff, v);
     }
 }
 
-template <typename U>
+int copy_unroll() {
+    static int u = 0;
+    if (!u) {
+        const char* e = getenv("DAB_COPY_UNROLL");
+        u = (e && atoi(e) == 4) ? 4 : 8;
+    }
+    return u;
+}
+
+template <typename U, typename S>
 int32_t launch_copy(dab_ctx* ctx, char* dst, const char* src, const BoxGeom& g) {
     unsigned long long total = g.upr * g.e1 * g.e2 * g.e3;
     if (total == 0) return DAB_OK;
-    int grid = total < (1ull << 31) ? dab_persistent_grid(ctx, copy_box_kernel<U, unsigned int>, 256, (size_t)((total + 1023) / 1024))
-                                    : dab_persistent_grid(ctx, copy_box_kernel<U, unsigned long long>, 256, (size_t)((total + 1023) / 1024));
-    if (total < (1ull << 31)) {
-        copy_box_kernel<U, unsigned int><<<grid, 256, 0, ctx->stream>>>(dst, src, g, (unsigned int)total);
+    const bool small = total < (1ull << 31);
+    const int un = copy_unroll();
+    const size_t work = (size_t)((total + 256ull * un - 1) / (256ull * un));
+#define LAUNCH(I, UN)                                                                                          \
+    do {                                                                                                       \
+        int grid = dab_persistent_grid(ctx, copy_box_kernel<U, S, I, UN>, 256, work);                          \
+        copy_box_kernel<U, S, I, UN><<<grid, 256, 0, ctx->stream>>>(dst, src, g, (I)total);                    \
+    } while (0)
+    if (small) {
+        if (un == 4) LAUNCH(unsigned int, 4);
+        else LAUNCH(unsigned int, 8);
     } else {
-        copy_box_kernel<U, unsigned long long><<<grid, 256, 0, ctx->stream>>>(dst, src, g, total);
+        if (un == 4) LAUNCH(unsigned long long, 4);
+        else LAUNCH(unsigned long long, 8);
     }
+#undef LAUNCH
     DAB_LAUNCHED(ctx);
     return DAB_OK;
+}
+
+template <typename U>
+int32_t launch_copy_s(dab_ctx* ctx, char* dst, const char* src, const BoxGeom& g, size_t svec) {
+    if (svec >= sizeof(U)) return launch_copy<U, U>(ctx, dst, src, g);
+    if constexpr (sizeof(U) > 8)
+        if (svec == 8) return launch_copy<U, long long>(ctx, dst, src, g);
+    if constexpr (sizeof(U) > 4)
+        if (svec == 4) return launch_copy<U, int>(ctx, dst, src, g);
+    if constexpr (sizeof(U) > 2)
+        if (svec == 2) return launch_copy<U, short>(ctx, dst, src, g);
+    if constexpr (sizeof(U) > 1) return launch_copy<U, char>(ctx, dst, src, g);
+    return launch_copy<U, U>(ctx, dst, src, g);
+}
+
+size_t pow2_align(size_t bits) {
+    size_t v = 16;
+    while (v > 1 && (bits & (v - 1))) v >>= 1;
+    return v;
+}
+
+// rows of row_bytes bytes; e[] rows with pitches; load unit from the source geometry, store unit from the destination's
+int32_t copy_rows(dab_ctx* ctx, char* t, const char* s, size_t row_bytes, const size_t e[3], const long long spp[3], const long long dpp[3]) {
+    size_t sbits = (size_t)(uintptr_t)s | row_bytes, dbits = (size_t)(uintptr_t)t | row_bytes;
+    for (int d = 0; d < 3; ++d)
+        if (e[d] > 1) {
+            sbits |= (size_t)spp[d];
+            dbits |= (size_t)dpp[d];
+        }
+    const size_t lvec = pow2_align(sbits), svec = pow2_align(dbits);
+    BoxGeom g;
+    g.upr = row_bytes / lvec;
+    g.e1 = e[0];
+    g.e2 = e[1];
+    g.e3 = e[2];
+    g.sp1 = spp[0]; g.sp2 = spp[1]; g.sp3 = spp[2];
+    g.dp1 = dpp[0]; g.dp2 = dpp[1]; g.dp3 = dpp[2];
+    switch (lvec) {
+        case 16: return launch_copy_s<int4>(ctx, t, s, g, svec);
+        case 8: return launch_copy_s<long long>(ctx, t, s, g, svec);
+        case 4: return launch_copy_s<int>(ctx, t, s, g, svec);
+        case 2: return launch_copy_s<short>(ctx, t, s, g, svec);
+        default: return launch_copy_s<char>(ctx, t, s, g, svec);
+    }
 }
 
 }  // namespace
@@ -95,14 +183,13 @@ int32_t dab_copy_box(dab_ctx* ctx, int32_t elem_bytes, void* dst, const size_t d
         t += dst_off[d] * dp[d];
     }
     // collapse: a dim that spans both arrays entirely merges into the run below it
-    size_t ext[4] = {extent[0], extent[1], extent[2], extent[3]};
-    size_t row_bytes = ext[0] * es;
-    size_t e[3] = {ext[1], ext[2], ext[3]};
+    size_t row_bytes = extent[0] * es;
+    size_t e[3] = {extent[1], extent[2], extent[3]};
     long long spp[3] = {(long long)sp[1], (long long)sp[2], (long long)sp[3]};
     long long dpp[3] = {(long long)dp[1], (long long)dp[2], (long long)dp[3]};
     int nd = 3;
-    while (nd > 0 && (size_t)spp[0] == row_bytes && (size_t)dpp[0] == row_bytes) {
-        row_bytes *= e[0];
+    while (nd > 0 && ((size_t)spp[0] == row_bytes && (size_t)dpp[0] == row_bytes || e[0] == 1)) {
+        if (e[0] > 1) row_bytes *= e[0];
         for (int d = 0; d + 1 < nd; ++d) {
             e[d] = e[d + 1];
             spp[d] = spp[d + 1];
@@ -113,27 +200,24 @@ int32_t dab_copy_box(dab_ctx* ctx, int32_t elem_bytes, void* dst, const size_t d
         dpp[nd - 1] = 0;
         --nd;
     }
-    // widest unit dividing every address component
-    size_t align = (size_t)((uintptr_t)s | (uintptr_t)t | row_bytes);
-    for (int d = 0; d < 3; ++d)
-        if (e[d] > 1) align |= (size_t)spp[d] | (size_t)dpp[d];
-    size_t vec = 16;
-    while (vec > 1 && (align & (vec - 1))) vec >>= 1;
-    if (vec > 16) vec = 16;
-    BoxGeom g;
-    g.upr = row_bytes / vec;
-    g.e1 = e[0];
-    g.e2 = e[1];
-    g.e3 = e[2];
-    g.sp1 = spp[0]; g.sp2 = spp[1]; g.sp3 = spp[2];
-    g.dp1 = dpp[0]; g.dp2 = dpp[1]; g.dp3 = dpp[2];
-    switch (vec) {
-        case 16: return launch_copy<int4>(ctx, t, s, g);
-        case 8: return launch_copy<long long>(ctx, t, s, g);
-        case 4: return launch_copy<int>(ctx, t, s, g);
-        case 2: return launch_copy<short>(ctx, t, s, g);
-        default: return launch_copy<char>(ctx, t, s, g);
+    if (nd == 0 && row_bytes >= 4096) {
+        // contiguous slab: peel so that the SOURCE body is 16-byte aligned (peer loads stay 16 B wide)
+        size_t head = (16 - ((uintptr_t)s & 15)) & 15;
+        head -= head % es;  // stay on element boundaries (es divides 16)
+        if (head) {
+            int32_t st = copy_rows(ctx, t, s, head, e, spp, dpp);
+            if (st != DAB_OK) return st;
+        }
+        size_t body = (row_bytes - head) & ~(size_t)15;
+        if (body) {
+            int32_t st = copy_rows(ctx, t + head, s + head, body, e, spp, dpp);
+            if (st != DAB_OK) return st;
+        }
+        size_t tail = row_bytes - head - body;
+        if (tail) return copy_rows(ctx, t + head + body, s + head + body, tail, e, spp, dpp);
+        return DAB_OK;
     }
+    return copy_rows(ctx, t, s, row_bytes, e, spp, dpp);
 }
 
 }  // extern "C"

@@ -120,6 +120,16 @@ class Runtime:
         if ptr:
             _lib.call("dab_free", self.ctx, C.c_void_p(ptr))
 
+    def alloc_temp(self, nbytes: int) -> int:
+        """Stream-ordered temporary (cudaMallocAsync pool): no synchronisation, not IPC-exportable."""
+        p = C.c_void_p()
+        _lib.call("dab_alloc_async", self.ctx, int(nbytes), C.byref(p))
+        return int(p.value)
+
+    def free_temp(self, ptr: int):
+        if ptr:
+            _lib.call("dab_free_async", self.ctx, C.c_void_p(ptr))
+
     def launches(self) -> int:
         n = C.c_uint64(0)
         _lib.call("dab_launch_count", self.ctx, C.byref(n))

@@ -126,6 +126,9 @@ int32_t dab_event_destroy(dab_ctx* ctx, void* event);
  * src/darray.jl:47-49). */
 int32_t dab_alloc(dab_ctx* ctx, size_t nbytes, void** dptr);
 int32_t dab_free(dab_ctx* ctx, void* dptr);
+/* stream-ordered temporaries (cudaMallocAsync pool; ~1 us, no synchronisation; not IPC-exportable) */
+int32_t dab_alloc_async(dab_ctx* ctx, size_t nbytes, void** dptr);
+int32_t dab_free_async(dab_ctx* ctx, void* dptr);
 int32_t dab_host_alloc(dab_ctx* ctx, size_t nbytes, void** hptr); /* pinned staging */
 int32_t dab_host_free(dab_ctx* ctx, void* hptr);
 /* distribute(A) / Array(d) per chunk (src/darray.jl:544-555, 574-582): async on the ctx stream

@@ -61,8 +61,8 @@ report("DArray sum(A, dims=1) API, 1 worker", 4 * R * Cc, timed(lambda: dab.sum(
 n = 1 << 28
 src = dab.B200Array.empty(rt, (n + 64,), F32)
 dst = dab.B200Array.empty(rt, (n + 64,), F32)
-cp = lambda so, do, ext, ss, ds, es=4: _lib.call("dab_copy_box", rt.ctx, es, C.c_void_p(dst.ptr), _lib.sz4(ds), _lib.sz4(do), C.c_void_p(src.ptr), _lib.sz4(ss),
-                                                  _lib.sz4(so), _lib.sz4(ext))
+cp = lambda so, do, ext, ss, ds, es=4: _lib.call("dab_copy_box", rt.ctx, es, C.c_void_p(dst.ptr), _lib.sz4(ds), _lib.sz4(list(do) + [0] * (4 - len(do))), C.c_void_p(src.ptr), _lib.sz4(ss),
+                                                  _lib.sz4(list(so) + [0] * (4 - len(so))), _lib.sz4(ext))
 report("copy_box contiguous aligned 1 GiB (moved bytes)", 4 * n, timed(lambda: cp([0], [0], [n], [n + 64], [n + 64])))
 report("copy_box contiguous src+4B misaligned", 4 * n, timed(lambda: cp([1], [0], [n], [n + 64], [n + 64])))
 report("copy_box 2-D strided 8192x8192 of 16384 rows", 4 * 8192 * 8192, timed(lambda: cp([1024, 0], [0, 0], [8192, 8192], [16384, 8192 * 2], [8192, 8192])))

@@ -119,6 +119,7 @@ def main():
     ap.add_argument("--log2n", type=int, default=30, help="log2 of the elements per GPU (default 2^30 = 4 GiB chunk)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,6 +238,37 @@ def main():
     except Exception as ex:  # never lose the main line because of the e2e leg
         e2e = {"value": None, "unit": "GB/s", "error": repr(ex)[:200]}
 
+    # ---- extras (not part of `value`): BASELINE configs 4 and 5 at this N
+    extras = {}
+    if not args.no_extras:
+        try:
+            g = dab.defaultdist((65536, 65536), world)                   # (2,4) at N=8
+            dimsA = (32768 * g[0], 16384 * g[1])                         # 32768 x 16384 Float32 (2 GiB) per GPU; exactly 65536^2 at N=8
+            A = dab.drand(dimsA, dtype=np.float32, seed=SEED + 1)
+            reps = 10
+            ms_d, _ = timed(lambda: dab.sum(A, dims=1).close(), reps)    # within-chunk kernel + between-phase exchange + R allocation
+            ms_d = max_over_ranks(ms_d)
+            extras["sum_dims1"] = {"GBs": 4.0 * dimsA[0] * dimsA[1] * reps / (ms_d * 1e-3) / 1e9, "dims": list(dimsA), "grid": list(g),
+                                   "ms": ms_d / reps, "bytes_per_elem": 4,
+                                   "what": "sum(A, dims=1): per-chunk column reduction + partial-slab exchange to the fibre owners (NCCL send/recv)"}
+            if world > 1:
+                A.share()
+                rt.barrier()
+                nxt = A.layout.pids[(A.layout.pids.index(rt.myid()) + 1) % world]
+                I = A.layout.localindices(nxt)
+                sub = A[I[0][0] - 1:I[0][1], I[1][0] - 1:I[1][0] - 1 + 2048]   # 32768 x 2048 Float32 = 256 MiB inside the neighbour's chunk
+                dst = dab.B200Array.empty(rt, (32768, 2048), np.float32)
+                sub.copy_to(dst)
+                ms_h, _ = timed(lambda: sub.copy_to(dst), reps)
+                ms_h = max_over_ranks(ms_h)
+                extras["halo_getindex"] = {"GBs_per_reader": 4.0 * 32768 * 2048 * reps / (ms_h * 1e-3) / 1e9, "slab_bytes": 4 * 32768 * 2048,
+                                           "peak_GBs": 770.0, "what": "every rank pulls a 256 MiB slab of its right neighbour's chunk over NVLink (CUDA-IPC peer loads)"}
+                extras["halo_getindex"]["frac_of_peak"] = extras["halo_getindex"]["GBs_per_reader"] / 770.0
+                dst.free()
+            A.close()
+        except Exception as ex:
+            extras["error"] = repr(ex)[:300]
+
     line = {"metric": "GB/s for map! and sum on Float32 DArray", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -251,7 +283,7 @@ def main():
             "kernels": {"broadcast_GBs_per_gpu": bc_gbs, "sum_GBs_per_gpu": sum_gbs, "maximum_GBs_per_gpu": max_gbs,
                         "broadcast_frac": bc_gbs / peak, "sum_frac": sum_gbs / peak, "maximum_frac": max_gbs / peak,
                         "ms_broadcast": ms_bc / args.steps, "ms_sum": ms_sum / args.steps},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clk, "parity_spot_check": ok, "sum": float(s)}
+            "e2e": e2e, "extras": extras, "gpu_launches": launches, "clocks": clk, "parity_spot_check": ok, "sum": float(s)}
     if rank == 0:
         if world == 1 and not args.no_cpu:
             try:

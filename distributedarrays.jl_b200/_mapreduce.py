@@ -58,6 +58,20 @@ def classify_map(f: Optional[Callable], dtype) -> Tuple[Optional[int], Optional[
         return _lib.MAP_ABS2, None, e
     if e.op in _CMPMAP:
         l, r = e.args
+
+        def unpromote(side, const):
+            """``x > 0.5`` with x::Float32 promotes x to Float64 (Julia); when the Float64 constant is exactly representable in
+            x's type the comparison is equivalent in that type, and the predicate kernel can run on the raw chunk."""
+            if side.op == "convert" and side.args[0].op == "arg" and side.args[0].jt == tag and const.op == "const":
+                c = const.val
+                if tag == "f32" and const.jt == "f64" and float(np.float32(c)) == c:
+                    return side.args[0], Expr("const", (), tag, c)
+                if tag in ("i32", "i64") and const.jt in ("i64",) and side.jt == "i64":
+                    return side.args[0], Expr("const", (), tag, c) if -2**31 <= c < 2**31 or tag == "i64" else (side, const)
+            return side, const
+
+        l, r = unpromote(l, r)
+        r, l = unpromote(r, l)
         if l.op == "arg" and r.op == "const" and l.jt == tag:
             return _CMPMAP[e.op], np.asarray(r.val, dtype=np.dtype(dtype)), e
         if r.op == "arg" and l.op == "const" and r.jt == tag:

@@ -279,21 +279,32 @@ int32_t dab_d2h_2d(dab_ctx* ctx, void* hptr, size_t hpitch, const void* dptr, si
 template <typename T, typename Gen>
 __global__ void __launch_bounds__(256) dab_generate_kernel(T* __restrict__ x, size_t n, Gen gen) {
     constexpr int VPT = 16 / sizeof(T);
+    constexpr int UNROLL = 4;
     size_t head = ((16 - ((uintptr_t)x & 15)) & 15) / sizeof(T);
     if (head > n) head = n;
-    size_t nvec = (n - head) / VPT;
+    const size_t nvec = (n - head) / VPT;
     int4* xv = reinterpret_cast<int4*>(x + head);
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    constexpr size_t TILE = 256 * UNROLL;
+    const size_t ntiles = nvec / TILE;
+    if (blockIdx.x < ntiles) {  // flat grid: one CTA per 16 KiB tile (see ew1_kernel)
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const size_t i = (size_t)blockIdx.x * TILE + (size_t)u * 256 + threadIdx.x;
+            Pack<T> p;
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) p.v[k] = gen(head + i * VPT + k);
+            st_stream(xv + i, as_int4(p));
+        }
+        return;
+    }
+    for (size_t i = ntiles * TILE + threadIdx.x; i < nvec; i += 256) {
         Pack<T> p;
 #pragma unroll
         for (int k = 0; k < VPT; ++k) p.v[k] = gen(head + i * VPT + k);
         st_stream(xv + i, as_int4(p));
     }
-    if (blockIdx.x == gridDim.x - 1) {
-        for (size_t i = threadIdx.x; i < head; i += blockDim.x) x[i] = gen(i);
-        for (size_t i = head + nvec * VPT + threadIdx.x; i < n; i += blockDim.x) x[i] = gen(i);
-    }
+    for (size_t i = threadIdx.x; i < head; i += blockDim.x) x[i] = gen(i);
+    for (size_t i = head + nvec * VPT + threadIdx.x; i < n; i += blockDim.x) x[i] = gen(i);
 }
 
 template <typename T>
@@ -312,9 +323,11 @@ struct RandGen {
 template <typename T, typename Gen>
 static int32_t launch_generate(dab_ctx* ctx, T* x, size_t n, Gen gen) {
     if (n == 0) return DAB_OK;
-    size_t nvec = n / (16 / sizeof(T)) + 1;
-    int grid = dab_persistent_grid(ctx, dab_generate_kernel<T, Gen>, 256, (nvec + 255) / 256);
-    dab_generate_kernel<T, Gen><<<grid, 256, 0, ctx->stream>>>(x, n, gen);
+    size_t head = ((16 - ((uintptr_t)x & 15)) & 15) / sizeof(T);
+    if (head > n) head = n;
+    size_t grid = ((n - head) / (16 / sizeof(T))) / 1024 + 1;
+    if (grid > 0x7fffffffull) return dab_fail(ctx, DAB_ERR_ARG, "array too large for one launch");
+    dab_generate_kernel<T, Gen><<<(unsigned)grid, 256, 0, ctx->stream>>>(x, n, gen);
     DAB_LAUNCHED(ctx);
     return DAB_OK;
 }

@@ -246,18 +246,43 @@ std::string build_source(const char* expr, int32_t out_dt, int nargs, const int3
     s += "#define DAB_EXPR (";
     s += expr;
     s += ")\n";
-    // ---- linear kernel
+    // ---- linear kernel: flat grid, one CTA per 2 x 256 vectors of 4 elements (same shape as ew1_kernel: measured 6.9 vs 6.6 TB/s
+    // for the persistent grid-stride form); the extra last CTA takes the remainder vectors and the scalar tail
     s += "extern \"C\" __global__ void __launch_bounds__(256) dab_bc_linear(BcParams p) {\n"
          "  const u64 n = p.shape[0] * p.shape[1] * p.shape[2] * p.shape[3];\n"
          "  const u64 nv = n / 4;\n"
+         "  const u64 ntiles = nv / 512;\n"
          "  OUT_T* o = (OUT_T*)p.out;\n";
     for (int k = 0; k < nargs; ++k) {
         std::string K = std::to_string(k);
         if (is_arr[k]) s += "  const T" + K + "* q" + K + " = (const T" + K + "*)p.ptr[" + K + "];\n";
         else s += "  const T" + K + " a" + K + " = bits_as<T" + K + ">(p.scalar[" + K + "]);\n";
     }
-    s += "  const u64 stride = (u64)gridDim.x * blockDim.x;\n"
-         "  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {\n";
+    s += "  if ((u64)blockIdx.x < ntiles) {\n"
+         "    const u64 i0 = (u64)blockIdx.x * 512 + threadIdx.x;\n";
+    for (int k = 0; k < nargs; ++k)
+        if (is_arr[k]) {
+            std::string K = std::to_string(k);
+            s += "    const VecN<T" + K + ", 4> v" + K + "_0 = *(const VecN<T" + K + ", 4>*)(q" + K + " + 4 * i0);\n";
+            s += "    const VecN<T" + K + ", 4> v" + K + "_1 = *(const VecN<T" + K + ", 4>*)(q" + K + " + 4 * (i0 + 256));\n";
+        }
+    for (int u = 0; u < 2; ++u) {
+        std::string U = std::to_string(u);
+        s += "    { VecN<OUT_T, 4> r;\n"
+             "#pragma unroll\n"
+             "      for (int j = 0; j < 4; ++j) {\n";
+        for (int k = 0; k < nargs; ++k)
+            if (is_arr[k]) {
+                std::string K = std::to_string(k);
+                s += "        const T" + K + " a" + K + " = v" + K + "_" + U + ".v[j];\n";
+            }
+        s += "        r.v[j] = (OUT_T)DAB_EXPR;\n"
+             "      }\n"
+             "      *(VecN<OUT_T, 4>*)(o + 4 * (i0 + " + std::to_string(256 * u) + ")) = r; }\n";
+    }
+    s += "    return;\n"
+         "  }\n"
+         "  for (u64 i = ntiles * 512 + threadIdx.x; i < nv; i += blockDim.x) {\n";
     for (int k = 0; k < nargs; ++k)
         if (is_arr[k]) {
             std::string K = std::to_string(k);
@@ -275,15 +300,13 @@ std::string build_source(const char* expr, int32_t out_dt, int nargs, const int3
          "    }\n"
          "    *(VecN<OUT_T, 4>*)(o + 4 * i) = r;\n"
          "  }\n"
-         "  if (blockIdx.x == gridDim.x - 1) {\n"
-         "    for (u64 i = nv * 4 + threadIdx.x; i < n; i += blockDim.x) {\n";
+         "  for (u64 i = nv * 4 + threadIdx.x; i < n; i += blockDim.x) {\n";
     for (int k = 0; k < nargs; ++k)
         if (is_arr[k]) {
             std::string K = std::to_string(k);
-            s += "      const T" + K + " a" + K + " = q" + K + "[i];\n";
+            s += "    const T" + K + " a" + K + " = q" + K + "[i];\n";
         }
-    s += "      o[i] = (OUT_T)DAB_EXPR;\n"
-         "    }\n"
+    s += "    o[i] = (OUT_T)DAB_EXPR;\n"
          "  }\n"
          "}\n";
     // ---- general (strided / extruded) kernel
@@ -439,8 +462,9 @@ int32_t dab_broadcast_expr(dab_ctx* ctx, const char* expr, int32_t out_dtype, vo
     Driver& drv = driver();
     void* args[] = {&p};
     CUfunction fn = linear ? comp.linear : comp.general;
-    size_t work = linear ? (n / 4 + 255) / 256 : (n + 255) / 256;
-    int grid = dab_grid_for(ctx, work, linear ? comp.occ_linear : comp.occ_general);
+    size_t work = (n + 255) / 256;
+    size_t grid = linear ? (n / 4) / 512 + 1 : (size_t)dab_grid_for(ctx, work, comp.occ_general);
+    if (grid > 0x7fffffffull) return dab_fail(ctx, DAB_ERR_ARG, "array too large for one launch");
     CUresult cr = drv.LaunchKernel(fn, (unsigned)grid, 1, 1, 256, 1, 1, 0, (CUstream)ctx->stream, args, nullptr);
     if (cr != CUDA_SUCCESS) {
         const char* es = "?";

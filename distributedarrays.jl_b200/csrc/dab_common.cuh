@@ -35,6 +35,7 @@ struct dab_ctx {
     int mbox_ranks;         // 0 = not attached
     unsigned long long mbox_seq;
     int fuse_op;            // >= 0: the next launch_reduce appends the cross-rank combine for this DAB_* op
+    struct dab_alloc_cache* cache;  // size-bucketed reuse of small cudaMalloc blocks (dab_core.cu)
     char err[512];
 };
 

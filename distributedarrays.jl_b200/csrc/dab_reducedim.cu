@@ -9,7 +9,8 @@
 //       - long runs : one CTA per (run, split); 16-byte evict-first loads, 4 in flight per thread, per-run head/tail peel
 //         (run starts are not 16-byte aligned when reduce % (16/sizeof T) != 0); runs are split across CTAs when there are too
 //         few of them to fill 148 SMs, and a tiny second kernel folds the splits in order (deterministic, no atomics).
-//       - short runs: one warp per run, lanes strided (coalesced 128 B per warp load).
+//       - short / medium runs: a sub-warp group of G lanes per run (G = #16-byte vectors in the run, <= 32), so a warp streams
+//         32/G consecutive runs with 512 contiguous bytes per load instruction; flat grid.
 //   * inner  > 1  (reduce over a non-leading dim): threads map along i (coalesced), each walks r with 8 independent loads in
 //     flight; r is split across CTAs when inner*outer alone cannot fill the machine, then folded in order.
 // Accumulators are wide (fp64 / int64) exactly as in dab_reduce.cu; float results are rounded once at the end.
@@ -93,31 +94,83 @@ __global__ void __launch_bounds__(RD_THREADS) rdim_lead_cta_kernel(const T* __re
     }
 }
 
-// ---- leading-dims, short runs: one warp per run ----------------------------------------------------------------------------
-template <typename T, typename Map, typename R, typename Out>
-__global__ void __launch_bounds__(RD_THREADS) rdim_lead_warp_kernel(const T* __restrict__ x, size_t red, size_t outer, Map map,
-                                                                     Out* __restrict__ out, int accumulate) {
+// ---- leading-dims, short / medium runs: one sub-warp GROUP of G lanes per run --------------------------------------------------
+// G lanes cooperate on one contiguous run; a warp therefore streams 32/G consecutive runs per step, i.e. 32 lanes x 16 B = 512
+// contiguous bytes per load instruction when the runs are 16-byte aligned multiples of a vector (VEC == true), 128 B otherwise.
+// Flat grid: CTA b owns groups_per_cta * KRUNS consecutive runs (fixed mapping, deterministic).
+template <typename T, typename Map, typename R, typename Out, int G, bool VEC>
+__global__ void __launch_bounds__(RD_THREADS) rdim_lead_group_kernel(const T* __restrict__ x, size_t red, size_t outer, Map map,
+                                                                      Out* __restrict__ out, int accumulate, int kruns) {
     using A = typename R::A;
-    const int lane = threadIdx.x & 31;
-    const size_t warp = ((size_t)blockIdx.x * RD_THREADS + threadIdx.x) >> 5;
-    const size_t nwarps = ((size_t)gridDim.x * RD_THREADS) >> 5;
-    for (size_t seg = warp; seg < outer; seg += nwarps) {
-        const T* p = x + seg * red;
+    using V = typename Map::V;
+    constexpr int VPT = 16 / sizeof(T);
+    constexpr int GROUPS = RD_THREADS / G;
+    const int gl = threadIdx.x % G;           // lane inside the group
+    const int grp = threadIdx.x / G;          // group inside the CTA
+    const size_t first = ((size_t)blockIdx.x * GROUPS + grp) * (size_t)kruns;
+#pragma unroll 1
+    for (int kk = 0; kk < kruns; ++kk) {
+        const size_t seg = first + kk;
+        // groups past the last run stay in the loop with an empty run: the full-mask shuffles below need every lane of the warp
+        const bool active = seg < outer;
+        const size_t nred = active ? red : 0;
+        const T* p = x + (active ? seg : 0) * red;
         A acc = R::identity();
-        size_t j = lane;
-        for (; j + 96 < red; j += 128) {  // 4 independent loads in flight
-            T a0 = p[j], a1 = p[j + 32], a2 = p[j + 64], a3 = p[j + 96];
-            auto t = R::tile(R::tile(map(a0), map(a1)), R::tile(map(a2), map(a3)));
-            acc = R::comb(acc, R::lift(t));
-        }
-        for (; j < red; j += 32) acc = R::comb(acc, R::lift(map(p[j])));
+        if (VEC) {
+            const int4* pv = reinterpret_cast<const int4*>(p);
+            const size_t nvec = nred / VPT;
+            size_t j = gl;
+            for (; j + 3 * G < nvec; j += 4 * G) {   // 4 independent 16-byte loads in flight
+                int4 r[4];
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) acc = R::comb(acc, shfl_down<A>(acc, d));
-        if (lane == 0) {
+                for (int u = 0; u < 4; ++u) r[u] = ld_stream(pv + j + (size_t)u * G);
+                V tv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    Pack<T> pk = as_pack<T>(r[u]);
+                    V m = map(pk.v[0]);
+#pragma unroll
+                    for (int k = 1; k < VPT; ++k) m = R::tile(m, map(pk.v[k]));
+                    tv[u] = m;
+                }
+                acc = R::comb(acc, R::lift(R::tile(R::tile(tv[0], tv[1]), R::tile(tv[2], tv[3]))));
+            }
+            for (; j < nvec; j += G) {
+                Pack<T> pk = as_pack<T>(ld_stream(pv + j));
+                V m = map(pk.v[0]);
+#pragma unroll
+                for (int k = 1; k < VPT; ++k) m = R::tile(m, map(pk.v[k]));
+                acc = R::comb(acc, R::lift(m));
+            }
+        } else {
+            size_t j = gl;
+            for (; j + 3 * G < nred; j += 4 * G) {
+                T a0 = p[j], a1 = p[j + G], a2 = p[j + 2 * G], a3 = p[j + 3 * G];
+                acc = R::comb(acc, R::lift(R::tile(R::tile(map(a0), map(a1)), R::tile(map(a2), map(a3)))));
+            }
+            for (; j < nred; j += G) acc = R::comb(acc, R::lift(map(p[j])));
+        }
+#pragma unroll
+        for (int d = G / 2; d > 0; d >>= 1) acc = R::comb(acc, shfl_down<A>(acc, d));  // stays inside the G-lane group
+        if (active && gl == 0) {
             if (accumulate) acc = R::comb((A)out[seg], acc);
             out[seg] = narrow<A, Out>(acc);
         }
     }
+}
+
+template <typename T, typename Map, typename R, typename Out, int G>
+int32_t launch_group(dab_ctx* ctx, const T* x, size_t red, size_t outer, Map map, Out* out, int accumulate) {
+    constexpr int VPT = 16 / sizeof(T);
+    const bool vec = (red % VPT == 0) && (((uintptr_t)x & 15) == 0);
+    const int groups = RD_THREADS / G;
+    int kruns = 4;
+    size_t grid = (outer + (size_t)groups * kruns - 1) / ((size_t)groups * kruns);
+    if (grid > 0x7fffffffull) return dab_fail(ctx, DAB_ERR_ARG, "too many runs for one launch");
+    if (vec) rdim_lead_group_kernel<T, Map, R, Out, G, true><<<(unsigned)grid, RD_THREADS, 0, ctx->stream>>>(x, red, outer, map, out, accumulate, kruns);
+    else rdim_lead_group_kernel<T, Map, R, Out, G, false><<<(unsigned)grid, RD_THREADS, 0, ctx->stream>>>(x, red, outer, map, out, accumulate, kruns);
+    DAB_LAUNCHED(ctx);
+    return DAB_OK;
 }
 
 // ---- non-leading dim: threads along i, loop over r --------------------------------------------------------------------------
@@ -199,12 +252,15 @@ int32_t launch_rdim(dab_ctx* ctx, const T* x, size_t inner, size_t red, size_t o
     using A = typename R::A;
     const size_t target_ctas = (size_t)ctx->sm_count * 8;
     if (inner == 1) {
-        if (red < 2048 && outer >= (size_t)ctx->sm_count) {
-            size_t warps_needed = outer;
-            int grid = dab_persistent_grid(ctx, rdim_lead_warp_kernel<T, Map, R, Out>, RD_THREADS, (warps_needed + 7) / 8);
-            rdim_lead_warp_kernel<T, Map, R, Out><<<grid, RD_THREADS, 0, ctx->stream>>>(x, red, outer, map, out, accumulate);
-            DAB_LAUNCHED(ctx);
-            return DAB_OK;
+        if (red < 4096 && outer >= (size_t)ctx->sm_count * 8) {
+            // lanes per run: as many as the run has 16-byte vectors (power of two, <= 32)
+            constexpr int VPT = 16 / sizeof(T);
+            size_t units = red / VPT;
+            if (units >= 32) return launch_group<T, Map, R, Out, 32>(ctx, x, red, outer, map, out, accumulate);
+            if (units >= 16) return launch_group<T, Map, R, Out, 16>(ctx, x, red, outer, map, out, accumulate);
+            if (units >= 8) return launch_group<T, Map, R, Out, 8>(ctx, x, red, outer, map, out, accumulate);
+            if (units >= 4) return launch_group<T, Map, R, Out, 4>(ctx, x, red, outer, map, out, accumulate);
+            return launch_group<T, Map, R, Out, 2>(ctx, x, red, outer, map, out, accumulate);
         }
         // split long runs when there are too few of them; keep every split >= 16 KiB of input
         size_t max_split = red * sizeof(T) / 16384;

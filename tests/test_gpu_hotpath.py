@@ -339,7 +339,12 @@ def test_reference_sum_dims_errors(dab, rt8):
 
 
 @pytest.mark.parametrize("shape,dims", [((4096, 300), 1), ((300, 4096), 2), ((5, 7, 9), 2), ((100003, 3), 1), ((3, 100003), 2), ((33, 1), 1),
-                                        ((1 << 21,), 1)])
+                                        ((1 << 21,), 1),
+                                        # sub-warp-group kernel: G = 32/16/8/4/2 lanes per run, vector and scalar variants, ragged tails
+                                        ((1000, 5000), 1), ((1001, 3000), 1), ((64, 200000), 1), ((36, 100001), 1), ((20, 100001), 1),
+                                        ((7, 50000), 1), ((2, 40000), 1), ((3000, 2400), 1),
+                                        # strided kernel with small inner / split r
+                                        ((64, 128, 700), 2), ((3, 100000, 2), 2), ((1030, 5000), 2)])
 def test_reducedim_shapes_f32(dab, rt2, shape, dims):
     n = int(np.prod(shape))
     A = orc.rand_u01(21, 0, n).reshape(shape, order="F")
@@ -347,6 +352,40 @@ def test_reducedim_shapes_f32(dab, rt2, shape, dims):
     got = dab.to_array(dab.sum(DA, dims=dims))
     want = A.astype(np.float64).sum(axis=dims - 1, keepdims=True)
     assert got.dtype == np.float32 and np.allclose(got, want, rtol=TOL, atol=0)
+    mx = dab.to_array(dab.maximum(DA, dims=dims))
+    assert np.array_equal(mx, A.max(axis=dims - 1, keepdims=True))
+    Ai = (A * 1000).astype(np.int32)
+    si = dab.to_array(dab.sum(dab.distribute(Ai), dims=dims))
+    assert si.dtype == np.int64 and np.array_equal(si, Ai.astype(np.int64).sum(axis=dims - 1, keepdims=True))
+
+
+def test_full_size_8gib_chunk(dab, rt1):
+    """north_star: "an 8 GiB-per-chunk Float32 DArray" = 2^31 elements: 64-bit indexing, in-place map!, sum, maximum."""
+    n = 1 << 31
+    if rt1.device_info()["free_bytes"] < 18 * (1 << 30):
+        pytest.skip("not enough free HBM")
+    from darray_b200 import _lib
+
+    x = dab.drand((n,), dtype=F32, seed=77)
+    s0 = float(dab.sum(x))
+    assert abs(s0 / n - 0.5) < 1e-4
+    dab.map_inplace(lambda v: 2 * v + 1, x, x)                      # config-1 function at the north-star chunk size
+    ch = x.chunks[1]
+    w = 4096
+    host = np.empty(w, dtype=F32)
+    for off in (0, (1 << 30) - 7, (1 << 31) - w, 3 * (1 << 29) + 12345):
+        _lib.call("dab_d2h", rt1.ctx, C.c_void_p(host.ctypes.data), C.c_void_p(ch.ptr + 4 * off), 4 * w)
+        rt1.sync()
+        assert np.array_equal(host, F32(2) * orc.rand_u01(77, off, w) + F32(1))
+    s1 = float(dab.sum(x))
+    assert abs(s1 - (2 * s0 + n)) <= 2e-6 * s1
+    assert 1 <= dab.minimum(x) and dab.maximum(x) < 3
+    # exact check of the last 2^24 elements (offset near 2^31: exercises the upper index range of the reduce kernel)
+    out = np.zeros(2, dtype=np.uint64)
+    off = n - (1 << 24)
+    _lib.call("dab_reduce_host", rt1.ctx, _lib.F32, _lib.SUM, _lib.MAP_ID, None, C.c_void_p(ch.ptr + 4 * off), 1 << 24, C.c_void_p(out.ctypes.data))
+    exact = 2 * ocore.rand_ksum(77, off, 1 << 24) * 2.0 ** -24 + (1 << 24)
+    assert abs(out.view(np.float64)[1] - exact) <= 1e-9 * exact
 
 
 # ---------------------------------------------------------------------------------------------- K8 halo getindex / makelocal

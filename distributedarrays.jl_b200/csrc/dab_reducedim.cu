@@ -285,9 +285,11 @@ int32_t launch_rdim(dab_ctx* ctx, const T* x, size_t inner, size_t red, size_t o
         return DAB_OK;
     }
     size_t base_ctas = (inner * outer + RD_THREADS - 1) / RD_THREADS;
-    size_t max_split = red / 64;
+    // split r so that the work items fill >= 4 waves of the persistent grid (a 1.08-wave launch loses ~45 % to the tail), while
+    // every split keeps >= 256 rows so that the partial buffer stays < 1 % of the input
+    size_t max_split = red / 256;
     if (max_split < 1) max_split = 1;
-    size_t want = base_ctas >= target_ctas ? 1 : (target_ctas + base_ctas - 1) / base_ctas;
+    size_t want = base_ctas >= 4 * target_ctas ? 1 : (4 * target_ctas + base_ctas - 1) / base_ctas;
     int nsplit = (int)(want < max_split ? want : max_split);
     if (nsplit > 1024) nsplit = 1024;
     A* partials = nullptr;

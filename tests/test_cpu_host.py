@@ -228,3 +228,41 @@ def test_workers_run_cpu_baseline_smoke():
         x0, x1 = orc.affine_unfused(1.5, x0, 0.25), orc.affine_unfused(1.5, x1, 0.25)
     want = np.float32(ocore.sum_f32(x0) + ocore.sum_f32(x1))
     assert res == want
+
+
+# ------------------------------------------------------------------------------------------------ committed golden fixtures
+def test_golden_fixtures(dab):
+    import json
+
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))
+    assert orc.defaultdist_cuts(50, 4) == g["reference_literals"]["defaultdist_50_4"]["value"] == dab.cuts_for(50, 4)
+    assert repr(float(orc.julia_mapreduce(None, "+", np.full((100, 100), 1.1)))) == g["reference_literals"]["sum_fill_1p1_100x100_local"]["value"]
+    for key, bits in g["rand_u01_f32_bits"].items():
+        seed, start = [int(x[len(p):]) for x, p in zip(key.split("_"), ("seed", "start"))]
+        assert [int(v) for v in orc.rand_u01(seed, start, 16).view(np.uint32)] == bits
+        assert [int(v) for v in ocore.rand_u01_f32(seed, start, 16).view(np.uint32)] == bits
+    assert ocore.rand_ksum(1234, 0, 65536) == g["rand_u01_ksum"]["seed1234_start0_n65536"]
+    for key, lay in g["layouts"].items():
+        dims, npids = key.split("_np")
+        dims = tuple(int(x) for x in dims.split("x"))
+        assert list(dab.defaultdist(dims, int(npids))) == lay["grid"]
+        assert [dab.cuts_for(d, c) for d, c in zip(dims, lay["grid"])] == lay["cuts"]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` must print ONE JSON line with the contract keys, using only the CPU."""
+    import json
+    import subprocess
+    import sys
+
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"], capture_output=True,
+                       text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config",
+              "cpu_baseline", "e2e"):
+        assert k in j, k
+    assert j["impl"] == "reference" and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["value"] > 0
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["value"] == j["value"]

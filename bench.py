@@ -275,7 +275,9 @@ def main():
             "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "l2": "inputs (4 GiB/GPU) >> 126 MB L2, no flush needed", "grid": list(x.layout.grid),
-                       "combine": "NCCL all-gather of the P chunk results + ordered left fold" if world > 1 else "single chunk"},
+                       "combine": ("single chunk" if world == 1 else
+                                   "fused in the reduce kernel: peer-memory all-gather of the P chunk results over NVLink + ordered left fold"
+                                   if rt.fused_combine else "NCCL all-gather of the P chunk results + ordered left fold")},
             "roofline": {"bound": "hbm", "kernel": "ew1_kernel<float, AffineF<float>, 2>", "entry": bc_entry, "achieved": bc_gbs, "peak": peak,
                          "peak_kind": peak_kind, "unit": "GB/s", "frac": bc_gbs / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 2^30 elements, ncu --set full capture
@@ -295,6 +297,8 @@ def main():
                 line["cpu_baseline"] = {"value": None, "error": repr(ex)[:200]}
         print(json.dumps(line))
     fence()
+    dab.d_closeall()
+    rt.shutdown()
 
 
 if __name__ == "__main__":

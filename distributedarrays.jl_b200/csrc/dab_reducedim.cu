@@ -108,6 +108,38 @@ __global__ void __launch_bounds__(RD_THREADS) rdim_lead_group_kernel(const T* __
     const int gl = threadIdx.x % G;           // lane inside the group
     const int grp = threadIdx.x / G;          // group inside the CTA
     const size_t first = ((size_t)blockIdx.x * GROUPS + grp) * (size_t)kruns;
+    if (VEC && red / VPT <= (size_t)G && kruns == 4) {
+        // very short runs (at most one 16-byte vector per lane): issue the loads of all 4 runs of this group before reducing any
+        // of them, so that 4 independent requests per lane are in flight instead of one load -> shuffle chain at a time
+        const size_t nvec = red / VPT;
+        int4 r[4];
+        bool act[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const size_t seg = first + u;
+            act[u] = seg < outer && (size_t)gl < nvec;
+            if (act[u]) r[u] = ld_stream(reinterpret_cast<const int4*>(x + seg * red) + gl);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            A acc = R::identity();
+            if (act[u]) {
+                Pack<T> pk = as_pack<T>(r[u]);
+                V m = map(pk.v[0]);
+#pragma unroll
+                for (int k = 1; k < VPT; ++k) m = R::tile(m, map(pk.v[k]));
+                acc = R::lift(m);
+            }
+#pragma unroll
+            for (int d = G / 2; d > 0; d >>= 1) acc = R::comb(acc, shfl_down<A>(acc, d));
+            const size_t seg = first + u;
+            if (gl == 0 && seg < outer) {
+                if (accumulate) acc = R::comb((A)out[seg], acc);
+                out[seg] = narrow<A, Out>(acc);
+            }
+        }
+        return;
+    }
 #pragma unroll 1
     for (int kk = 0; kk < kruns; ++kk) {
         const size_t seg = first + kk;

@@ -182,6 +182,13 @@ class Runtime:
             self._ipc_cache.clear()
             _lib.lib().dab_shutdown(self.ctx)
             self.ctx = None
+        if self.dist is not None:
+            try:
+                if self.dist.is_initialized():
+                    self.dist.destroy_process_group()
+            except Exception:
+                pass
+            self.dist = None
         if _RT is self:
             _RT = None
 

@@ -154,6 +154,7 @@ def main():
     dab.d_closeall()
     rt.barrier()
     log("multi-gpu check passed on", P, "GPUs")
+    rt.shutdown()
 
 
 if __name__ == "__main__":

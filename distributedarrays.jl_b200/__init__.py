@@ -17,7 +17,8 @@ from ._darray import (B200Array, DArray, SubDArray, allowscalar, dab_dtype, np_d
                      dfill, distribute, dones, drand, dzeros, fill_, localindices, localpart, locate, makelocal, pinned_empty, procs,
                      registry_size, similar, to_array)
 from .layout import Layout, chunk_idxs, cuts_for, defaultdist, make_layout, slab_plan
-from ._mapreduce import all, any, count, extrema, mapreduce, mapreducedim, maximum, minimum, prod, reduce, sum  # noqa: A004
+from ._mapreduce import (all, any, axpy_, count, dot, extrema, isequal, mapreduce, mapreducedim, maximum, mean, minimum, norm,  # noqa: A004
+                         prod, reduce, rmul_, sum)
 from .runtime import Runtime, init, myid, nworkers, runtime, workers
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -84,6 +84,8 @@ _SIGS = {
     "dab_broadcast_expr": (_i32, [_vp, C.c_char_p, _i32, _vp, C.POINTER(_sz), C.POINTER(_sz), _i32, C.POINTER(_i32), _pvp,
                                   C.POINTER(_sz), C.POINTER(_u64)]),
     "dab_jit_compile_check": (_i32, [C.c_char_p, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_sz)]),
+    "dab_mapreduce_expr": (_i32, [_vp, C.c_char_p, _i32, _i32, _sz, _i32, C.POINTER(_i32), _pvp, C.POINTER(_u64), _vp]),
+    "dab_jit_compile_check_reduce": (_i32, [C.c_char_p, _i32, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_sz)]),
     "dab_reduce": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "dab_reduce_host": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "dab_reduce_result_dtype": (_i32, [_i32, _i32, _i32, C.POINTER(_i32)]),

@@ -90,17 +90,15 @@ def _result_dtype(dtype, op: int, mapc: int) -> np.dtype:
 # ---- whole-array reductions ------------------------------------------------------------------------------------------------
 
 
-def _chunk_partials(d: DArray, op: int, mapc: int, param) -> Tuple[np.ndarray, np.dtype]:
-    """One kernel per local chunk, the chunk results of ALL workers on every rank (bytes, 16 per worker, worker order)."""
+def _gather_slots(d: DArray, launch: Callable[[int, B200Array, int], None]) -> np.ndarray:
+    """Run ``launch(pid, chunk, slot_ptr)`` (one reduce kernel writing a 16-byte result slot) for every local chunk, then make
+    the slots of ALL workers visible on every rank: bytes, 16 per worker, in worker order."""
     rt = d.rt
-    code = dab_dtype(d.dtype)
     wpr = rt.workers_per_rank
     slots = B200Array.empty(rt, (16 * wpr,), np.uint8, temp=True)
-    pp = C.c_void_p(param.ctypes.data) if param is not None else None
     try:
         for pid, ch in d.chunks.items():
-            k = (pid - 1) % wpr
-            _lib.call("dab_reduce", rt.ctx, code, op, mapc, pp, C.c_void_p(ch.ptr), ch.size, C.c_void_p(slots.ptr + 16 * k))
+            launch(pid, ch, slots.ptr + 16 * ((pid - 1) % wpr))
         if rt.world > 1:
             allslots = B200Array.empty(rt, (16 * wpr * rt.world,), np.uint8, temp=True)
             _lib.call("dab_allgather", rt.ctx, C.c_void_p(slots.ptr), C.c_void_p(allslots.ptr), 16 * wpr)
@@ -111,7 +109,7 @@ def _chunk_partials(d: DArray, op: int, mapc: int, param) -> Tuple[np.ndarray, n
     finally:
         rt.sync()
         slots.free()
-    return host.view(np.uint8), _result_dtype(d.dtype, op, mapc)
+    return host.view(np.uint8)
 
 
 def _fold(host: np.ndarray, pids: Sequence[int], rdt: np.dtype, op: int):
@@ -125,41 +123,99 @@ def _fold(host: np.ndarray, pids: Sequence[int], rdt: np.dtype, op: int):
     return out[0], vals
 
 
-def _mapreduce_all(f, op, d: DArray, return_partials: bool = False):
-    opc = op if isinstance(op, int) else _op_code(op)
-    mapc, param, expr = classify_map(f, d.dtype)
-    src, tmp = d, None
-    if mapc is None:
-        # general f: materialise f.(d) with the SAME layout (one fused kernel per chunk), then reduce with identity
-        from ._broadcast import LocalArg, run_local
-        from ._darray import darray_like
-        out_dt = _NPT[expr.jt]
-        tmp = darray_like(lambda I: B200Array.empty(d.rt, shape_of(I), out_dt), d, dtype=out_dt)
-        for pid, out in tmp.chunks.items():
-            run_local(d.rt, expr, out, [LocalArg(d.chunks[pid], None, tag_of(d.dtype))])
-        src, mapc, param = tmp, (_lib.MAP_NONZERO if out_dt == np.dtype(np.bool_) else _lib.MAP_ID), None
+def _check_nonempty(d: DArray, opc: int):
     if opc in (_lib.MAX, _lib.MIN):
-        for pid in src.layout.pids:
-            if int(np.prod(shape_of(src.layout.localindices(pid)))) == 0:
-                if tmp is not None:
-                    tmp.close()
+        for pid in d.layout.pids:
+            if int(np.prod(shape_of(d.layout.localindices(pid)))) == 0:
                 raise _lib.ArgumentError(_lib.ERR_EMPTY, "reducing over an empty collection is not allowed")
+
+
+def _empty_slot(rt, opc: int, rdt: np.dtype, slot_ptr: int):
+    """An empty localpart contributes the identity (Base: sum -> 0, prod -> 1, all -> true, any/count -> 0)."""
+    v = np.zeros(2, dtype=np.uint64)
+    one = {_lib.PROD: 1, _lib.ALL: 1}.get(opc, 0)
+    v.view(np.uint8)[:rdt.itemsize] = np.asarray([one], dtype=rdt).view(np.uint8)
+    _lib.call("dab_h2d", rt.ctx, C.c_void_p(slot_ptr), C.c_void_p(v.ctypes.data), 16)
+    rt.sync()
+
+
+def _mapreduce_expr(expr: Expr, opc: int, d: DArray, others: Sequence, return_partials: bool = False):
+    """General ``mapreduce(f, op, d, others...)``: f is an arbitrary traced expression over 1..8 arguments.  ONE fused NVRTC
+    kernel per localpart (``dab_mapreduce_expr``), no temporary f.(d) array; combine as in ``_mapreduce_all``."""
+    from ._broadcast import _NPT as NPT, _localise, _prepare_remote_reads, codegen
     rt = d.rt
+    args = [d] + list(others)
+    for a in others:
+        if isinstance(a, DArray) and a.dims != d.dims:
+            raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"mapreduce arguments differ in size: {d.dims} vs {a.dims}")
+        if isinstance(a, np.ndarray) and a.ndim > 0 and tuple(a.shape) != d.dims:
+            raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"mapreduce arguments differ in size: {d.dims} vs {a.shape}")
+    if len(args) > 8:
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "more than 8 mapreduce arguments are not served")
+    _check_nonempty(d, opc)
+    val_tag = expr.jt
+    val_code = dab_dtype(NPT[val_tag])
+    if val_tag == "bool" and opc == _lib.SUM:
+        opc_k = _lib.COUNT                       # sum of Bools == count (Int64)
+    else:
+        opc_k = opc
+    rdt = np.dtype(np.int64) if val_tag in ("bool", "i32", "i64") and opc in (_lib.SUM, _lib.PROD, _lib.ALL, _lib.ANY, _lib.COUNT) else NPT[val_tag]
+    src = codegen(expr).encode()
+    _prepare_remote_reads(d.layout, rt, [a for a in others if isinstance(a, DArray)])
+    temps = []
+
+    def launch(pid, ch, slot_ptr):
+        if ch.size == 0:
+            return _empty_slot(rt, opc, rdt, slot_ptr)
+        I = d.layout.localindices(pid)
+        largs = [_localise(rt, a, I, pid) for a in args]
+        n = len(largs)
+        dts = (C.c_int32 * n)(*[dab_dtype(NPT[la.tag]) for la in largs])
+        ptrs = (C.c_void_p * n)(*[la.arr.ptr if la.arr is not None else None for la in largs])
+        scal = (C.c_uint64 * n)()
+        for k, la in enumerate(largs):
+            if la.arr is None:
+                scal[k] = int.from_bytes(np.asarray(la.scalar, dtype=NPT[la.tag]).tobytes().ljust(8, b"\0"), "little")
+            elif la.temp:
+                temps.append(la.arr)
+        _lib.call("dab_mapreduce_expr", rt.ctx, src, val_code, opc_k, ch.size, n, dts, ptrs, scal, C.c_void_p(slot_ptr))
+
     try:
-        if rt.workers_per_rank == 1 and src.layout.pids == rt.workers() and not return_partials:
-            # production mapping, one chunk per GPU: kernel + NCCL all-gather + ordered fold in ONE C-ABI call
-            ch = src.chunks[rt.myid()]
-            rdt = _result_dtype(src.dtype, opc, mapc)
-            out = np.zeros(2, dtype=np.uint64)
-            _lib.call("dab_mapreduce_all", rt.ctx, dab_dtype(src.dtype), opc, mapc, C.c_void_p(param.ctypes.data) if param is not None else None,
-                      C.c_void_p(ch.ptr), ch.size, C.c_void_p(out.ctypes.data))
-            return out.view(np.uint8)[:rdt.itemsize].view(rdt)[0]
-        host, rdt = _chunk_partials(src, opc, mapc, param)
-        res, vals = _fold(host, src.layout.pids, rdt, opc)
-        return (res, vals) if return_partials else res
+        host = _gather_slots(d, launch)
     finally:
-        if tmp is not None:
-            tmp.close()
+        for t in temps:
+            t.free()
+    res, vals = _fold(host, d.layout.pids, rdt, opc if opc != _lib.COUNT else _lib.SUM)
+    return (res, vals) if return_partials else res
+
+
+def _mapreduce_all(f, op, d: DArray, return_partials: bool = False, others: Sequence = ()):
+    opc = op if isinstance(op, int) else _op_code(op)
+    if others:
+        expr = trace(f, [tag_of(d.dtype)] + [_arg_tag_of(a) for a in others])
+        return _mapreduce_expr(expr, opc, d, others, return_partials)
+    mapc, param, expr = classify_map(f, d.dtype)
+    if mapc is None:
+        return _mapreduce_expr(expr, opc, d, (), return_partials)   # general closure: one fused NVRTC kernel per chunk
+    _check_nonempty(d, opc)
+    rt = d.rt
+    pp = C.c_void_p(param.ctypes.data) if param is not None else None
+    rdt = _result_dtype(d.dtype, opc, mapc)
+    if rt.workers_per_rank == 1 and d.layout.pids == rt.workers() and not return_partials:
+        # production mapping, one chunk per GPU: reduce kernel + cross-worker combine + ordered fold in ONE C-ABI call
+        ch = d.chunks[rt.myid()]
+        out = np.zeros(2, dtype=np.uint64)
+        _lib.call("dab_mapreduce_all", rt.ctx, dab_dtype(d.dtype), opc, mapc, pp, C.c_void_p(ch.ptr), ch.size, C.c_void_p(out.ctypes.data))
+        return out.view(np.uint8)[:rdt.itemsize].view(rdt)[0]
+    code = dab_dtype(d.dtype)
+    host = _gather_slots(d, lambda pid, ch, slot: _lib.call("dab_reduce", rt.ctx, code, opc, mapc, pp, C.c_void_p(ch.ptr), ch.size, C.c_void_p(slot)))
+    res, vals = _fold(host, d.layout.pids, rdt, opc)
+    return (res, vals) if return_partials else res
+
+
+def _arg_tag_of(a) -> str:
+    from ._broadcast import _arg_tag
+    return _arg_tag(a)
 
 
 def reduce(op, d: DArray, dims=None, init=None):
@@ -167,12 +223,15 @@ def reduce(op, d: DArray, dims=None, init=None):
     return mapreduce(None, op, d, dims=dims, init=init)
 
 
-def mapreduce(f: Optional[Callable], op, d: DArray, dims=None, init=None, _partials: bool = False):
-    """``mapreduce(f, op, d::DArray[; dims, init])`` (reference src/mapreduce.jl:29-35 and :42-94)."""
+def mapreduce(f: Optional[Callable], op, d: DArray, *ds, dims=None, init=None, _partials: bool = False):
+    """``mapreduce(f, op, d::DArray, ds...[; dims, init])`` (reference src/mapreduce.jl:29-35 and :42-94).  With extra arguments
+    (same-size DArrays / arrays / scalars) ``f`` takes one value per argument: ``mapreduce(*, +, x, y)`` is ``dot(x, y)``."""
     if dims is None:
         if init is not None:
             raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "mapreduce(f, op, d; init) without dims falls back to scalar iteration in the reference; not served")
-        return _mapreduce_all(f, op, d, _partials)
+        return _mapreduce_all(f, op, d, _partials, ds)
+    if ds:
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "multi-argument mapreduce with dims is not served")
     return mapreducedim(f, op, d, dims, init)
 
 
@@ -399,3 +458,72 @@ def mapreducedim(f: Optional[Callable], op, d: DArray, dims, init=None) -> DArra
     finally:
         if tmp is not None:
             tmp.close()
+
+
+# ---- Level-1 linear algebra and friends built from the same kernels (reference src/linalg.jl:24-59, ext/StatisticsExt.jl:6) ----------
+
+
+def dot(x: DArray, y: DArray):
+    """``dot(x, y)`` (reference src/linalg.jl:34-46): per-chunk dot products, summed over the chunks -- one fused pass, 8 B/element."""
+    if x.dims != y.dims:
+        raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"dot: {x.dims} vs {y.dims}")
+    return _mapreduce_all(lambda a, b: a * b, _lib.SUM, x, False, (y,))
+
+
+def norm(x: DArray, p=2):
+    """``norm(x, p)`` (reference src/linalg.jl:48-59) for p in (1, 2, Inf)."""
+    if p == 2:
+        return np.sqrt(_mapreduce_all(abs2_fn, _lib.SUM, x))
+    if p == 1:
+        return _mapreduce_all(abs, _lib.SUM, x)
+    if p in (np.inf, float("inf")):
+        return _mapreduce_all(abs, _lib.MAX, x)
+    raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"norm with p={p} is not served")
+
+
+def abs2_fn(v):
+    return v * v
+
+
+def axpy_(a, x: DArray, y: DArray) -> DArray:
+    """``axpy!(a, x, y)``: y .= a .* x .+ y (reference src/linalg.jl:24-32)."""
+    from ._broadcast import broadcast_into
+    if x.dims != y.dims:
+        raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"axpy!: {x.dims} vs {y.dims}")
+    s = np.asarray(a, dtype=x.dtype)[()]
+    return broadcast_into(y, lambda u, v: s * u + v, x, y)
+
+
+def rmul_(x: DArray, a) -> DArray:
+    """``rmul!(x, a)``: x .= x .* a (reference src/linalg.jl:169-176)."""
+    from ._broadcast import broadcast_into
+    s = np.asarray(a, dtype=x.dtype)[()]
+    return broadcast_into(x, lambda u: u * s, x)
+
+
+def isequal(d: DArray, other) -> bool:
+    """``d == a`` (reference src/darray.jl:403-414): sizes equal and every localpart equal to the matching slice -- one fused
+    ``all(x .== y)`` pass per chunk."""
+    shape = other.dims if isinstance(other, DArray) else tuple(np.shape(other))
+    if tuple(shape) != tuple(d.dims):
+        return False
+    if d.size == 0:
+        return True
+    if not isinstance(other, DArray):
+        other = np.asarray(other)
+    return bool(_mapreduce_all(lambda a, b: a == b, _lib.ALL, d, False, (other,)))
+
+
+def mean(d: DArray, dims=None, f: Optional[Callable] = None):
+    """``mean(d[; dims])`` (reference ext/StatisticsExt.jl:6: ``sum(f, A, dims) ./ prod(size(A)[dims])``)."""
+    if dims is None:
+        return mapreduce(f, "+", d) / d.size
+    from ._broadcast import broadcast
+    region = _normalise_region(dims, d.ndim)
+    cnt = int(np.prod([d.dims[r - 1] for r in region if r <= d.ndim])) if region else 1
+    S = mapreducedim(f, "+", d, dims)
+    out_t = np.float64 if S.dtype.kind in "iub" or S.dtype == np.float64 else np.float32
+    c = out_t(cnt)
+    R = broadcast(lambda s: s / c, S)
+    S.close()
+    return R

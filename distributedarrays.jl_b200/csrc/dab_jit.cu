@@ -382,6 +382,191 @@ int32_t compile(dab_ctx* ctx, const std::string& src, Compiled* out) {
     return DAB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Fused map + reduce for an arbitrary traced expression:  mapreduce(f, op, args...)  on one localpart in ONE pass over HBM
+// (reference src/mapreduce.jl:31 with a general closure f; also dot = mapreduce(*, +, x, y), isequal = all(x .== y), ...).
+// Same structure as the hand-written reduce_kernel: flat grid, 2 x 16/32-byte vector loads per argument in flight, 8-value tree in
+// the value type, wide (fp64 / int64) carrier, one partial per CTA; a second tiny launch folds the <= 16384 partials in a fixed
+// order (deterministic) and writes the 16-byte result slot.
+struct MrSpec {
+    const char *tile_t, *acc_t, *out_t, *tile_comb, *acc_comb, *acc_id;
+};
+
+bool mr_spec(int32_t val_dt, int32_t op, MrSpec* sp) {
+    const bool flt = val_dt == DAB_F32 || val_dt == DAB_F64, boolean = val_dt == DAB_U8;
+    const char* vt = ctype_of(val_dt);
+    switch (op) {
+        case DAB_SUM:
+        case DAB_COUNT:
+            if (op == DAB_COUNT && !boolean) return false;
+            if (flt) *sp = {vt, "double", vt, "jl_add(a, b)", "jl_add(a, b)", "0.0"};
+            else if (boolean) *sp = {"int", "long long", "long long", "(a + b)", "jl_add(a, b)", "0ll"};
+            else *sp = {"long long", "long long", "long long", "jl_add(a, b)", "jl_add(a, b)", "0ll"};
+            return true;
+        case DAB_PROD:
+            if (boolean) return false;
+            if (flt) *sp = {vt, "double", vt, "jl_mul(a, b)", "jl_mul(a, b)", "1.0"};
+            else *sp = {"long long", "long long", "long long", "jl_mul(a, b)", "jl_mul(a, b)", "1ll"};
+            return true;
+        case DAB_MAX:
+        case DAB_MIN: {
+            if (boolean) return false;
+            const bool mx = op == DAB_MAX;
+            const char* id = val_dt == DAB_F32   ? (mx ? "(-__int_as_float(0x7f800000))" : "__int_as_float(0x7f800000)")
+                             : val_dt == DAB_F64 ? (mx ? "(-__longlong_as_double(0x7ff0000000000000ll))" : "__longlong_as_double(0x7ff0000000000000ll)")
+                             : val_dt == DAB_I32 ? (mx ? "((int)0x80000000)" : "0x7fffffff")
+                                                 : (mx ? "((long long)0x8000000000000000ll)" : "0x7fffffffffffffffll");
+            *sp = {vt, vt, vt, mx ? "jl_max(a, b)" : "jl_min(a, b)", mx ? "jl_max(a, b)" : "jl_min(a, b)", id};
+            return true;
+        }
+        case DAB_ALL:
+        case DAB_ANY:
+            if (!boolean) return false;
+            *sp = {"int", "long long", "long long", "(a + b)", "jl_add(a, b)", "0ll"};
+            return true;
+        default: return false;
+    }
+}
+
+struct MrParamsHost {
+    const void* ptr[8];
+    unsigned long long scalar[8];
+    unsigned long long n;
+    void* partials;
+    int tiles_per_cta;
+};
+struct MrFinalHost {
+    const void* partials;
+    void* out;
+    long long n;
+    unsigned int nparts;
+    int mode;
+};
+
+std::string build_mr_source(const char* expr, int32_t val_dt, int32_t op, int nargs, const int32_t* dts, const bool* is_arr, const MrSpec& sp) {
+    std::string s = kPrelude;
+    s += std::string("typedef ") + ctype_of(val_dt) + " VAL_T;\n";
+    for (int k = 0; k < nargs; ++k) s += std::string("typedef ") + ctype_of(dts[k]) + " T" + std::to_string(k) + ";\n";
+    s += std::string("typedef ") + sp.tile_t + " TILE_T;\ntypedef " + sp.acc_t + " ACC_T;\ntypedef " + sp.out_t + " OUT_T;\n";
+    s += "#define DAB_EXPR (";
+    s += expr;
+    s += ")\n";
+    s += std::string("DEV TILE_T tile_comb(TILE_T a, TILE_T b) { return ") + sp.tile_comb + "; }\n";
+    s += std::string("DEV ACC_T acc_comb(ACC_T a, ACC_T b) { return ") + sp.acc_comb + "; }\n";
+    s += std::string("#define ACC_ID ((ACC_T)") + sp.acc_id + ")\n";
+    s += R"MR(
+struct MrParams { const void* ptr[8]; u64 scalar[8]; u64 n; void* partials; int tiles_per_cta; };
+struct MrFinal { const void* partials; void* out; i64 n; unsigned int nparts; int mode; };
+DEV ACC_T acc_shfl(ACC_T v, int d) {
+    if (sizeof(ACC_T) == 8) {
+        i64 x; memcpy(&x, &v, 8);
+        int lo = __shfl_down_sync(0xffffffffu, (int)(x & 0xffffffffll), d), hi = __shfl_down_sync(0xffffffffu, (int)(x >> 32), d);
+        x = ((i64)hi << 32) | (unsigned int)lo;
+        ACC_T r; memcpy(&r, &x, 8); return r;
+    } else {
+        int x = 0; memcpy(&x, &v, sizeof(ACC_T));
+        x = __shfl_down_sync(0xffffffffu, x, d);
+        ACC_T r; memcpy(&r, &x, sizeof(ACC_T)); return r;
+    }
+}
+DEV ACC_T block_reduce(ACC_T acc, ACC_T* smem) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc = acc_comb(acc, acc_shfl(acc, d));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) smem[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        acc = lane < 8 ? smem[lane] : ACC_ID;
+#pragma unroll
+        for (int d = 4; d > 0; d >>= 1) acc = acc_comb(acc, acc_shfl(acc, d));
+    }
+    return acc;
+}
+extern "C" __global__ void __launch_bounds__(256) dab_mr_final(MrFinal p) {
+    __shared__ ACC_T smem[8];
+    const ACC_T* parts = (const ACC_T*)p.partials;
+    ACC_T acc = ACC_ID;
+    unsigned int i = threadIdx.x;
+    for (; i + 768 < p.nparts; i += 1024) {   // 4 independent loads in flight
+        ACC_T a0 = parts[i], a1 = parts[i + 256], a2 = parts[i + 512], a3 = parts[i + 768];
+        acc = acc_comb(acc, acc_comb(acc_comb(a0, a1), acc_comb(a2, a3)));
+    }
+    for (; i < p.nparts; i += 256) acc = acc_comb(acc, parts[i]);
+    acc = block_reduce(acc, smem);
+    if (threadIdx.x == 0) {
+        OUT_T res;
+        if (p.mode == 1) res = (OUT_T)(acc == (ACC_T)p.n);
+        else if (p.mode == 2) res = (OUT_T)(acc != (ACC_T)0);
+        else res = (OUT_T)acc;
+        u64 w0 = 0, w1 = 0;
+        memcpy(&w0, &res, sizeof(OUT_T));
+        memcpy(&w1, &acc, sizeof(ACC_T));
+        ((u64*)p.out)[0] = w0;
+        ((u64*)p.out)[1] = w1;
+    }
+}
+)MR";
+    // ---- partial kernel
+    s += "extern \"C\" __global__ void __launch_bounds__(256) dab_mr_partial(MrParams p) {\n"
+         "  __shared__ ACC_T smem[8];\n"
+         "  const u64 n = p.n, nv = n / 4, ntiles = nv / 512;\n";
+    for (int k = 0; k < nargs; ++k) {
+        std::string K = std::to_string(k);
+        if (is_arr[k]) s += "  const T" + K + "* q" + K + " = (const T" + K + "*)p.ptr[" + K + "];\n";
+        else s += "  const T" + K + " a" + K + " = bits_as<T" + K + ">(p.scalar[" + K + "]);\n";
+    }
+    s += "  ACC_T acc = ACC_ID;\n"
+         "  u64 t_end = ((u64)blockIdx.x + 1) * (u64)p.tiles_per_cta;\n"
+         "  if (t_end > ntiles) t_end = ntiles;\n"
+         "#pragma unroll 1\n"
+         "  for (u64 t = (u64)blockIdx.x * (u64)p.tiles_per_cta; t < t_end; ++t) {\n"
+         "    const u64 i0 = t * 512 + threadIdx.x;\n";
+    for (int k = 0; k < nargs; ++k)
+        if (is_arr[k]) {
+            std::string K = std::to_string(k);
+            s += "    const VecN<T" + K + ", 4> v" + K + "_0 = *(const VecN<T" + K + ", 4>*)(q" + K + " + 4 * i0);\n";
+            s += "    const VecN<T" + K + ", 4> v" + K + "_1 = *(const VecN<T" + K + ", 4>*)(q" + K + " + 4 * (i0 + 256));\n";
+        }
+    s += "    TILE_T m[8];\n";
+    for (int u = 0; u < 2; ++u) {
+        std::string U = std::to_string(u);
+        s += "#pragma unroll\n    for (int j = 0; j < 4; ++j) {\n";
+        for (int k = 0; k < nargs; ++k)
+            if (is_arr[k]) {
+                std::string K = std::to_string(k);
+                s += "      const T" + K + " a" + K + " = v" + K + "_" + U + ".v[j];\n";
+            }
+        s += "      m[" + std::to_string(4 * u) + " + j] = (TILE_T)((VAL_T)DAB_EXPR);\n    }\n";
+    }
+    s += "#pragma unroll\n"
+         "    for (int w = 8; w > 1; w >>= 1)\n"
+         "#pragma unroll\n"
+         "      for (int k = 0; k < w / 2; ++k) m[k] = tile_comb(m[k], m[k + w / 2]);\n"
+         "    acc = acc_comb(acc, (ACC_T)m[0]);\n"
+         "  }\n"
+         "  if (blockIdx.x == gridDim.x - 1) {\n"
+         "    for (u64 i = ntiles * 2048 + threadIdx.x; i < n; i += blockDim.x) {\n";
+    for (int k = 0; k < nargs; ++k)
+        if (is_arr[k]) {
+            std::string K = std::to_string(k);
+            s += "      const T" + K + " a" + K + " = q" + K + "[i];\n";
+        }
+    s += "      acc = acc_comb(acc, (ACC_T)(TILE_T)((VAL_T)DAB_EXPR));\n"
+         "    }\n"
+         "  }\n"
+         "  acc = block_reduce(acc, smem);\n"
+         "  if (threadIdx.x == 0) ((ACC_T*)p.partials)[blockIdx.x] = acc;\n"
+         "}\n";
+    return s;
+}
+
+struct CompiledMr {
+    CUfunction partial = nullptr, final_ = nullptr;
+};
+std::unordered_map<std::string, CompiledMr> g_mr_cache;
+
 }  // namespace
 
 extern "C" {
@@ -472,6 +657,100 @@ int32_t dab_broadcast_expr(dab_ctx* ctx, const char* expr, int32_t out_dtype, vo
         return dab_fail(ctx, DAB_ERR_CUDA, "cuLaunchKernel failed: %s", es);
     }
     ctx->launches++;
+    return DAB_OK;
+}
+
+
+int32_t dab_mapreduce_expr(dab_ctx* ctx, const char* expr, int32_t val_dtype, int32_t op, size_t n, int32_t nargs, const int32_t* arg_dtypes,
+                           const void* const* arg_ptrs, const uint64_t* arg_scalars, void* out_dev) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, expr && out_dev, DAB_ERR_ARG, "dab_mapreduce_expr: null pointer");
+    DAB_REQUIRE(ctx, nargs >= 1 && nargs <= 8 && arg_dtypes && arg_ptrs && arg_scalars, DAB_ERR_ARG, "dab_mapreduce_expr: bad argument table");
+    DAB_REQUIRE(ctx, ctype_of(val_dtype), DAB_ERR_ARG, "dab_mapreduce_expr: bad value dtype %d", val_dtype);
+    DAB_REQUIRE(ctx, n > 0, DAB_ERR_EMPTY, "dab_mapreduce_expr: empty input (the host runtime handles n == 0)");
+    MrSpec sp;
+    if (!mr_spec(val_dtype, op, &sp))
+        return dab_fail(ctx, DAB_ERR_UNSUPPORTED, "mapreduce op %d on value dtype %d is not served (no host fallback)", op, val_dtype);
+    bool is_arr[8] = {false};
+    bool vec_ok = true;
+    std::string key = "mr|" + std::to_string(ctx->device) + "|" + std::to_string(val_dtype) + "|" + std::to_string(op) + "|";
+    for (int k = 0; k < nargs; ++k) {
+        DAB_REQUIRE(ctx, ctype_of(arg_dtypes[k]), DAB_ERR_ARG, "dab_mapreduce_expr: bad dtype of arg %d", k);
+        is_arr[k] = arg_ptrs[k] != nullptr;
+        key += std::to_string(arg_dtypes[k]) + (is_arr[k] ? "a" : "s");
+        if (is_arr[k] && ((uintptr_t)arg_ptrs[k] % (4 * dab_dtype_size(arg_dtypes[k])))) vec_ok = false;
+    }
+    if (!vec_ok) return dab_fail(ctx, DAB_ERR_UNSUPPORTED, "dab_mapreduce_expr: arguments must be aligned to 4 elements");
+    key += "|";
+    key += expr;
+    CompiledMr comp;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_mr_cache.find(key);
+        if (it == g_mr_cache.end()) {
+            DAB_CUDA(ctx, cudaFree(0));
+            Driver& drv = driver();
+            if (!drv.ok) return dab_fail(ctx, DAB_ERR_NVRTC, "CUDA driver API unavailable: %s", drv.why);
+            std::vector<char> cubin;
+            int32_t st = compile_cubin(ctx, build_mr_source(expr, val_dtype, op, nargs, arg_dtypes, is_arr, sp), &cubin);
+            if (st != DAB_OK) return st;
+            CUmodule mod;
+            if (drv.ModuleLoadData(&mod, cubin.data()) != CUDA_SUCCESS) return dab_fail(ctx, DAB_ERR_NVRTC, "cuModuleLoadData failed");
+            if (drv.ModuleGetFunction(&comp.partial, mod, "dab_mr_partial") != CUDA_SUCCESS ||
+                drv.ModuleGetFunction(&comp.final_, mod, "dab_mr_final") != CUDA_SUCCESS)
+                return dab_fail(ctx, DAB_ERR_NVRTC, "cuModuleGetFunction failed");
+            g_mr_cache[key] = comp;
+        } else {
+            comp = it->second;
+        }
+    }
+    const size_t ntiles = (n / 4) / 512;
+    size_t k = 2;
+    const size_t max_parts = 16384;
+    if ((ntiles + k - 1) / k > max_parts) k = (ntiles + max_parts - 1) / max_parts;
+    size_t grid = (ntiles + k - 1) / k;
+    if (grid < 1) grid = 1;
+    MrParamsHost p;
+    memset(&p, 0, sizeof(p));
+    for (int a = 0; a < nargs; ++a) {
+        p.ptr[a] = arg_ptrs[a];
+        p.scalar[a] = arg_scalars[a];
+    }
+    p.n = n;
+    p.partials = ctx->block_partials;
+    p.tiles_per_cta = (int)k;
+    MrFinalHost f;
+    f.partials = ctx->block_partials;
+    f.out = out_dev;
+    f.n = (long long)n;
+    f.nparts = (unsigned int)grid;
+    f.mode = op == DAB_ALL ? 1 : (op == DAB_ANY ? 2 : 0);
+    Driver& drv = driver();
+    void* a1[] = {&p};
+    void* a2[] = {&f};
+    if (drv.LaunchKernel(comp.partial, (unsigned)grid, 1, 1, 256, 1, 1, 0, (CUstream)ctx->stream, a1, nullptr) != CUDA_SUCCESS ||
+        drv.LaunchKernel(comp.final_, 1, 1, 1, 256, 1, 1, 0, (CUstream)ctx->stream, a2, nullptr) != CUDA_SUCCESS)
+        return dab_fail(ctx, DAB_ERR_CUDA, "cuLaunchKernel failed (dab_mapreduce_expr)");
+    ctx->launches += 2;
+    return DAB_OK;
+}
+
+// Diagnostic twin of dab_jit_compile_check for the fused map+reduce kernels.
+int32_t dab_jit_compile_check_reduce(const char* expr, int32_t val_dtype, int32_t op, int32_t nargs, const int32_t* arg_dtypes,
+                                     const int32_t* arg_is_array, size_t* cubin_bytes) {
+    if (!expr || !ctype_of(val_dtype) || nargs < 1 || nargs > 8 || !arg_dtypes || !arg_is_array)
+        return dab_fail(nullptr, DAB_ERR_ARG, "dab_jit_compile_check_reduce: bad argument");
+    MrSpec sp;
+    if (!mr_spec(val_dtype, op, &sp)) return dab_fail(nullptr, DAB_ERR_UNSUPPORTED, "op %d on value dtype %d not served", op, val_dtype);
+    bool is_arr[8] = {false};
+    for (int k = 0; k < nargs; ++k) {
+        if (!ctype_of(arg_dtypes[k])) return dab_fail(nullptr, DAB_ERR_ARG, "bad dtype of arg %d", k);
+        is_arr[k] = arg_is_array[k] != 0;
+    }
+    std::vector<char> cubin;
+    int32_t st = compile_cubin(nullptr, build_mr_source(expr, val_dtype, op, nargs, arg_dtypes, is_arr, sp), &cubin);
+    if (st != DAB_OK) return st;
+    if (cubin_bytes) *cubin_bytes = cubin.size();
     return DAB_OK;
 }
 

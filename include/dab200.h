@@ -178,6 +178,15 @@ int32_t dab_broadcast_expr(dab_ctx* ctx, const char* expr, int32_t out_dtype, vo
 int32_t dab_jit_compile_check(const char* expr, int32_t out_dtype, int32_t nargs, const int32_t* arg_dtypes,
                               const int32_t* arg_is_array, size_t* cubin_bytes);
 
+/* Fused map + reduce of an arbitrary traced expression over one localpart, ONE pass over HBM:  mapreduce(f, op, args...)
+ * (reference src/mapreduce.jl:31 with a general closure f; dot(x, y) = mapreduce(*, +, x, y); d == a via all(x .== y)).
+ * expr / args as in dab_broadcast_expr but all array arguments are dense with n elements (linear indexing); val_dtype is the
+ * type of the expression's value.  The 16-byte result slot at out_dev has the layout of dab_reduce.  NVRTC-compiled, cached. */
+int32_t dab_mapreduce_expr(dab_ctx* ctx, const char* expr, int32_t val_dtype, int32_t op, size_t n, int32_t nargs, const int32_t* arg_dtypes,
+                           const void* const* arg_ptrs, const uint64_t* arg_scalars, void* out_dev);
+int32_t dab_jit_compile_check_reduce(const char* expr, int32_t val_dtype, int32_t op, int32_t nargs, const int32_t* arg_dtypes,
+                                     const int32_t* arg_is_array, size_t* cubin_bytes);
+
 /* ==== whole-chunk reductions K4 / K7 (HBM-bound, 4 B/element) ==========================
  * Replace mapreduce(f, op, localpart(d)) / reduce(f, localpart(d)) run per worker at
  * src/mapreduce.jl:23,31 and all/any/count/extrema at :100,109,118,127.

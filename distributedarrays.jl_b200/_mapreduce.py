@@ -278,8 +278,21 @@ def count(d: DArray, f: Optional[Callable] = None) -> int:
 
 
 def extrema(d: DArray):
-    """reference src/mapreduce.jl:124-131: per-chunk (min, max), folded with (min, max)."""
-    return (_mapreduce_all(None, _lib.MIN, d), _mapreduce_all(None, _lib.MAX, d))
+    """``extrema(d)`` (reference src/mapreduce.jl:124-131): per-chunk (min, max) in ONE pass over the chunk, then the fold
+    ``(t, s) -> (min(t[1], s[1]), max(t[2], s[2]))`` over the workers in procs order."""
+    if d.dtype == np.dtype(np.bool_):
+        return (_mapreduce_all(None, _lib.MIN, d), _mapreduce_all(None, _lib.MAX, d))
+    _check_nonempty(d, _lib.MAX)
+    rt, code, es = d.rt, dab_dtype(d.dtype), d.dtype.itemsize
+    host = _gather_slots(d, lambda pid, ch, slot: _lib.call("dab_reduce", rt.ctx, code, _lib.EXTREMA, _lib.MAP_ID, None, C.c_void_p(ch.ptr), ch.size,
+                                                            C.c_void_p(slot)))
+    lo = np.array([host[16 * (p - 1):16 * (p - 1) + es].view(d.dtype)[0] for p in d.layout.pids], dtype=d.dtype)
+    hi = np.array([host[16 * (p - 1) + es:16 * (p - 1) + 2 * es].view(d.dtype)[0] for p in d.layout.pids], dtype=d.dtype)
+    out = np.zeros(2, dtype=d.dtype)
+    L = _lib.lib()
+    _lib.check(L.dab_combine_ordered(code, _lib.MIN, C.c_void_p(lo.ctypes.data), lo.size, C.c_void_p(out[0:1].ctypes.data)))
+    _lib.check(L.dab_combine_ordered(code, _lib.MAX, C.c_void_p(hi.ctypes.data), hi.size, C.c_void_p(out[1:2].ctypes.data)))
+    return (out[0], out[1])
 
 
 # ---- dimensional reduction ------------------------------------------------------------------------------------------------------

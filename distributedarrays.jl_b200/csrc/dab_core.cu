@@ -127,7 +127,7 @@ int32_t dab_init(int32_t device, dab_ctx** out) {
         unsigned long long keep = ~0ull;
         INIT_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
-    INIT_CUDA(cudaMalloc(&ctx->block_partials, ((size_t)DAB_MAX_REDUCE_BLOCKS + DAB_MAX_REDUCE_BLOCKS / 256 + 16) * 8));
+    INIT_CUDA(cudaMalloc(&ctx->block_partials, ((size_t)DAB_MAX_REDUCE_BLOCKS + DAB_MAX_REDUCE_BLOCKS / 256 + 16) * 16));
     INIT_CUDA(cudaMalloc((void**)&ctx->counter, (DAB_MAX_REDUCE_BLOCKS / 256 + 16) * 4));
     INIT_CUDA(cudaMemsetAsync(ctx->counter, 0, (DAB_MAX_REDUCE_BLOCKS / 256 + 16) * 4, ctx->stream));
     INIT_CUDA(cudaMalloc(&ctx->result_slot, DAB_SLOT_BYTES));

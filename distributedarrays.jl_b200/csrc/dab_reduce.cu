@@ -113,16 +113,23 @@ __global__ void __launch_bounds__(RD_THREADS, 8) reduce_kernel(const T* __restri
     fin = block_reduce<R>(fin, smem);
     if (threadIdx.x == 0) {
         *counter = 0;
-        Out res;
-        if (finalize_mode == 1) res = (Out)(fin == (A)n_for_all);  // ALL
-        else if (finalize_mode == 2) res = (Out)(fin != (A)0);      // ANY
-        else res = (Out)fin;
-        memcpy(out, &res, sizeof(Out));
-        if (sizeof(Out) < 8) memset((char*)out + sizeof(Out), 0, 8 - sizeof(Out));
-        A wide = fin;
-        memcpy((char*)out + 8, &wide, sizeof(A));
-        if (sizeof(A) < 8) memset((char*)out + 8 + sizeof(A), 0, 8 - sizeof(A));
+        if constexpr (std::is_arithmetic<A>::value) {
+            Out res;
+            if (finalize_mode == 1) res = (Out)(fin == (A)n_for_all);  // ALL
+            else if (finalize_mode == 2) res = (Out)(fin != (A)0);      // ANY
+            else res = (Out)fin;
+            memcpy(out, &res, sizeof(Out));
+            if (sizeof(Out) < 8) memset((char*)out + sizeof(Out), 0, 8 - sizeof(Out));
+            A wide = fin;
+            memcpy((char*)out + 8, &wide, sizeof(A));
+            if (sizeof(A) < 8) memset((char*)out + 8 + sizeof(A), 0, 8 - sizeof(A));
+        } else {  // extrema: the (min, max) pair fills the slot (8 bytes for 4-byte T, 16 for 8-byte T)
+            memset(out, 0, 16);
+            memcpy(out, &fin, sizeof(A));
+        }
     }
+    if constexpr (!std::is_arithmetic<Out>::value) return;
+    else {
     if (fc.nranks <= 1) return;
     // ---- fused cross-worker combine over NVLink peer memory (replaces remotecall_fetch + reduce(op, results), reference
     // src/mapreduce.jl:30-34, and an ncclAllGather + D2H copy): thread j of this last CTA PUSHES this rank's chunk result into
@@ -181,6 +188,7 @@ __global__ void __launch_bounds__(RD_THREADS, 8) reduce_kernel(const T* __restri
         h[1] = (unsigned long long)timed_out;
         __threadfence_system();
     }
+    }  // arithmetic Out
 }
 
 template <typename T, typename Map, typename R, typename Out>
@@ -220,6 +228,9 @@ int32_t reduce_arith(dab_ctx* ctx, int32_t op, const T* x, size_t n, void* out) 
         case DAB_PROD: return launch_reduce<T, MapF<T, FN>, ProdTraits<T>, ResultOfSum<T>>(ctx, x, n, map, out, 0);
         case DAB_MAX: return launch_reduce<T, MapF<T, FN>, MaxTraits<T>, T>(ctx, x, n, map, out, 0);
         case DAB_MIN: return launch_reduce<T, MapF<T, FN>, MinTraits<T>, T>(ctx, x, n, map, out, 0);
+        case DAB_EXTREMA:
+            if constexpr (FN == DAB_MAP_ID) return launch_reduce<T, ExtMapF<T>, ExtremaTraits<T>, Pair<T>>(ctx, x, n, ExtMapF<T>{(T)0}, out, 0);
+            else return dab_fail(ctx, DAB_ERR_UNSUPPORTED, "extrema with a map is not served (no host fallback)");
         default: return dab_fail(ctx, DAB_ERR_UNSUPPORTED, "reduce op %d needs a predicate map (no host fallback)", op);
     }
 }
@@ -321,7 +332,8 @@ int32_t dab_reduce_result_dtype(int32_t dtype, int32_t op, int32_t map, int32_t*
             *out_dtype = (!pred && (dtype == DAB_F32 || dtype == DAB_F64)) ? dtype : DAB_I64;
             return DAB_OK;
         case DAB_MAX:
-        case DAB_MIN: *out_dtype = dtype; return DAB_OK;
+        case DAB_MIN:
+        case DAB_EXTREMA: *out_dtype = dtype; return DAB_OK;
         case DAB_ALL:
         case DAB_ANY:
         case DAB_COUNT: *out_dtype = DAB_I64; return DAB_OK;
@@ -334,7 +346,7 @@ int32_t dab_reduce(dab_ctx* ctx, int32_t dtype, int32_t op, int32_t map, const v
                    void* out_dev) {
     DAB_ENTER(ctx);
     DAB_REQUIRE(ctx, out_dev && (x || n == 0), DAB_ERR_ARG, "dab_reduce: null pointer");
-    DAB_REQUIRE(ctx, op >= DAB_SUM && op <= DAB_COUNT, DAB_ERR_ARG, "dab_reduce: bad op %d", op);
+    DAB_REQUIRE(ctx, op >= DAB_SUM && op <= DAB_EXTREMA, DAB_ERR_ARG, "dab_reduce: bad op %d", op);
     if (n == 0) return empty_result(ctx, dtype, op, out_dev);
     // predicate maps turn the value into a Bool: only SUM/ALL/ANY/COUNT make sense
     switch (dtype) {

@@ -60,6 +60,25 @@ struct MinTraits {
     __device__ static __forceinline__ A lift(V v) { return v; }
     __device__ static __forceinline__ A comb(A a, A b) { return jl::min(a, b); }
 };
+// extrema(localpart) in ONE pass (reference src/mapreduce.jl:124-131): the accumulator is the (min, max) pair
+template <typename T>
+struct Pair {
+    T lo, hi;
+};
+template <typename T>
+struct ExtremaTraits {
+    using A = Pair<T>;
+    __device__ static __forceinline__ A identity() { return A{highest_of<T>(), lowest_of<T>()}; }
+    __device__ static __forceinline__ A tile(A a, A b) { return A{jl::min(a.lo, b.lo), jl::max(a.hi, b.hi)}; }
+    __device__ static __forceinline__ A lift(A v) { return v; }
+    __device__ static __forceinline__ A comb(A a, A b) { return tile(a, b); }
+};
+template <typename T>
+struct ExtMapF {
+    using V = Pair<T>;
+    T p;
+    __device__ __forceinline__ V operator()(T x) const { return V{x, x}; }
+};
 struct CountTraits {  // V = int (0/1) ; all / any / count all reduce to "number of trues"
     using A = long long;
     __device__ static __forceinline__ A identity() { return 0; }
@@ -99,7 +118,15 @@ struct PredF {
 // ---- shuffles for 4- and 8-byte accumulators -------------------------------------------------------
 template <typename A>
 __device__ __forceinline__ A shfl_down(A v, int d) {
-    if constexpr (sizeof(A) == 8) {
+    if constexpr (sizeof(A) == 16) {
+        int w[4];
+        memcpy(w, &v, 16);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = __shfl_down_sync(0xffffffffu, w[k], d);
+        A r;
+        memcpy(&r, w, 16);
+        return r;
+    } else if constexpr (sizeof(A) == 8) {
         long long x;
         memcpy(&x, &v, 8);
         int lo = __shfl_down_sync(0xffffffffu, (int)(x & 0xffffffffll), d);

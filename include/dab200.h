@@ -67,7 +67,9 @@ enum {
     DAB_MIN = 3,   /* Julia min                                                                  */
     DAB_ALL = 4,   /* Base._all  (src/mapreduce.jl:97-104)  result int64 0/1                     */
     DAB_ANY = 5,   /* Base._any  (src/mapreduce.jl:106-113) result int64 0/1                     */
-    DAB_COUNT = 6  /* Base.count (src/mapreduce.jl:115-122) result int64                         */
+    DAB_COUNT = 6, /* Base.count (src/mapreduce.jl:115-122) result int64                         */
+    DAB_EXTREMA = 7 /* Base.extrema (src/mapreduce.jl:124-131) in ONE pass: the result slot holds (min, max) as two T (dab_reduce
+                       only, MAP_ID only; the cross-worker fold takes min of mins / max of maxes)            */
 };
 
 /* ---- map functions f of mapreduce(f, op, A) / unary broadcast ------------------------ */

@@ -233,7 +233,8 @@ static float fast_max_f32(const float* a, size_t n) {
 /* ---------------------------------------------------------------- P workers, one thread each */
 /* Each worker w owns chunk w of n_per elements (allocated + first-touched by its own thread), the
  * way the reference runs one single-threaded Julia process per worker.
- * op: 0 = affine in place (map!(x->a*x+b, d, d)), 1 = sum, 2 = maximum, 3 = affine then sum.
+ * op: 0 = affine in place (map!(x->a*x+b, d, d)), 1 = sum, 2 = maximum, 3 = affine then sum, 4 = sum(dims=1) of the chunk as a
+ * 4096-row matrix, 5 = memcpy of the chunk.
  * Runs `iters` timed passes after `warm` warm-ups; returns best-of seconds per pass (wall time of
  * the slowest worker + the caller-side fold), writes the folded result of the last pass. */
 typedef struct {
@@ -249,14 +250,30 @@ static void* worker_main(void* p) {
     worker_arg* g = (worker_arg*)p;
     float* x = (float*)aligned_alloc(64, ((g->n_per * sizeof(float) + 63) / 64) * 64);
     orc_rand_u01_f32(x, g->seed, (uint64_t)g->w * g->n_per, g->n_per);
+    /* op 4: sum(A, dims=1) of the chunk seen as a (4096 x n_per/4096) column-major matrix (per-column pairwise, A.3);
+     * op 5: memcpy of the chunk (generous upper bound for the reference's serialise + TCP slab fetch) */
+    const size_t rows = 4096, cols = g->n_per / rows;
+    float* aux = NULL;
+    if (g->op == 4) aux = (float*)calloc(cols ? cols : 1, sizeof(float));
+    if (g->op == 5) aux = (float*)aligned_alloc(64, ((g->n_per * sizeof(float) + 63) / 64) * 64);
     for (int it = 0; it < g->passes; ++it) {
         pthread_barrier_wait(g->bar); /* pass start */
         if (g->op == 0 || g->op == 3) orc_affine_f32(x, x, g->a, g->b, g->n_per);
         if (g->op == 1 || g->op == 3) g->partial[g->w] = orc_sum_f32(x, g->n_per, 8, 4);
         if (g->op == 2) g->partial[g->w] = fast_max_f32(x, g->n_per);
+        if (g->op == 4) {
+            memset(aux, 0, cols * sizeof(float));
+            orc_sumdim_f32(x, 1, rows, cols, aux, 8, 4);
+            g->partial[g->w] = aux[cols / 2];
+        }
+        if (g->op == 5) {
+            memcpy(aux, x, g->n_per * sizeof(float));
+            g->partial[g->w] = aux[g->n_per / 2];
+        }
         pthread_barrier_wait(g->bar); /* pass end */
     }
     free(x);
+    free(aux);
     return NULL;
 }
 

@@ -19,15 +19,14 @@ and a halo fetch otherwise; allocating broadcast / ``map`` build the result with
 from __future__ import annotations
 
 import ctypes as C
-import math
 import struct
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
 from . import _lib
-from ._darray import B200Array, DArray, SubDArray, dab_dtype, darray, makelocal
-from .layout import default_procs, make_layout, rlen, shape_of
+from ._darray import B200Array, DArray, dab_dtype, darray, makelocal
+from .layout import shape_of
 from .runtime import runtime
 
 # Julia-type tags and the promotion lattice

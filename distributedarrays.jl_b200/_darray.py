@@ -20,8 +20,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from .layout import (Layout, Range, contains, default_procs, layout_from_chunk_shapes, make_layout, rlen, shape_of,
-                     slab_plan)
+from .layout import Layout, Range, default_procs, layout_from_chunk_shapes, make_layout, rlen, shape_of, slab_plan
 from .runtime import Runtime, runtime
 
 _DT = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64, np.dtype(np.int32): _lib.I32,

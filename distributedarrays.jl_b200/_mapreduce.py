@@ -15,14 +15,14 @@ from __future__ import annotations
 import builtins
 import ctypes as C
 import operator
-from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
+from typing import Callable, Dict, Optional, Sequence, Tuple
 
 import numpy as np
 
 from . import _lib
 from ._broadcast import Expr, broadcast, tag_of, trace, _NPT
 from ._darray import B200Array, DArray, dab_dtype, np_dtype
-from .layout import Layout, collapse_for_region, ravel, rlen, shape_of, unravel
+from .layout import Layout, collapse_for_region, ravel, shape_of, unravel
 
 _OPS = {"+": _lib.SUM, "add": _lib.SUM, "sum": _lib.SUM, "*": _lib.PROD, "mul": _lib.PROD, "prod": _lib.PROD, "max": _lib.MAX,
         "min": _lib.MIN}

@@ -29,7 +29,6 @@ Indices are 1-based inclusive ranges ``(lo, hi)`` exactly as in the reference.
 from __future__ import annotations
 
 import itertools
-import math
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional, Sequence, Tuple
 

@@ -2,9 +2,6 @@
 (op, value type) combination the host runtime can request, and unsupported combinations are refused, not silently served."""
 import ctypes as C
 
-import numpy as np
-import pytest
-
 
 def _check(dab, f, tags, op, arrays=None):
     from darray_b200 import _lib

@@ -18,7 +18,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import darray_b200 as dab  # noqa: E402
 from darray_b200 import _lib  # noqa: E402
-from oracle import core as ocore  # noqa: E402
 from oracle import darray_oracle as orc  # noqa: E402
 
 F32 = np.float32

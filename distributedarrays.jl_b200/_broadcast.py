@@ -564,3 +564,38 @@ def map_inplace(f: Callable, dest: DArray, src: DArray) -> DArray:
 
 
 map_bang = map_inplace
+
+
+def map_localparts(f: Callable, A, B=None) -> DArray:
+    """``map_localparts(f, d1, d2)`` and the binary operators built on it -- ``+ - div mod rem & | xor`` between two DArrays or
+    a DArray and an Array of the same element type (reference src/mapreduce.jl:137-189).  The result keeps the layout of the
+    (first) DArray argument (``DArray(d1) do I ... end``, :138-140), NOT the default layout an allocating broadcast would pick; a
+    second DArray with different cuts is first brought to that layout (``samedist``, :172-178) -- here by the halo fetch inside
+    the fused kernel launch.  ``f`` acts elementwise (traced like any broadcast function)."""
+    lead = A if isinstance(A, DArray) else B
+    if not isinstance(lead, DArray):
+        raise TypeError("map_localparts needs at least one DArray")
+    args = (A,) if B is None else (A, B)
+    for a in args:
+        shp = a.dims if isinstance(a, DArray) else tuple(np.shape(a))
+        if tuple(shp) != tuple(lead.dims):
+            raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"DimensionMismatch: {lead.dims} vs {shp}")   # samedist, :173
+        dt = a.dtype if isinstance(a, (DArray, np.ndarray)) else np.asarray(a).dtype
+        if np.dtype(dt) != lead.dtype:
+            raise TypeError(f"MethodError: no method matching op(::DArray{{{lead.dtype}}}, ::{type(a).__name__}{{{np.dtype(dt)}}}) "
+                            "(the reference defines these operators for equal element types only)")
+    expr = trace(f, [_arg_tag(a) for a in args])
+    rt = lead.rt
+    out_dt = _NPT[expr.jt]
+    from ._darray import darray_like
+    dest = darray_like(lambda I: B200Array.empty(rt, shape_of(I), out_dt), lead, dtype=out_dt)
+    _prepare_remote_reads(dest.layout, rt, args)
+    for pid, out in dest.chunks.items():
+        I = dest.layout.localindices(pid)
+        largs = [_localise(rt, a, I, pid) for a in args]
+        run_local(rt, expr, out, largs)
+        for la in largs:
+            if la.temp and la.arr is not None:
+                rt.sync()
+                la.arr.free()
+    return dest

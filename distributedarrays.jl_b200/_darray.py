@@ -269,6 +269,27 @@ class DArray:
         a = to_array(self)
         return a.astype(dtype) if dtype is not None else a
 
+    # ---- binary operators between (D)Arrays of one element type: map_localparts (reference src/mapreduce.jl:134-189) ---------
+    def _mlp(self, other, f, swap=False):
+        from ._broadcast import map_localparts
+        if swap:
+            return map_localparts(f, other, self)
+        return map_localparts(f, self, other)
+
+    def __neg__(self):
+        from ._broadcast import map_
+        return map_(lambda x: -x, self)                       # Base.:(-)(D::DArray) = map(-, D)  (:134)
+
+    def __add__(self, o): return self._mlp(o, lambda a, b: a + b)
+    def __radd__(self, o): return self._mlp(o, lambda a, b: a + b, True)
+    def __sub__(self, o): return self._mlp(o, lambda a, b: a - b)
+    def __rsub__(self, o): return self._mlp(o, lambda a, b: a - b, True)
+    def __and__(self, o): return self._mlp(o, lambda a, b: a & b)
+    def __or__(self, o): return self._mlp(o, lambda a, b: a | b)
+    def __xor__(self, o): return self._mlp(o, lambda a, b: a ^ b)
+    def __floordiv__(self, o): return self._mlp(o, lambda a, b: a // b)       # div (truncated)
+    def __mod__(self, o): return self._mlp(o, lambda a, b: a % b)             # rem (Julia's %)
+
 
 def _oob(k, s):
     raise IndexError(f"BoundsError: index {k} out of range for dimension of size {s}")

@@ -105,3 +105,26 @@ def test_full_size_dot_and_general_mapreduce_rate(dab, rt1):
     assert abs(d - exact) <= 1e-6 * exact
     g = float(dab.mapreduce(lambda v: 2 * v + 1, "+", x))
     assert abs(g - (2 * exact + n)) <= 1e-6 * (2 * exact + n)
+
+
+def test_map_localparts_operators(dab, rt8):
+    """reference src/mapreduce.jl:134-189: + - div mod rem & | xor between DArrays / Arrays of ONE element type; the result keeps
+    the first DArray's layout; a differently cut second DArray is brought to it (samedist)."""
+    rng = np.random.default_rng(37)
+    A = rng.integers(-40, 40, (30, 44)).astype(np.int64)
+    B = rng.integers(1, 9, (30, 44)).astype(np.int64)
+    a = dab.distribute(A, dist=(2, 4))
+    b = dab.distribute(B, dist=(8, 1))                       # different cuts -> samedist
+    for got, want in ((a + b, A + B), (a - b, A - B), (a & b, A & B), (a | b, A | B), (a ^ b, A ^ B), (a // b, np.trunc(A / B).astype(np.int64)),
+                      (a % b, np.fmod(A, B)), (-a, -A), (a + B, A + B), (A - b, A - B)):
+        assert isinstance(got, dab.DArray) and np.array_equal(dab.to_array(got), want)
+    s = a + b
+    assert s.layout.grid == (2, 4) and s.indices == a.indices and s.layout.pids == a.layout.pids     # layout of the first DArray
+    assert (A - b).indices == b.indices
+    F = rng.standard_normal((30, 44))
+    f = dab.distribute(F)
+    assert np.array_equal(dab.to_array(f + f), F + F) and np.array_equal(dab.to_array(f - F), F - F)
+    with pytest.raises(dab.DimensionMismatch):
+        a + dab.distribute(A[:, :40])
+    with pytest.raises(TypeError):
+        a + f                                              # Int64 + Float64 DArrays: no such method in the reference

@@ -252,6 +252,71 @@ __global__ void __launch_bounds__(RD_THREADS) rdim_strided_kernel(const T* __res
     }
 }
 
+// ---- non-leading dim, vectorised: each thread owns 16 bytes (VPT consecutive outputs along `inner`) and walks r with 16-byte loads
+// (512 contiguous bytes per warp load instruction); needs inner % VPT == 0 and a 16-byte aligned base
+template <typename T, typename Map, typename R, typename Out>
+__global__ void __launch_bounds__(RD_THREADS) rdim_strided_vec_kernel(const T* __restrict__ x, size_t inner, size_t red, size_t outer,
+                                                                       int nsplit, Map map, typename R::A* __restrict__ partials,
+                                                                       Out* __restrict__ out, int accumulate) {
+    using A = typename R::A;
+    constexpr int VPT = 16 / sizeof(T);
+    constexpr int UNROLL = 4;
+    const size_t nout = inner * outer;
+    const size_t nvout = nout / VPT;                 // vectors of outputs
+    const size_t ivec = inner / VPT;                 // vectors per column
+    const size_t kblocks = (nvout + RD_THREADS - 1) / RD_THREADS;
+    const size_t work = kblocks * (size_t)nsplit;
+    const size_t split_len = (red + nsplit - 1) / nsplit;
+    for (size_t w = blockIdx.x; w < work; w += gridDim.x) {
+        const size_t kb = w % kblocks;
+        const size_t sp = w / kblocks;
+        const size_t kv = kb * RD_THREADS + threadIdx.x;
+        if (kv >= nvout) continue;
+        const size_t o = kv / ivec;
+        const size_t iv = kv - o * ivec;
+        size_t lo = sp * split_len, hi = lo + split_len;
+        if (hi > red) hi = red;
+        const int4* p = reinterpret_cast<const int4*>(x + inner * (o * red)) + iv;   // + r * ivec per step in r
+        A acc[VPT];
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) acc[k] = R::identity();
+        size_t r = lo;
+        for (; r + UNROLL <= hi; r += UNROLL) {
+            int4 v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) v[u] = ld_stream(p + (r + u) * ivec);
+            typename Map::V m[UNROLL][VPT];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                Pack<T> pk = as_pack<T>(v[u]);
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) m[u][k] = map(pk.v[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) {
+                auto t = R::tile(R::tile(m[0][k], m[1][k]), R::tile(m[2][k], m[3][k]));
+                acc[k] = R::comb(acc[k], R::lift(t));
+            }
+        }
+        for (; r < hi; ++r) {
+            Pack<T> pk = as_pack<T>(ld_stream(p + r * ivec));
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) acc[k] = R::comb(acc[k], R::lift(map(pk.v[k])));
+        }
+        const size_t k0 = kv * VPT;
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) {
+            if (nsplit == 1) {
+                A a = acc[k];
+                if (accumulate) a = R::comb((A)out[k0 + k], a);
+                out[k0 + k] = narrow<A, Out>(a);
+            } else {
+                partials[sp * nout + k0 + k] = acc[k];
+            }
+        }
+    }
+}
+
 // ---- ordered fold of the split partials: thread per output -----------------------------------------------------------------
 template <typename R, typename Out>
 __global__ void __launch_bounds__(RD_THREADS) rdim_finish_kernel(const typename R::A* __restrict__ partials, size_t nout, int nsplit,
@@ -316,7 +381,9 @@ int32_t launch_rdim(dab_ctx* ctx, const T* x, size_t inner, size_t red, size_t o
         }
         return DAB_OK;
     }
-    size_t base_ctas = (inner * outer + RD_THREADS - 1) / RD_THREADS;
+    // 16-byte path when whole vectors of outputs line up; needs enough vector-outputs to be worth it
+    const bool vec = (inner % (16 / sizeof(T)) == 0) && (((uintptr_t)x & 15) == 0) && (inner * outer / (16 / sizeof(T)) >= 4096);
+    size_t base_ctas = vec ? (inner * outer / (16 / sizeof(T)) + RD_THREADS - 1) / RD_THREADS : (inner * outer + RD_THREADS - 1) / RD_THREADS;
     // split r so that the work items fill >= 4 waves of the persistent grid (a 1.08-wave launch loses ~45 % to the tail), while
     // every split keeps >= 256 rows so that the partial buffer stays < 1 % of the input
     size_t max_split = red / 256;
@@ -330,8 +397,13 @@ int32_t launch_rdim(dab_ctx* ctx, const T* x, size_t inner, size_t red, size_t o
         if (st != DAB_OK) return st;
         partials = (A*)ctx->dim_scratch;
     }
-    int grid = dab_persistent_grid(ctx, rdim_strided_kernel<T, Map, R, Out>, RD_THREADS, base_ctas * (size_t)nsplit);
-    rdim_strided_kernel<T, Map, R, Out><<<grid, RD_THREADS, 0, ctx->stream>>>(x, inner, red, outer, nsplit, map, partials, out, accumulate);
+    if (vec) {
+        int grid = dab_persistent_grid(ctx, rdim_strided_vec_kernel<T, Map, R, Out>, RD_THREADS, base_ctas * (size_t)nsplit);
+        rdim_strided_vec_kernel<T, Map, R, Out><<<grid, RD_THREADS, 0, ctx->stream>>>(x, inner, red, outer, nsplit, map, partials, out, accumulate);
+    } else {
+        int grid = dab_persistent_grid(ctx, rdim_strided_kernel<T, Map, R, Out>, RD_THREADS, base_ctas * (size_t)nsplit);
+        rdim_strided_kernel<T, Map, R, Out><<<grid, RD_THREADS, 0, ctx->stream>>>(x, inner, red, outer, nsplit, map, partials, out, accumulate);
+    }
     DAB_LAUNCHED(ctx);
     if (nsplit > 1) {
         size_t nout = inner * outer;

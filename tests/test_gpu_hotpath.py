@@ -344,7 +344,9 @@ def test_reference_sum_dims_errors(dab, rt8):
                                         ((1000, 5000), 1), ((1001, 3000), 1), ((64, 200000), 1), ((36, 100001), 1), ((20, 100001), 1),
                                         ((7, 50000), 1), ((2, 40000), 1), ((3000, 2400), 1),
                                         # strided kernel with small inner / split r
-                                        ((64, 128, 700), 2), ((3, 100000, 2), 2), ((1030, 5000), 2)])
+                                        ((64, 128, 700), 2), ((3, 100000, 2), 2), ((1030, 5000), 2),
+                                        # vectorised strided kernel (16-byte loads along inner), without and with the r-split
+                                        ((65536, 600), 2), ((32768, 4100), 2)])
 def test_reducedim_shapes_f32(dab, rt2, shape, dims):
     n = int(np.prod(shape))
     A = orc.rand_u01(21, 0, n).reshape(shape, order="F")

@@ -269,6 +269,10 @@ class DArray:
         a = to_array(self)
         return a.astype(dtype) if dtype is not None else a
 
+    # NumPy must defer to the reflected operators below (Array - DArray is a DArray, reference src/mapreduce.jl:186), instead of
+    # gathering the DArray through __array__ and computing on the host
+    __array_ufunc__ = None
+
     # ---- binary operators between (D)Arrays of one element type: map_localparts (reference src/mapreduce.jl:134-189) ---------
     def _mlp(self, other, f, swap=False):
         from ._broadcast import map_localparts

@@ -123,6 +123,15 @@ __global__ void __launch_bounds__(RD_THREADS, 8) reduce_kernel(const T* __restri
             A wide = fin;
             memcpy((char*)out + 8, &wide, sizeof(A));
             if (sizeof(A) < 8) memset((char*)out + 8 + sizeof(A), 0, 8 - sizeof(A));
+            if (fc.host_out && fc.nranks <= 1) {
+                // single worker: the scalar goes straight into pinned host memory (zero-copy), no D2H memcpy launch
+                unsigned long long bits = 0;
+                memcpy(&bits, &res, sizeof(Out));
+                volatile unsigned long long* h = reinterpret_cast<volatile unsigned long long*>(fc.host_out);
+                h[0] = bits;
+                h[1] = 0ull;
+                __threadfence_system();
+            }
         } else {  // extrema: the (min, max) pair fills the slot (8 bytes for 4-byte T, 16 for 8-byte T)
             memset(out, 0, 16);
             memcpy(out, &fin, sizeof(A));
@@ -209,6 +218,10 @@ int32_t launch_reduce(dab_ctx* ctx, const T* x, size_t n, Map map, void* out, in
         fc.seq = ++ctx->mbox_seq;
         fc.rank = ctx->rank;
         fc.nranks = ctx->mbox_ranks;
+        fc.op = ctx->fuse_op;
+    } else if (ctx->fuse_op >= 0) {
+        fc.host_out = ctx->host_slot;  // one worker: zero-copy scalar to the host, nothing to combine
+        fc.nranks = 1;
         fc.op = ctx->fuse_op;
     }
     reduce_kernel<T, Map, R, Out><<<(unsigned)grid, RD_THREADS, 0, ctx->stream>>>(x, n, head, map, (typename R::A*)ctx->block_partials,

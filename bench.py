@@ -112,8 +112,8 @@ def cpu_leg(log2n_per_worker, steps, warmup, workers=None):
             cand.append(p)
             p //= 2
         for p in cand or [cores]:
-            _, m, _ = ocore.workers_run(3, p, 1 << 22, SEED, A_COEF, B_COEF, 1, 2)
-            tried[p] = 12.0 * (1 << 22) * p / m / 1e9
+            _, m, _ = ocore.workers_run(3, p, n_per, SEED, A_COEF, B_COEF, 1, 2)   # same chunk size as the timed run (>> LLC)
+            tried[p] = 12.0 * n_per * p / m / 1e9
         P = max(tried, key=tried.get)
     best, mean, res = ocore.workers_run(3, P, n_per, SEED, A_COEF, B_COEF, max(1, warmup), max(1, steps))
     gbs = 12.0 * n_per * P / mean / 1e9

@@ -361,6 +361,80 @@ def test_reducedim_shapes_f32(dab, rt2, shape, dims):
     assert si.dtype == np.int64 and np.array_equal(si, Ai.astype(np.int64).sum(axis=dims - 1, keepdims=True))
 
 
+def test_randomized_layouts_slices_and_reductions(dab, rt8):
+    """Seeded random sweep: random shapes (1-3 dims), random explicit grids, random unit-range slices, every dims subset -- halo
+    reads bit-exact, integer reductions exact, layouts identical to the oracle's."""
+    rng = np.random.default_rng(2024)
+    for case in range(40):
+        nd = int(rng.integers(1, 4))
+        shape = tuple(int(x) for x in rng.integers(1, 33, nd))
+        # a random grid with <= 8 chunks, each dim split at most into its extent
+        grid = []
+        left = 8
+        for s in shape:
+            g = int(rng.integers(1, min(s, left) + 1))
+            grid.append(g)
+            left = max(1, left // g)
+        A = rng.integers(-20, 20, shape).astype(np.int64)
+        procs = list(range(1, int(np.prod(grid)) + 1))
+        d = dab.distribute(A, procs=procs, dist=grid)
+        od = orc.distribute(A, procs=procs, dist=grid)
+        assert d.indices == od.indices and d.cuts == od.cuts, (shape, grid)
+        sl = []
+        for s in shape:
+            lo = int(rng.integers(0, s))
+            sl.append(slice(lo, int(rng.integers(lo + 1, s + 1))))
+        assert np.array_equal(np.asarray(d[tuple(sl)]), A[tuple(sl)]), (shape, grid, sl)
+        assert dab.sum(d) == A.sum() and dab.maximum(d) == A.max() and dab.extrema(d) == (A.min(), A.max())
+        for k in range(1, nd + 1):
+            dims = tuple(sorted(int(x) + 1 for x in rng.choice(nd, size=k, replace=False)))
+            ax = tuple(x - 1 for x in dims)
+            R = dab.sum(d, dims=dims)
+            oR = orc.darray_mapreducedim(None, "+", od, dims)
+            assert R.indices == oR.indices and R.layout.pids == oR.pids, (shape, grid, dims)
+            assert np.array_equal(dab.to_array(R), A.sum(axis=ax, keepdims=True)), (shape, grid, dims)
+        B = rng.integers(1, 5, shape).astype(np.int64)
+        e = dab.distribute(B)                                        # default layout: usually differs from `grid`
+        assert np.array_equal(dab.to_array(dab.broadcast(lambda x, y: x * y - 1, d, e)), A * B - 1)
+        assert np.array_equal(dab.to_array(d + e), A + B)
+        d.close()
+        e.close()
+    dab.d_closeall()
+    assert dab.registry_size() == 0
+
+
+def test_full_size_c4_c5(dab, rt8):
+    """BASELINE configs 4 and 5 at full size on one GPU (8 workers, grid (2,4), 2 GiB chunks): sum(A, dims=1) of 65536 x 65536
+    Float32 -- 64 sampled columns against the exact integer column sums, all columns through the identity sum(R) == sum(A) --
+    and a 256 MiB slab read from non-owned chunks, bit-exact on sampled windows."""
+    if rt8.device_info()["free_bytes"] < 24 * (1 << 30):
+        pytest.skip("not enough free HBM")
+    n = 65536
+    A = dab.drand((n, n), dtype=F32, seed=11)
+    assert A.layout.grid == (2, 4) and dab.layout.shape_of(A.indices[0]) == (32768, 16384)
+    R = dab.sum(A, dims=1)
+    assert R.dims == (1, n) and R.layout.grid == (1, 4) and R.layout.pids == [1, 3, 5, 7]   # owners: grid row 1 (src/mapreduce.jl:44)
+    r = dab.to_array(R)[0]
+    for c in list(range(0, n, 2048)) + [n - 1, 16383, 16384, 49151]:
+        exact = ocore.rand_ksum(11, c * n, n) * 2.0 ** -24
+        assert abs(float(r[c]) - exact) <= TOL * exact, c
+    tot = float(dab.sum(A))
+    assert abs(float(r.astype(np.float64).sum()) - tot) <= 2e-6 * tot
+    mx = dab.to_array(dab.maximum(A, dims=1))[0]
+    assert mx.max() == dab.maximum(A) and (mx <= 1).all() and (mx > 0.99).all()
+    # C5: 2^26 elements = 256 MiB, rows 100..100+4096 x columns 20000..20000+16384: spans the chunks of workers 3 and 5
+    # (grid row 1, grid columns 2 and 3), neither of which is the reading worker's own chunk
+    sub = A[100:100 + 4096, 20000:20000 + 16384]
+    dev = sub.to_device()
+    from darray_b200 import _lib
+    host = np.empty(4096, dtype=F32)
+    for col in (0, 1, 7777, 16383):
+        _lib.call("dab_d2h", rt8.ctx, C.c_void_p(host.ctypes.data), C.c_void_p(dev.ptr + 4 * 4096 * col), 4 * 4096)
+        rt8.sync()
+        assert np.array_equal(host, orc.rand_u01(11, (20000 + col) * n + 100, 4096))
+    dev.free()
+
+
 def test_full_size_8gib_chunk(dab, rt1):
     """north_star: "an 8 GiB-per-chunk Float32 DArray" = 2^31 elements: 64-bit indexing, in-place map!, sum, maximum."""
     n = 1 << 31

@@ -230,8 +230,8 @@ Driver& driver() {
 }
 
 struct Compiled {
-    CUfunction linear = nullptr, general = nullptr;
-    int occ_linear = 1, occ_general = 1;
+    CUfunction linear = nullptr, general = nullptr, rows = nullptr;
+    int occ_linear = 1, occ_general = 1, occ_rows = 1;
 };
 
 std::mutex g_mu;
@@ -331,6 +331,43 @@ std::string build_source(const char* expr, int32_t out_dt, int nargs, const int3
     s += "    o[(i64)i0 * p.ostr[0] + (i64)i1 * p.ostr[1] + (i64)i2 * p.ostr[2] + (i64)i3 * p.ostr[3]] = (OUT_T)DAB_EXPR;\n"
          "  }\n"
          "}\n";
+    // ---- "rows" kernel: the destination is dense, every array argument is either dense along dim 0 (stride 1, 16-byte aligned
+    // rows) or extruded along dim 0 (stride 0): each thread produces 4 consecutive elements of one row with vector accesses and
+    // decomposes the index once per 4 elements.  Serves  a .- m  with a 1 x n  m,  a .* v  with a column vector v, ... (the
+    // extrusion cases of reference src/broadcast.jl:103-120) at streaming speed.
+    s += "extern \"C\" __global__ void __launch_bounds__(256) dab_bc_rows(BcParams p) {\n"
+         "  const u64 n0v = p.shape[0] / 4, n1 = p.shape[1], n2 = p.shape[2];\n"
+         "  const u64 total = n0v * n1 * n2 * p.shape[3];\n"
+         "  OUT_T* o = (OUT_T*)p.out;\n";
+    for (int k = 0; k < nargs; ++k) {
+        std::string K = std::to_string(k);
+        if (is_arr[k]) s += "  const T" + K + "* q" + K + " = (const T" + K + "*)p.ptr[" + K + "];\n  const bool d" + K + " = p.str[" + K + "][0] != 0;\n";
+        else s += "  const T" + K + " a" + K + " = bits_as<T" + K + ">(p.scalar[" + K + "]);\n";
+    }
+    s += "  const u64 stride = (u64)gridDim.x * blockDim.x;\n"
+         "  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {\n"
+         "    const u64 i0 = (i % n0v) * 4, t0 = i / n0v, i1 = t0 % n1, t1 = t0 / n1, i2 = t1 % n2, i3 = t1 / n2;\n";
+    for (int k = 0; k < nargs; ++k)
+        if (is_arr[k]) {
+            std::string K = std::to_string(k);
+            s += "    const i64 f" + K + " = (i64)i1 * p.str[" + K + "][1] + (i64)i2 * p.str[" + K + "][2] + (i64)i3 * p.str[" + K + "][3];\n";
+            s += "    VecN<T" + K + ", 4> v" + K + ";\n";
+            s += "    if (d" + K + ") v" + K + " = *(const VecN<T" + K + ", 4>*)(q" + K + " + f" + K + " + (i64)i0);\n";
+            s += "    else { const T" + K + " b = q" + K + "[f" + K + "]; v" + K + ".v[0] = b; v" + K + ".v[1] = b; v" + K + ".v[2] = b; v" + K + ".v[3] = b; }\n";
+        }
+    s += "    VecN<OUT_T, 4> r;\n"
+         "#pragma unroll\n"
+         "    for (int j = 0; j < 4; ++j) {\n";
+    for (int k = 0; k < nargs; ++k)
+        if (is_arr[k]) {
+            std::string K = std::to_string(k);
+            s += "      const T" + K + " a" + K + " = v" + K + ".v[j];\n";
+        }
+    s += "      r.v[j] = (OUT_T)DAB_EXPR;\n"
+         "    }\n"
+         "    *(VecN<OUT_T, 4>*)(o + (i64)i0 + (i64)i1 * p.ostr[1] + (i64)i2 * p.ostr[2] + (i64)i3 * p.ostr[3]) = r;\n"
+         "  }\n"
+         "}\n";
     return s;
 }
 
@@ -373,8 +410,10 @@ int32_t compile(dab_ctx* ctx, const std::string& src, Compiled* out) {
         return dab_fail(ctx, DAB_ERR_NVRTC, "cuModuleLoadData failed: %s", es);
     }
     if (drv.ModuleGetFunction(&out->linear, mod, "dab_bc_linear") != CUDA_SUCCESS ||
-        drv.ModuleGetFunction(&out->general, mod, "dab_bc_general") != CUDA_SUCCESS)
+        drv.ModuleGetFunction(&out->general, mod, "dab_bc_general") != CUDA_SUCCESS ||
+        drv.ModuleGetFunction(&out->rows, mod, "dab_bc_rows") != CUDA_SUCCESS)
         return dab_fail(ctx, DAB_ERR_NVRTC, "cuModuleGetFunction failed");
+    if (drv.OccupancyMaxActiveBlocksPerMultiprocessor(&out->occ_rows, out->rows, 256, 0) != CUDA_SUCCESS || out->occ_rows < 1) out->occ_rows = 1;
     if (drv.OccupancyMaxActiveBlocksPerMultiprocessor(&out->occ_linear, out->linear, 256, 0) != CUDA_SUCCESS || out->occ_linear < 1)
         out->occ_linear = 1;
     if (drv.OccupancyMaxActiveBlocksPerMultiprocessor(&out->occ_general, out->general, 256, 0) != CUDA_SUCCESS || out->occ_general < 1)
@@ -644,11 +683,22 @@ int32_t dab_broadcast_expr(dab_ctx* ctx, const char* expr, int32_t out_dtype, vo
         }
         if (is_arr[k] && ((uintptr_t)arg_ptrs[k] % (4 * dab_dtype_size(arg_dtypes[k])))) linear = false;
     }
+    // rows kernel: dense destination, 4 | shape[0], every array argument dense-along-dim-0 with 4-element-aligned rows, or extruded
+    bool rows = !linear && shape[0] % 4 == 0 && out_strides[0] == 1 && ((uintptr_t)out % (4 * dab_dtype_size(out_dtype))) == 0;
+    for (int d = 1; d < 4 && rows; ++d)
+        if (shape[d] > 1 && out_strides[d] % 4) rows = false;
+    for (int k = 0; k < nargs && rows; ++k) {
+        if (!is_arr[k]) continue;
+        if (arg_strides[4 * k] == 0) continue;  // extruded along dim 0: scalar load per row
+        if (arg_strides[4 * k] != 1 || ((uintptr_t)arg_ptrs[k] % (4 * dab_dtype_size(arg_dtypes[k])))) rows = false;
+        for (int d = 1; d < 4 && rows; ++d)
+            if (shape[d] > 1 && arg_strides[4 * k + d] % 4) rows = false;
+    }
     Driver& drv = driver();
     void* args[] = {&p};
-    CUfunction fn = linear ? comp.linear : comp.general;
-    size_t work = (n + 255) / 256;
-    size_t grid = linear ? (n / 4) / 512 + 1 : (size_t)dab_grid_for(ctx, work, comp.occ_general);
+    CUfunction fn = linear ? comp.linear : (rows ? comp.rows : comp.general);
+    size_t work = rows ? (n / 4 + 255) / 256 : (n + 255) / 256;
+    size_t grid = linear ? (n / 4) / 512 + 1 : (size_t)dab_grid_for(ctx, work, rows ? comp.occ_rows : comp.occ_general);
     if (grid > 0x7fffffffull) return dab_fail(ctx, DAB_ERR_ARG, "array too large for one launch");
     CUresult cr = drv.LaunchKernel(fn, (unsigned)grid, 1, 1, 256, 1, 1, 0, (CUstream)ctx->stream, args, nullptr);
     if (cr != CUDA_SUCCESS) {

@@ -83,6 +83,14 @@ report("broadcast z .= abs.(x) (unary, 8 B/elem)", 8 * n, timed(lambda: dab.broa
 report("broadcast z .= x .- y .* x (NVRTC fused, 12 B/elem)", 12 * n, timed(lambda: dab.broadcast_into(z, lambda u, v: u - v * u, x, y)))
 report("broadcast z .= sqrt.(abs2.(x) .+ abs2.(y)) (NVRTC, 12 B/elem)", 12 * n, timed(lambda: dab.broadcast_into(z, lambda u, v: dab.sqrt(dab.abs2(u) + dab.abs2(v)), x, y)))
 report("sum(abs2, x) f32", 4 * n, timed(lambda: dab.sum(x, dab.abs2)))
+# extruded operands (reference test/darray.jl:885-898): a .- m with a 1 x n row m, a .* v with a column v; 8 B/elem
+M2 = dab.drand((16384, 16384), dtype=F32, seed=9)
+Z2 = dab.similar(M2)
+mrow = dab.drand((1, 16384), dtype=F32, seed=10)
+vcol = dab.drand((16384, 1), dtype=F32, seed=12)
+report("broadcast Z .= A .- m   (m 1 x n, extruded; NVRTC rows)", 8 * 16384 * 16384, timed(lambda: dab.broadcast_into(Z2, lambda u, v: u - v, M2, mrow)))
+report("broadcast Z .= A .* v   (v n x 1, extruded; NVRTC rows)", 8 * 16384 * 16384, timed(lambda: dab.broadcast_into(Z2, lambda u, v: u * v, M2, vcol)))
+M2.close(); Z2.close()
 report("count(x .> 0.5) f32", 4 * n, timed(lambda: dab.count(x, lambda v: v > 0.5)))
 report("extrema(x) f32 (2 passes)", 8 * n, timed(lambda: dab.extrema(x)))
 x.close(); y.close(); z.close()

@@ -107,15 +107,59 @@ function Base.copyto!(dest::B200Array{T}, bc::Broadcasted{<:B200Style}) where {T
         a, x, b = ab
         return map!(Affine{T}(a, b), dest, x)
     end
-    expr, args = lower(bc)                              # general tree -> "jl_sub(a0, jl_mul(a1, jl_sin(a2)))", (arrays/scalars...)
-    return broadcast_expr!(dest, expr, args)
+    return broadcast_expr!(dest, bc)                    # general tree -> "jl_sub(a0, jl_mul(a1, jl_sin(a2)))" -> NVRTC
 end
 match_affine(bc, ::Type{T}) where {T} =
     (bc.f === (+) && length(bc.args) == 2 && bc.args[1] isa Broadcasted && bc.args[1].f === (*) &&
      bc.args[1].args[1] isa T && bc.args[1].args[2] isa B200Array{T} && bc.args[2] isa T) ?
         (bc.args[1].args[1], bc.args[1].args[2], bc.args[2]) : nothing
-lower(bc) = error("DArrayB200: general broadcast lowering is provided by the host tracer; see distributedarrays.jl_b200/_broadcast.py")
-broadcast_expr!(dest, expr, args) = error("unreachable")
+# General trees: walk the Broadcasted and emit the C expression dab_broadcast_expr compiles with NVRTC (the same lowering the
+# Python tracer in distributedarrays.jl_b200/_broadcast.py performs; helper names are the jl_* functions of the JIT prelude).
+const FN2 = Dict{Any,String}((+) => "jl_add", (-) => "jl_sub", (*) => "jl_mul", (/) => "jl_div", rem => "jl_rem", mod => "jl_mod",
+                             div => "jl_idiv", max => "jl_max", min => "jl_min", (^) => "jl_pow", (<) => "jl_lt", (<=) => "jl_le",
+                             (>) => "jl_gt", (>=) => "jl_ge", (==) => "jl_eq", (!=) => "jl_ne", (&) => "jl_and", (|) => "jl_or", xor => "jl_xor")
+const FN1 = Dict{Any,String}((-) => "jl_neg", abs => "jl_abs", abs2 => "jl_abs2", sqrt => "jl_sqrt", inv => "jl_inv", floor => "jl_floor",
+                             ceil => "jl_ceil", sign => "jl_sign", sin => "jl_sin", cos => "jl_cos", tan => "jl_tan", exp => "jl_exp",
+                             log => "jl_log", tanh => "jl_tanh", isnan => "jl_isnan", identity => "")
+ctype(::Type{Float32}) = "float"; ctype(::Type{Float64}) = "double"; ctype(::Type{Int32}) = "int"; ctype(::Type{Int64}) = "long long"; ctype(::Type{Bool}) = "bool"
+literal(x::Float32) = "__int_as_float((int)0x$(string(reinterpret(UInt32, x), base = 16)))"
+literal(x::Float64) = "__longlong_as_double((long long)0x$(string(reinterpret(UInt64, x), base = 16))ULL)"
+literal(x::Integer) = "(($(ctype(typeof(x))))$(x))"
+literal(x::Bool) = x ? "true" : "false"
+
+# returns (expression string, element type); `args` collects the array / Ref-scalar leaves in order -> a0, a1, ...
+function lower(bc::Broadcasted, args::Vector{Any})
+    parts = [lower(a, args) for a in bc.args]
+    Ts = map(last, parts)
+    T = Base.promote_op(bc.f, Ts...)                                  # Julia's own result type: promotion stays exactly Julia's
+    conv = [Ti === Tp ? s : "(($(ctype(Tp)))($s))" for ((s, Ti), Tp) in zip(parts, promote_types(bc.f, Ts, T))]
+    name = length(conv) == 1 ? get(FN1, bc.f, nothing) : get(FN2, bc.f, nothing)
+    name === nothing && error("DArrayB200: $(bc.f) is not served by the broadcast lowering (no host fallback)")
+    (isempty(name) ? conv[1] : "$name($(join(conv, ", ")))", T)
+end
+lower(a::B200Array{T}, args) where {T} = (push!(args, a); ("a$(length(args) - 1)", T))
+lower(x::Number, args) = (literal(x), typeof(x))
+lower(r::Base.RefValue, args) = lower(r[], args)
+# comparison / arithmetic operands are promoted to a common type first (Base.promote); bitwise and comparison results keep Bool
+promote_types(f, Ts, T) = (f in (<, <=, >, >=, ==, !=)) ? fill(promote_type(Ts...), length(Ts)) : fill(T, length(Ts))
+
+function broadcast_expr!(dest::B200Array{T,N}, bc::Broadcasted) where {T,N}
+    args = Any[]
+    expr, Tr = lower(bc, args)
+    Tr === T || (expr = "(($(ctype(T)))($expr))")
+    shape = Csize_t[size(dest)..., ones(Int, 4 - N)...]
+    dense(sz) = Csize_t[cumprod([1; collect(sz)[1:end-1]])..., zeros(Int, 4 - length(sz))...]
+    ostr = dense(size(dest)); ostr[N+1:end] .= 0
+    strides = Csize_t[]
+    for a in args                                                        # 0 = extruded dim (src/broadcast.jl:112-113)
+        st = dense(size(a)); for d in 1:4; (d > ndims(a) || size(a, d) == 1) && (st[d] = 0); end; append!(strides, st)
+    end
+    check(ccall((:dab_broadcast_expr, libdab), Int32,
+                (Ptr{Cvoid}, Cstring, Int32, Ptr{Cvoid}, Ptr{Csize_t}, Ptr{Csize_t}, Int32, Ptr{Int32}, Ptr{Ptr{Cvoid}}, Ptr{Csize_t}, Ptr{UInt64}),
+                ctx(), expr, dab_dtype(T), dest.ptr, shape, ostr, length(args), Int32[dab_dtype(eltype(a)) for a in args],
+                Ptr{Cvoid}[a.ptr for a in args], strides, zeros(UInt64, length(args))), ctx())
+    dest
+end
 
 # ---- reductions --------------------------------------------------------------------------------------------------------------------
 const OPS = Dict{Any,Int32}(Base.add_sum => 0, (+) => 0, Base.mul_prod => 1, (*) => 1, max => 2, min => 3)

@@ -254,9 +254,23 @@ def main():
     except Exception as ex:  # never lose the main line because of the e2e leg
         e2e = {"value": None, "unit": "GB/s", "error": repr(ex)[:200]}
 
-    # ---- extras (not part of `value`): BASELINE configs 4 and 5 at this N
+    # ---- extras (not part of `value`): the TMA-staged variant of the broadcast kernel, BASELINE configs 4 and 5 at this N
     extras = {}
     if not args.no_extras:
+        try:
+            rt.set_option("ew_tma", 1)
+            ms_t, _ = timed(lambda: dab.broadcast_into(y, f, x), args.steps)
+            rt.set_option("ew_tma", 0)
+            ms_t = max_over_ranks(ms_t)
+            extras["broadcast_tma_variant"] = {"GBs_per_gpu": 8.0 * n_per * args.steps / (ms_t * 1e-3) / 1e9,
+                                               "what": "same y .= a.*x .+ b through the opt-in cp.async.bulk + mbarrier shared-memory ring "
+                                                       "(dab_set_option ew_tma=1); the default flat LDG/STG kernel is `kernels.broadcast_GBs_per_gpu`"}
+        except Exception as ex:
+            extras["broadcast_tma_variant"] = {"error": repr(ex)[:200]}
+            try:
+                rt.set_option("ew_tma", 0)
+            except Exception:
+                pass
         try:
             g = dab.defaultdist((65536, 65536), world)                   # (2,4) at N=8
             dimsA = (32768 * g[0], 16384 * g[1])                         # 32768 x 16384 Float32 (2 GiB) per GPU; exactly 65536^2 at N=8

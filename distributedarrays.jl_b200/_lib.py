@@ -59,6 +59,7 @@ _SIGS = {
     "dab_sync": (_i32, [_vp]),
     "dab_device_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_sz), C.POINTER(_sz)]),
     "dab_stream": (_i32, [_vp, _pvp]),
+    "dab_set_option": (_i32, [_vp, C.c_char_p, C.c_int64]),
     "dab_launch_count": (_i32, [_vp, C.POINTER(_u64)]),
     "dab_event_create": (_i32, [_vp, _pvp]),
     "dab_event_record": (_i32, [_vp, _vp]),

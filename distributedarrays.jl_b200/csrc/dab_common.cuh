@@ -36,6 +36,7 @@ struct dab_ctx {
     unsigned long long mbox_seq;
     int fuse_op;            // >= 0: the next launch_reduce appends the cross-rank combine for this DAB_* op
     struct dab_alloc_cache* cache;  // size-bucketed reuse of small cudaMalloc blocks (dab_core.cu)
+    int opt_ew_tma;         // dab_set_option("ew_tma"): route aligned unary elementwise launches through the TMA-staged kernel
     char err[512];
 };
 

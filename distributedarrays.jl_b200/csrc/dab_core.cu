@@ -188,6 +188,17 @@ int32_t dab_stream(dab_ctx* ctx, void** stream) {
     return DAB_OK;
 }
 
+// Tuning / experiment switches.  "ew_tma" = 1: unary elementwise kernels (dab_affine, dab_unary, dab_binary_scalar) use the
+// TMA-staged shared-memory ring instead of the default flat LDG/STG kernel (same results; measured slower, see dab_elementwise.cu).
+int32_t dab_set_option(dab_ctx* ctx, const char* key, int64_t value) {
+    if (!ctx || !key) return dab_fail(ctx, DAB_ERR_ARG, "null argument");
+    if (strcmp(key, "ew_tma") == 0) {
+        ctx->opt_ew_tma = value != 0;
+        return DAB_OK;
+    }
+    return dab_fail(ctx, DAB_ERR_ARG, "dab_set_option: unknown key %s", key);
+}
+
 int32_t dab_launch_count(dab_ctx* ctx, uint64_t* launches) {
     if (!ctx || !launches) return dab_fail(ctx, DAB_ERR_ARG, "null argument");
     *launches = ctx->launches;

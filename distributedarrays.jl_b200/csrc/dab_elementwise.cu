@@ -103,6 +103,100 @@ __global__ void __launch_bounds__(EW_THREADS) ew2_scalar_kernel(T* z, const T* x
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) z[i] = f(x[i], y[i]);
 }
 
+// ---- TMA-staged variant (opt-in: dab_set_option(ctx, "ew_tma", 1)) ----------------------------------------------------------------
+// The north-star design sketch asks for "TMA-staged tiles into shared memory"; this is that kernel: one elected thread streams
+// 32 KiB tiles global -> shared with cp.async.bulk (SASS UBLKCP.S.G) completing on an mbarrier ring (3 stages), all threads apply f
+// in place in shared memory, then the elected thread streams the tile shared -> global (UBLKCP.G.S, bulk async-group).  Persistent,
+// one CTA per SM.  Measured on B200 (tools/sweep_stream.cu, profiles/sweep_r1*.txt): 6.65-6.68 TB/s vs 6.95 TB/s for the flat LDG
+// kernel above -- every element is touched once, so staging buys no reuse and only adds a hop; it is therefore NOT the default.
+// Bit-identical results (tests/test_gpu_hotpath.py::test_affine_tma_variant).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "DAB_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DAB_WAIT_DONE;\n"
+        "bra DAB_WAIT_LOOP;\n"
+        "DAB_WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+constexpr int TMA_TILE_BYTES = 32768;
+constexpr int TMA_STAGES = 3;
+
+template <typename T, typename F>
+__global__ void __launch_bounds__(EW_THREADS) ew1_tma_kernel(T* __restrict__ y, const T* __restrict__ x, size_t ntiles, F f) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int VPT = 16 / sizeof(T);
+    constexpr int TILE_V = TMA_TILE_BYTES / 16;
+    constexpr size_t TILE_ELEMS = TMA_TILE_BYTES / sizeof(T);
+    int4* buf = reinterpret_cast<int4*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TMA_STAGES * TMA_TILE_BYTES);
+    const size_t mine = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TMA_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TMA_STAGES - 1 && (size_t)s < mine; ++s) {
+            const size_t tile = blockIdx.x + (size_t)s * gridDim.x;
+            mbar_expect_tx(&full[s], TMA_TILE_BYTES);
+            bulk_load(buf + (size_t)s * TILE_V, x + tile * TILE_ELEMS, TMA_TILE_BYTES, &full[s]);
+        }
+    }
+    for (size_t it = 0; it < mine; ++it) {
+        const int s = (int)(it % TMA_STAGES);
+        mbar_wait(&full[s], (uint32_t)((it / TMA_STAGES) & 1));
+        int4* p = buf + (size_t)s * TILE_V;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < TILE_V; i += EW_THREADS) {
+            Pack<T> pk = as_pack<T>(p[i]);
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) pk.v[k] = f(pk.v[k]);
+            p[i] = as_int4(pk);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk (async proxy) store
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const size_t tile = blockIdx.x + it * gridDim.x;
+            bulk_store(y + tile * TILE_ELEMS, p, TMA_TILE_BYTES);
+            bulk_commit();
+            const size_t nxt = it + TMA_STAGES - 1;
+            if (nxt < mine) {
+                const int sn = (int)(nxt % TMA_STAGES);
+                bulk_wait_read<1>();  // the store that last read stage sn (committed one iteration ago) has drained shared memory
+                mbar_expect_tx(&full[sn], TMA_TILE_BYTES);
+                bulk_load(buf + (size_t)sn * TILE_V, x + (blockIdx.x + nxt * gridDim.x) * TILE_ELEMS, TMA_TILE_BYTES, &full[sn]);
+            }
+        }
+    }
+    if (threadIdx.x == 0) bulk_wait_read<0>();
+}
+
 template <typename T>
 inline size_t head_of(const void* p, size_t n) {
     size_t h = ((16 - ((uintptr_t)p & 15)) & 15) / sizeof(T);
@@ -112,6 +206,25 @@ inline size_t head_of(const void* p, size_t n) {
 template <typename T, typename F>
 int32_t launch_ew1(dab_ctx* ctx, T* y, const T* x, size_t n, F f) {
     if (n == 0) return DAB_OK;
+    if (ctx->opt_ew_tma && (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && n * sizeof(T) >= (size_t)TMA_TILE_BYTES) {
+        // opt-in TMA-staged path for the 16-byte aligned bulk; the ragged tail goes through the regular kernel below
+        const size_t tile_elems = TMA_TILE_BYTES / sizeof(T);
+        const size_t ntiles = n / tile_elems;
+        const size_t smem = (size_t)TMA_STAGES * TMA_TILE_BYTES + 8 * TMA_STAGES;
+        static bool attr_set = false;
+        if (!attr_set) {
+            DAB_CUDA(ctx, cudaFuncSetAttribute(ew1_tma_kernel<T, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        int grid = ctx->sm_count < (int)ntiles ? ctx->sm_count : (int)ntiles;
+        ew1_tma_kernel<T, F><<<grid, EW_THREADS, smem, ctx->stream>>>(y, x, ntiles, f);
+        DAB_LAUNCHED(ctx);
+        const size_t done = ntiles * tile_elems;
+        if (done == n) return DAB_OK;
+        x += done;
+        y += done;
+        n -= done;
+    }
     if ((((uintptr_t)x) & 15) == (((uintptr_t)y) & 15) && (((uintptr_t)x) % sizeof(T)) == 0) {
         constexpr int UNROLL = 2;
         const size_t head = head_of<T>(x, n);

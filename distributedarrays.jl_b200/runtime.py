@@ -130,6 +130,10 @@ class Runtime:
         if ptr:
             _lib.call("dab_free_async", self.ctx, C.c_void_p(ptr))
 
+    def set_option(self, key: str, value: int):
+        """``dab_set_option``: e.g. ``set_option("ew_tma", 1)`` selects the TMA-staged elementwise kernel (same results)."""
+        _lib.call("dab_set_option", self.ctx, key.encode(), int(value))
+
     def launches(self) -> int:
         n = C.c_uint64(0)
         _lib.call("dab_launch_count", self.ctx, C.byref(n))

@@ -113,6 +113,9 @@ int32_t dab_sync(dab_ctx* ctx);
 int32_t dab_device_info(dab_ctx* ctx, int32_t* device, int32_t* sm_count, size_t* free_bytes, size_t* total_bytes);
 /* the ctx's cudaStream_t (as void*), so a host runtime can order its own work after ours. */
 int32_t dab_stream(dab_ctx* ctx, void** stream);
+/* tuning switches; "ew_tma" = 1 routes aligned unary elementwise launches through the TMA-staged (cp.async.bulk + mbarrier
+ * ring) kernel instead of the default flat LDG/STG kernel -- identical results, measured slower. */
+int32_t dab_set_option(dab_ctx* ctx, const char* key, int64_t value);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches claim). */
 int32_t dab_launch_count(dab_ctx* ctx, uint64_t* launches);
 

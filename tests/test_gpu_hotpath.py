@@ -86,6 +86,28 @@ def test_affine_bit_exact(dab, rt1, n, dtype):
         assert same_bits(dy.to_numpy()[:n - 3], want[1:n - 2])
 
 
+@pytest.mark.parametrize("n", [8192, 8192 * 3 + 5, (1 << 22) + 12345])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int64])
+def test_affine_tma_variant(dab, rt1, n, dtype):
+    """The opt-in TMA-staged kernel (cp.async.bulk + mbarrier ring; dab_set_option "ew_tma") gives bit-identical results to the
+    default kernel and to the oracle, including the ragged tail and in place."""
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal(n) * 100).astype(dtype)
+    a, b = dtype(3), dtype(-7)
+    want = orc.affine_unfused(a, x, b) if np.dtype(dtype).kind == "f" else (a * x + b)
+    d = dab.distribute(x)
+    y = dab.similar(d)
+    rt1.set_option("ew_tma", 1)
+    try:
+        dab.broadcast_into(y, lambda v: a * v + b, d)
+        assert rt1.last_kernel == "dab_affine" and same_bits(dab.to_array(y), want)
+        dab.map_inplace(lambda v: a * v + b, d, d)
+        assert same_bits(dab.to_array(d), want)
+        assert same_bits(dab.to_array(dab.map_(lambda v: abs(v), y)), np.abs(want))
+    finally:
+        rt1.set_option("ew_tma", 0)
+
+
 def test_affine_is_not_fma(dab, rt1):
     """a*x+b must be two roundings (Julia never contracts): pick values where fma(a,x,b) != (a*x)+b."""
     n = 1 << 16

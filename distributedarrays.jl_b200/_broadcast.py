@@ -504,8 +504,13 @@ def _prepare_remote_reads(dest_layout, rt, args):
 def broadcast_into(dest: DArray, f: Callable, *args) -> DArray:
     """``dest .= f.(args...)``: ``Base.copyto!(dest::DArray, bc::Broadcasted{Nothing})`` (reference src/broadcast.jl:65-85)."""
     shapes = [a.dims if isinstance(a, DArray) else (a.shape if isinstance(a, np.ndarray) else ()) for a in args]
-    if _bc_shape(list(shapes) + [()]) != tuple(dest.dims) and _bc_shape(shapes) != tuple(dest.dims):
-        raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"destination axes {dest.dims} are not compatible with source axes {_bc_shape(shapes)}")
+    # materialize!(dest, bc) instantiates the Broadcasted with axes(dest): every argument must be broadcastable TO dest's axes
+    # (each of its dims is 1 or equals dest's; missing trailing dims count as 1), else DimensionMismatch (src/broadcast.jl:66)
+    for shp in shapes:
+        for k, s in enumerate(shp):
+            want = dest.dims[k] if k < len(dest.dims) else 1
+            if s != 1 and s != want:
+                raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"destination axes {dest.dims} are not compatible with source axes {tuple(shp)}")
     expr = trace(f, [_arg_tag(a) for a in args])
     rt = dest.rt
     _prepare_remote_reads(dest.layout, rt, args)

@@ -577,6 +577,17 @@ def test_broadcast_mixed_types_and_layouts(dab, rt8):
     assert r.dtype == np.float64 and np.array_equal(dab.to_array(r), 1.5 * A.astype(np.float64))
     r = dab.broadcast(lambda x: F32(1.5) * x, a)
     assert r.dtype == np.float32 and np.array_equal(dab.to_array(r), F32(1.5) * A)
+    # in-place broadcast of SMALLER operands into dest (materialize! instantiates with axes(dest)): row, column, scalar
+    row = dab.distribute(B[:1, :])
+    col = B[:, :1].copy()
+    dab.broadcast_into(b, lambda v: v, row)
+    assert np.array_equal(dab.to_array(b), np.broadcast_to(B[:1, :], B.shape))
+    dab.broadcast_into(b, lambda u, v: u + v, row, col)
+    assert np.array_equal(dab.to_array(b), B[:1, :] + B[:, :1])
+    dab.broadcast_into(b, lambda: 7.0)
+    assert (dab.to_array(b) == 7.0).all()
+    with pytest.raises(dab.DimensionMismatch):
+        dab.broadcast_into(b, lambda v: v, dab.distribute(B[:2, :]))
 
 
 # ---------------------------------------------------------------------------------------------- full-size properties (BASELINE sizes)

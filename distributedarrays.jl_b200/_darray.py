@@ -576,11 +576,11 @@ def copyto(dest: DArray, src: np.ndarray) -> DArray:
 
 
 def similar(d: DArray, dtype=None, dims=None) -> DArray:
-    """``similar(d[, T[, dims]])`` (src/darray.jl:240-243): uninitialised, layout of ``d`` when dims are unchanged."""
+    """``similar(d[, T[, dims]])`` (src/darray.jl:240-243): ``DArray(I -> Array{T}(undef, ...), dims, procs(d))`` -- uninitialised,
+    on ``procs(d)`` with the DEFAULT distribution for those workers (a custom ``dist`` of ``d`` is not inherited, exactly as in the
+    reference)."""
     dt = np.dtype(dtype) if dtype is not None else d.dtype
-    if dims is None or tuple(dims) == d.dims:
-        return darray_like(lambda I: B200Array.empty(d.rt, shape_of(I), dt), d, dtype=dt)
-    return darray(lambda I: B200Array.empty(d.rt, shape_of(I), dt), dims, procs(d), dtype=dt, rt=d.rt)
+    return darray(lambda I: B200Array.empty(d.rt, shape_of(I), dt), d.dims if dims is None else dims, procs(d), dtype=dt, rt=d.rt)
 
 
 def fill_(d: DArray, x) -> DArray:

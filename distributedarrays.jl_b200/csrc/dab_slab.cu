@@ -35,45 +35,34 @@ __device__ __forceinline__ void store_as(char* dst, const U& v) {
 // U = load unit, S = store unit (sizeof(S) <= sizeof(U)), I = index type
 template <typename U, typename S, typename I, int UNROLL>
 __global__ void __launch_bounds__(256) copy_box_kernel(char* __restrict__ dst, const char* __restrict__ src, BoxGeom g, I total) {
-    const I stride = (I)gridDim.x * blockDim.x;
-    I idx = (I)blockIdx.x * blockDim.x + threadIdx.x;
+    // flat grid: CTA b moves the 256*UNROLL consecutive units starting at b*256*UNROLL (UNROLL independent loads per thread in
+    // flight); the block scheduler issues CTAs in address order, which keeps the owner's (possibly remote) DRAM pages a compact window
+    const I base = (I)blockIdx.x * (I)(256 * UNROLL) + threadIdx.x;
     const I upr = (I)g.upr, e1 = (I)g.e1, e2 = (I)g.e2;
     const bool flat = (g.e1 == 1 && g.e2 == 1 && g.e3 == 1);
-    for (; idx + (UNROLL - 1) * stride < total; idx += UNROLL * stride) {
-        U v[UNROLL];
-        size_t doff[UNROLL];
+    U v[UNROLL];
+    size_t doff[UNROLL];
+    bool ok[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            I id = idx + u * stride;
-            size_t soff;
-            if (flat) {
-                soff = doff[u] = (size_t)id * sizeof(U);
-            } else {
-                I row = id / upr, col = id - row * upr;
-                I j = row % e1, t = row / e1;
-                I k = t % e2, l = t / e2;
-                soff = (size_t)col * sizeof(U) + (size_t)j * g.sp1 + (size_t)k * g.sp2 + (size_t)l * g.sp3;
-                doff[u] = (size_t)col * sizeof(U) + (size_t)j * g.dp1 + (size_t)k * g.dp2 + (size_t)l * g.dp3;
-            }
-            v[u] = *reinterpret_cast<const U*>(src + soff);
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) store_as<U, S>(dst + doff[u], v[u]);
-    }
-    for (; idx < total; idx += stride) {
-        size_t soff, doff;
+    for (int u = 0; u < UNROLL; ++u) {
+        const I id = base + (I)(u * 256);
+        ok[u] = id < total;
+        if (!ok[u]) continue;
+        size_t soff;
         if (flat) {
-            soff = doff = (size_t)idx * sizeof(U);
+            soff = doff[u] = (size_t)id * sizeof(U);
         } else {
-            I row = idx / upr, col = idx - row * upr;
+            I row = id / upr, col = id - row * upr;
             I j = row % e1, t = row / e1;
             I k = t % e2, l = t / e2;
             soff = (size_t)col * sizeof(U) + (size_t)j * g.sp1 + (size_t)k * g.sp2 + (size_t)l * g.sp3;
-            doff = (size_t)col * sizeof(U) + (size_t)j * g.dp1 + (size_t)k * g.dp2 + (size_t)l * g.dp3;
+            doff[u] = (size_t)col * sizeof(U) + (size_t)j * g.dp1 + (size_t)k * g.dp2 + (size_t)l * g.dp3;
         }
-        U v = *reinterpret_cast<const U*>(src + soff);
-        store_as<U, S>(dst + doff, v);
+        v[u] = *reinterpret_cast<const U*>(src + soff);
     }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+        if (ok[u]) store_as<U, S>(dst + doff[u], v[u]);
 }
 
 int copy_unroll() {
@@ -94,8 +83,8 @@ int32_t launch_copy(dab_ctx* ctx, char* dst, const char* src, const BoxGeom& g) 
     const size_t work = (size_t)((total + 256ull * un - 1) / (256ull * un));
 #define LAUNCH(I, UN)                                                                                          \
     do {                                                                                                       \
-        int grid = dab_persistent_grid(ctx, copy_box_kernel<U, S, I, UN>, 256, work);                          \
-        copy_box_kernel<U, S, I, UN><<<grid, 256, 0, ctx->stream>>>(dst, src, g, (I)total);                    \
+        if (work > 0x7fffffffull) return dab_fail(ctx, DAB_ERR_ARG, "box too large for one launch");           \
+        copy_box_kernel<U, S, I, UN><<<(unsigned)work, 256, 0, ctx->stream>>>(dst, src, g, (I)total);          \
     } while (0)
     if (small) {
         if (un == 4) LAUNCH(unsigned int, 4);

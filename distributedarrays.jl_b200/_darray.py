@@ -294,6 +294,15 @@ class DArray:
     def __floordiv__(self, o): return self._mlp(o, lambda a, b: a // b)       # div (truncated)
     def __mod__(self, o): return self._mlp(o, lambda a, b: a % b)             # rem (Julia's %)
 
+    def __matmul__(self, x):                                                   # A*x  (reference src/linalg.jl:280-284)
+        from ._linalg import matmul
+        return matmul(self, x)
+
+    @property
+    def T(self):                                                               # transpose(A), lazy (LinearAlgebra.Transpose)
+        from ._linalg import Transpose
+        return Transpose(self)
+
 
 def _oob(k, s):
     raise IndexError(f"BoundsError: index {k} out of range for dimension of size {s}")

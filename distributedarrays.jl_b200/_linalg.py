@@ -1,0 +1,285 @@
+"""Level-2 linear algebra and transposes on DArrays (widening row f4/f3 of the scope table; all HBM-bound).
+
+Mirrors the reference's ``src/linalg.jl``:
+
+* ``transpose(D)`` / ``adjoint(D)`` lazy wrappers and ``copy`` of them (:1-17)           -> K10 ``dab_transpose_box``
+* ``mul!(y::DVector, A::DMatrix, x, a, b)`` and the Adjoint/Transpose forms (:78-167),
+  ``A*x``, ``A'*x``, ``transpose(A)*x`` (:280-284, 293-301)                               -> K9 ``dab_gemv`` + the same partial
+  exchange as mapreducedim_between (NCCL send/recv to the owner of each y chunk)
+* ``lmul!(D::Diagonal, DA)`` / ``rmul!(DA, D::Diagonal)`` (:169-187)                      -> fused broadcast with extrusion
+
+Matrix-matrix ``mul!`` (:189-277) has a different (tensor-core) roofline and is not served yet: it raises UnsupportedError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+from ._darray import B200Array, DArray, SubDArray, dab_dtype, darray
+from .layout import make_layout, rlen, shape_of
+from .runtime import Runtime
+
+_GEMV_DTYPES = (np.dtype(np.float32), np.dtype(np.float64), np.dtype(np.int32), np.dtype(np.int64))
+
+
+class Transpose:
+    """``transpose(D)``: lazy wrapper, as LinearAlgebra.Transpose{T,<:DArray{T,2}}."""
+
+    conj = False
+
+    def __init__(self, parent: DArray):
+        if parent.ndim != 2:
+            raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, "transpose/adjoint wrap a DMatrix")
+        self.parent = parent
+
+    @property
+    def dims(self):
+        return (self.parent.dims[1], self.parent.dims[0])
+
+    def copy(self) -> DArray:
+        return copy_transposed(self)
+
+    def __matmul__(self, x):
+        return matmul(self, x)
+
+
+class Adjoint(Transpose):
+    """``D'`` / ``adjoint(D)``.  Element types served here are real, so it equals the transpose (reference src/linalg.jl:1-8)."""
+
+    conj = True
+
+
+def transpose(D: DArray) -> Transpose:
+    return Transpose(D)
+
+
+def adjoint(D: DArray) -> Adjoint:
+    return Adjoint(D)
+
+
+def copy_transposed(W: Transpose) -> DArray:
+    """``copy(::Transpose{T,<:DArray{T,2}})`` / ``copy(::Adjoint…)`` (reference src/linalg.jl:1-17):
+    ``DArray(reverse(size(D)), procs(D)) do I;  transpose!(lp, convert(Array, D[reverse(I)...]))``.
+
+    Per result chunk: every intersecting source piece is pulled (peer loads when it lives on another GPU) and written transposed
+    by one kernel -- the fetched block is never materialised untransposed."""
+    D = W.parent
+    rt = D.rt
+    R = darray(lambda I: B200Array.empty(rt, shape_of(I), D.dtype), W.dims, procs=list(D.layout.pids), dtype=D.dtype, rt=rt)
+    if rt.world > 1:
+        if D._handles is None:
+            D.share()
+        rt.barrier()
+    es = D.dtype.itemsize
+    from .layout import slab_plan
+    for pid, out in R.chunks.items():
+        I = R.layout.localindices(pid)                    # ranges of the transposed array held here
+        if out.size == 0:
+            continue
+        J = (I[1], I[0])                                   # D[reverse(I)...]
+        dst_ld = rlen(I[0])
+        for piece in slab_plan(D.layout, J):
+            spid = D.layout.pids[piece.chunk]
+            sshape = shape_of(D.layout.indices[piece.chunk])
+            (sr, sc), (dr, dc) = piece.src, piece.dst       # source ranges inside the chunk, ranges inside the J-box (1-based)
+            rows, cols = rlen(sr), rlen(sc)
+            src = D.peer_ptr(spid) + ((sr[0] - 1) + (sc[0] - 1) * sshape[0]) * es
+            # J-box element (r, c) -> out[c, r]
+            dst = out.ptr + ((dc[0] - 1) + (dr[0] - 1) * dst_ld) * es
+            _lib.call("dab_transpose_box", rt.ctx, es, C.c_void_p(dst), dst_ld, C.c_void_p(src), sshape[0], rows, cols)
+    if rt.world > 1:
+        rt.sync()
+        rt.barrier()                                       # owners may not free / overwrite D before every reader is done
+    return R
+
+
+# ---- matrix-vector ------------------------------------------------------------------------------------------------------------------
+
+
+def matvec_exchange_plan(L, ylayout, trans: bool, rank_of, my_rank: int):
+    """Who ships which tile result where in ``mul!(y, A, x)``: tile (i, j) is computed by the rank holding ``procs(A)[i,j]``
+    (``procs(A)[j,i]`` for the transposed product) and consumed by the rank holding ``y.pids[i]`` (reference src/linalg.jl:90-98,
+    113-117).  Pure function of the layouts, so every rank derives the same matched send/recv lists (same (i, j) order on both
+    sides of each pair -- NCCL matches grouped point-to-point calls between two ranks in issue order)."""
+    g0, g1 = L.grid
+    gi, gj = (g1, g0) if trans else (g0, g1)
+    plan = {"owned": [], "local": [], "sends": [], "recvs": []}
+    for i in range(gi):
+        orank = rank_of(ylayout.pids[i])
+        plen = rlen(ylayout.indices[i][0])
+        if orank == my_rank:
+            plan["owned"].append(i)
+        for j in range(gj):
+            trank = rank_of(L.pids[(j + i * g0) if trans else (i + j * g0)])
+            if orank == my_rank and trank == my_rank:
+                plan["local"].append((i, j, plen))
+            elif orank == my_rank:
+                plan["recvs"].append((i, j, plen, trank))
+            elif trank == my_rank:
+                plan["sends"].append((i, j, plen, orank))
+    return plan
+
+
+def _unwrap(A) -> Tuple[DArray, bool]:
+    if isinstance(A, Transpose):
+        return A.parent, True
+    return A, False
+
+
+def _x_block(rt: Runtime, x, lo: int, hi: int, dtype: np.dtype) -> B200Array:
+    """``convert(localtype(x), x[lo:hi])`` on this rank's GPU: host vectors are sliced and uploaded, DVectors halo-fetched."""
+    n = hi - lo + 1
+    if isinstance(x, DArray):
+        if x.dtype != dtype:
+            raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"mul!: vector eltype {x.dtype} vs matrix eltype {dtype}")
+        out = B200Array.empty(rt, (n,), dtype, temp=True)
+        SubDArray(x, ((lo, hi),), (False,)).copy_to(out)
+        return out
+    h = np.ascontiguousarray(np.asarray(x)[lo - 1:hi], dtype=dtype)
+    out = B200Array.empty(rt, (n,), dtype, temp=True)
+    if n:
+        out.copy_from_host(h, sync=True)
+    return out
+
+
+def mul_(y: DArray, A: Union[DArray, Transpose], x, alpha=1, beta=0) -> DArray:
+    """``mul!(y::DVector, A::DMatrix, x::AbstractVector, α=1, β=0)`` (reference src/linalg.jl:78-118) and, for a
+    ``Transpose``/``Adjoint`` wrapper, :120-167.  Error contract as the reference: DimensionMismatch when the contracted sizes
+    differ, ArgumentError when y's cuts do not match the matrix cuts along the kept dim."""
+    M, trans = _unwrap(A)
+    if isinstance(x, (DArray, np.ndarray)) and len(np.shape(x) if not isinstance(x, DArray) else x.dims) == 2:
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "matrix-matrix mul! is not served by the B200 backend yet")
+    if M.ndim != 2 or y.ndim != 1:
+        raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, "mul!: y must be a DVector and A a DMatrix")
+    rd, cd = (1, 0) if trans else (0, 1)
+    xlen = x.dims[0] if isinstance(x, DArray) else int(np.shape(x)[0])
+    if M.dims[cd] != xlen:
+        raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"DimensionMismatch: A has {M.dims[cd]} columns, x has length {xlen}")
+    if list(y.layout.cuts[0]) != list(M.layout.cuts[rd]):
+        raise _lib.ArgumentError(_lib.ERR_ARG, "cuts of output vector must match cuts of %s dimension of matrix" % ("second" if trans else "first"))
+    dt = y.dtype
+    if dt not in _GEMV_DTYPES or M.dtype != dt:
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"mul!: eltypes y={dt} A={M.dtype} (served: equal Float32/Float64/Int32/Int64)")
+    rt = y.rt
+    L = M.layout
+    g0, g1 = L.grid
+    gi, gj = (g1, g0) if trans else (g0, g1)             # y chunks, tiles per y chunk
+    cuts_c = L.cuts[cd]
+    if isinstance(x, DArray) and rt.world > 1:
+        if x._handles is None:
+            x.share()
+        rt.barrier()
+
+    def tile_pid(i, j):                                    # procs(A)[i,j]  /  procs(A)[j,i]
+        return L.pids[(j + i * g0) if trans else (i + j * g0)]
+
+    # ---- R[i,j] = localpart(A) * xj on the tile owners (src/linalg.jl:90-98)
+    R: Dict[Tuple[int, int], B200Array] = {}
+    xblocks: Dict[int, B200Array] = {}
+    for j in range(gj):
+        for i in range(gi):
+            pid = tile_pid(i, j)
+            if pid not in M.chunks:
+                continue
+            ch = M.chunks[pid]
+            if j not in xblocks:
+                xblocks[j] = _x_block(rt, x, cuts_c[j], cuts_c[j + 1] - 1, dt)
+            nout = ch.shape[rd]
+            r = B200Array.empty(rt, (nout,), dt, temp=True)
+            _lib.call("dab_gemv", rt.ctx, dab_dtype(dt), 1 if trans else 0, C.c_void_p(ch.ptr), ch.shape[0], ch.shape[1],
+                      C.c_void_p(xblocks[j].ptr), C.c_void_p(r.ptr))
+            R[(i, j)] = r
+    # ---- ship the tile results to the owner of y's chunk i (the fetch(rij) of :113-115), all pairs in one grouped exchange
+    ypids = y.layout.pids
+    plan = matvec_exchange_plan(L, y.layout, trans, rt.rank_of, rt.rank)
+    stacks: Dict[int, B200Array] = {}
+    for i in plan["owned"]:
+        stacks[i] = B200Array.empty(rt, (rlen(y.layout.indices[i][0]) * gj,), dt, temp=True)
+    isz = dt.itemsize
+    local = plan["local"]
+    sends = [(R[(i, j)].ptr, plen * isz, peer) for i, j, plen, peer in plan["sends"]]
+    recvs = [(stacks[i].ptr + j * plen * isz, plen * isz, peer) for i, j, plen, peer in plan["recvs"]]
+    for i, j, plen in local:
+        if plen:
+            _lib.call("dab_d2d", rt.ctx, C.c_void_p(stacks[i].ptr + j * plen * dt.itemsize), C.c_void_p(R[(i, j)].ptr), plen * dt.itemsize)
+    sends = [s for s in sends if s[1]]
+    recvs = [r for r in recvs if r[1]]
+    if sends or recvs:
+        _lib.call("dab_group_start", rt.ctx)
+        for ptr, nb, peer in sends:
+            _lib.call("dab_send", rt.ctx, C.c_void_p(ptr), nb, peer)
+        for ptr, nb, peer in recvs:
+            _lib.call("dab_recv", rt.ctx, C.c_void_p(ptr), nb, peer)
+        _lib.call("dab_group_end", rt.ctx)
+    # ---- scale y (:101-111), then add!(localpart(y), R[i,j], α) for each j (:114-117; j order)
+    a_s = np.asarray(alpha, dtype=dt)
+    b_s = np.asarray(beta, dtype=dt)
+    for i, stack in stacks.items():
+        ych = y.chunks[ypids[i]]
+        plen = ych.size
+        if plen == 0:
+            continue
+        code = dab_dtype(dt)
+        if beta != 1:
+            if beta == 0:
+                z = np.zeros((), dtype=dt)
+                _lib.call("dab_fill", rt.ctx, code, C.c_void_p(ych.ptr), plen, C.c_void_p(z.ctypes.data))
+            else:
+                _lib.call("dab_binary_scalar", rt.ctx, code, _lib.MUL, C.c_void_p(ych.ptr), C.c_void_p(ych.ptr),
+                          C.c_void_p(b_s.ctypes.data), 0, plen)
+        for j in range(gj):
+            rp = stack.ptr + j * plen * dt.itemsize
+            if alpha != 1:
+                _lib.call("dab_binary_scalar", rt.ctx, code, _lib.MUL, C.c_void_p(rp), C.c_void_p(rp), C.c_void_p(a_s.ctypes.data), 1, plen)
+            _lib.call("dab_binary", rt.ctx, code, _lib.ADD, C.c_void_p(ych.ptr), C.c_void_p(ych.ptr), C.c_void_p(rp), plen)
+    for t in list(R.values()) + list(xblocks.values()) + list(stacks.values()):
+        t.free()
+    if isinstance(x, DArray) and rt.world > 1:
+        rt.sync()
+        rt.barrier()
+    return y
+
+
+def matmul(A: Union[DArray, Transpose], x) -> DArray:
+    """``A*x`` (reference src/linalg.jl:280-284): y lives on ``procs(A)[:,1]`` with one chunk per grid row; ``A'*x`` /
+    ``transpose(A)*x`` (:293-301, 303-311): on ``procs(A)[1,:]``, one chunk per grid column."""
+    M, trans = _unwrap(A)
+    xnd = len(x.dims) if isinstance(x, DArray) else np.ndim(x)
+    if xnd != 1:
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "matrix-matrix products are not served by the B200 backend yet")
+    if M.ndim != 2:
+        raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, "A must be a DMatrix")
+    xdt = x.dtype if isinstance(x, DArray) else np.asarray(x).dtype
+    T = np.result_type(M.dtype, xdt)                       # promote_op(t*s + t*s)
+    if T != M.dtype:
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"A*x: eltype {M.dtype} with a {xdt} vector needs a converted copy of A")
+    g0, g1 = M.layout.grid
+    rd = 1 if trans else 0
+    pids = [M.layout.pids[j * g0] for j in range(g1)] if trans else [M.layout.pids[i] for i in range(g0)]
+    rt = M.rt
+    y = darray(lambda I: B200Array.empty(rt, shape_of(I), T), (M.dims[rd],), procs=pids, dist=[M.layout.grid[rd]], dtype=T, rt=rt)
+    return mul_(y, A, x)
+
+
+# ---- Diagonal scaling ---------------------------------------------------------------------------------------------------------------
+
+
+def lmul_diag(d, DA: DArray) -> DArray:
+    """``lmul!(D::Diagonal, DA::DMatrix)`` with ``d = D.diag`` (reference src/linalg.jl:169-177): DA[i,j] = d[i]*DA[i,j]."""
+    from ._broadcast import broadcast_into
+    dv = np.asarray(d)
+    if DA.ndim != 2 or dv.shape != (DA.dims[0],):
+        raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"lmul!: diagonal of length {dv.shape} vs matrix {DA.dims}")
+    return broadcast_into(DA, lambda s, a: s * a, dv.astype(DA.dtype).reshape(-1, 1), DA)
+
+
+def rmul_diag(DA: DArray, d) -> DArray:
+    """``rmul!(DA::DMatrix, D::Diagonal)`` (reference src/linalg.jl:179-187): DA[i,j] = DA[i,j]*d[j]."""
+    from ._broadcast import broadcast_into
+    dv = np.asarray(d)
+    if DA.ndim != 2 or dv.shape != (DA.dims[1],):
+        raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"rmul!: diagonal of length {dv.shape} vs matrix {DA.dims}")
+    return broadcast_into(DA, lambda a, s: a * s, DA, dv.astype(DA.dtype).reshape(1, -1))

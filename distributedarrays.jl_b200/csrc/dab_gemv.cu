@@ -1,0 +1,370 @@
+// dab_gemv.cu -- K9: the per-tile matrix-vector product of mul!(y::DVector, A::DMatrix, x) (reference src/linalg.jl:78-118) and of
+// its adjoint/transpose form (:120-167):   R[i,j] = localpart(A) * xj   /   localpart(A)' * xj   on one column-major chunk.
+//
+// Roofline: HBM.  Every element of the chunk is read exactly once (elem_bytes per element); x (one column / row block of the
+// vector) is re-read out of L1/L2, the result vector is negligible.  No tensor cores: 2 flop per 4 bytes.
+//
+// Numerics.  Float32/Float64 products are accumulated in fp64 (the f32 x f32 product is exact in fp64), each output rounded once
+// at the end; Int32/Int64 wrap like Julia's machine integers (order-independent).  The reference calls BLAS gemv for floats, whose
+// summation order is unspecified, so the float contract is the north-star tolerance (1e-6 rel), not bit equality.
+// Determinism: the split of the reduction over CTAs depends only on (m, n, dtype); partials are combined in split order.
+//
+//   trans = 0 (r = A x, reduce over columns):  a thread owns VEC consecutive rows and sweeps columns; a CTA is RT row-vectors x CL
+//       column lanes (RT * CL = 256); the column range is split over gridDim.y.  Column lanes are folded through shared memory in
+//       lane order, splits by gemv_finish.
+//   trans = 1 (r = A' x, reduce down each contiguous column):  LI lanes run down a column (16-B loads), a thread carries COLS
+//       adjacent columns so x is loaded once per COLS column elements; the row range is split over gridDim.y.
+#include "dab_common.cuh"
+
+namespace {
+
+constexpr int GV_THREADS = 256;
+
+template <typename T> struct GvAcc { using type = T; };
+template <> struct GvAcc<float> { using type = double; };
+template <> struct GvAcc<int32_t> { using type = uint32_t; };   // wrap-around without signed-overflow UB
+template <> struct GvAcc<int64_t> { using type = uint64_t; };
+
+template <typename T, int VEC>
+struct alignas(sizeof(T) * VEC) GvVec { T v[VEC]; };
+
+// acc += a * b.  fp64: one DFMA (for Float32 inputs the product is exact in fp64, so fused and unfused agree bit for bit)
+__device__ __forceinline__ void gv_mac(double& acc, double a, double b) { acc = __fma_rn(a, b, acc); }
+__device__ __forceinline__ void gv_mac(uint32_t& acc, uint32_t a, uint32_t b) { acc += a * b; }
+__device__ __forceinline__ void gv_mac(uint64_t& acc, uint64_t a, uint64_t b) { acc += a * b; }
+
+template <typename T, int VEC>
+__device__ __forceinline__ GvVec<T, VEC> gv_load_stream(const T* p) {
+    GvVec<T, VEC> r;
+    if constexpr (sizeof(T) * VEC == 16) {
+        int4 t = __ldcs(reinterpret_cast<const int4*>(p));
+        memcpy(&r, &t, 16);
+    } else {
+        static_assert(VEC == 1, "vector width");
+        r.v[0] = __ldcs(p);
+    }
+    return r;
+}
+template <typename T, int VEC>
+__device__ __forceinline__ GvVec<T, VEC> gv_load_cached(const T* p) {
+    GvVec<T, VEC> r;
+    if constexpr (sizeof(T) * VEC == 16) {
+        int4 t = __ldg(reinterpret_cast<const int4*>(p));
+        memcpy(&r, &t, 16);
+    } else {
+        r.v[0] = __ldg(p);
+    }
+    return r;
+}
+
+// ---- r = A x ----------------------------------------------------------------------------------------------------------------
+// grid (row tiles, column splits); lrt = log2(RT)
+template <typename T, int VEC, int U>
+__global__ void __launch_bounds__(GV_THREADS) gemv_n_kernel(const T* __restrict__ A, size_t m, size_t n, const T* __restrict__ x, int lrt,
+                                                            size_t cols_per_split, typename GvAcc<T>::type* __restrict__ part,
+                                                            T* __restrict__ y) {
+    using Acc = typename GvAcc<T>::type;
+    __shared__ Acc sh[GV_THREADS * VEC];
+    const int RT = 1 << lrt, CL = GV_THREADS >> lrt;
+    const int ri = threadIdx.x & (RT - 1), cl = threadIdx.x >> lrt;
+    const size_t row0 = ((size_t)blockIdx.x * RT + ri) * VEC;
+    const size_t jlo = (size_t)blockIdx.y * cols_per_split;
+    const size_t jhi = (jlo + cols_per_split < n) ? jlo + cols_per_split : n;
+    Acc acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = Acc(0);
+    if (row0 < m) {
+        const T* col = A + row0;
+        size_t j = jlo + cl;
+        const size_t step = (size_t)CL;
+        for (; j + (U - 1) * step < jhi; j += U * step) {
+            GvVec<T, VEC> a[U];
+            T xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                a[u] = gv_load_stream<T, VEC>(col + (j + u * step) * m);
+                xv[u] = __ldg(x + j + u * step);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) gv_mac(acc[v], (Acc)a[u].v[v], (Acc)xv[u]);
+        }
+        for (; j < jhi; j += step) {
+            GvVec<T, VEC> a = gv_load_stream<T, VEC>(col + j * m);
+            const Acc xj = (Acc)__ldg(x + j);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) gv_mac(acc[v], (Acc)a.v[v], xj);
+        }
+    }
+    if (CL > 1) {  // fold the column lanes in lane order
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) sh[threadIdx.x * VEC + v] = acc[v];
+        __syncthreads();
+        if (cl == 0)
+            for (int c = 1; c < CL; ++c)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[v] += sh[((c << lrt) + ri) * VEC + v];
+    }
+    if (cl == 0 && row0 < m) {
+        if (part) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) part[(size_t)blockIdx.y * m + row0 + v] = acc[v];
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) y[row0 + v] = (T)acc[v];
+        }
+    }
+}
+
+// ---- r = A' x ---------------------------------------------------------------------------------------------------------------
+// grid (column tiles, row splits); lli = log2(LI); a CTA covers (256 / LI) * COLS columns
+template <typename T, int VEC, int COLS>
+__global__ void __launch_bounds__(GV_THREADS) gemv_t_kernel(const T* __restrict__ A, size_t m, size_t n, const T* __restrict__ x, int lli,
+                                                            size_t rows_per_split, typename GvAcc<T>::type* __restrict__ part,
+                                                            T* __restrict__ y) {
+    using Acc = typename GvAcc<T>::type;
+    __shared__ Acc sh[GV_THREADS * COLS];
+    const int LI = 1 << lli, CB = GV_THREADS >> lli;
+    const int li = threadIdx.x & (LI - 1), cb = threadIdx.x >> lli;
+    const size_t col0 = ((size_t)blockIdx.x * CB + cb) * COLS;
+    const size_t ilo = (size_t)blockIdx.y * rows_per_split;
+    const size_t ihi = (ilo + rows_per_split < m) ? ilo + rows_per_split : m;
+    Acc acc[COLS];
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) acc[c] = Acc(0);
+    if (col0 < n) {
+        const int nc = (n - col0 < (size_t)COLS) ? (int)(n - col0) : COLS;
+        const size_t step = (size_t)LI * VEC;
+        if (nc == COLS) {
+            for (size_t i = ilo + (size_t)li * VEC; i < ihi; i += step) {
+                GvVec<T, VEC> a[COLS];
+#pragma unroll
+                for (int c = 0; c < COLS; ++c) a[c] = gv_load_stream<T, VEC>(A + (col0 + c) * m + i);
+                const GvVec<T, VEC> xv = gv_load_cached<T, VEC>(x + i);
+#pragma unroll
+                for (int c = 0; c < COLS; ++c)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) gv_mac(acc[c], (Acc)a[c].v[v], (Acc)xv.v[v]);
+            }
+        } else {
+            for (size_t i = ilo + (size_t)li * VEC; i < ihi; i += step) {
+                const GvVec<T, VEC> xv = gv_load_cached<T, VEC>(x + i);
+                for (int c = 0; c < nc; ++c) {
+                    GvVec<T, VEC> a = gv_load_stream<T, VEC>(A + (col0 + c) * m + i);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) gv_mac(acc[c], (Acc)a.v[v], (Acc)xv.v[v]);
+                }
+            }
+        }
+    }
+    // fold the LI lanes of each column group: fixed binary tree through shared memory (lanes of one group are contiguous threads)
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) sh[threadIdx.x * COLS + c] = acc[c];
+    __syncthreads();
+    for (int s = LI >> 1; s > 0; s >>= 1) {
+        if (li < s)
+#pragma unroll
+            for (int c = 0; c < COLS; ++c) sh[threadIdx.x * COLS + c] += sh[(threadIdx.x + s) * COLS + c];
+        __syncthreads();
+    }
+    if (li == 0 && col0 < n) {
+        for (int c = 0; c < COLS && col0 + c < n; ++c) {
+            const Acc r = sh[threadIdx.x * COLS + c];
+            if (part) part[(size_t)blockIdx.y * n + col0 + c] = r;
+            else y[col0 + c] = (T)r;
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GV_THREADS) gemv_finish_kernel(const typename GvAcc<T>::type* __restrict__ part, size_t nout, int nsplit,
+                                                                 T* __restrict__ y) {
+    using Acc = typename GvAcc<T>::type;
+    const size_t k = (size_t)blockIdx.x * GV_THREADS + threadIdx.x;
+    if (k >= nout) return;
+    Acc acc = part[k];
+    for (int s = 1; s < nsplit; ++s) acc += part[(size_t)s * nout + k];
+    y[k] = (T)acc;
+}
+
+int32_t gv_scratch(dab_ctx* ctx, size_t bytes) {
+    if (ctx->dim_scratch_bytes >= bytes) return DAB_OK;
+    if (ctx->dim_scratch) {
+        DAB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        DAB_CUDA(ctx, cudaFree(ctx->dim_scratch));
+        ctx->dim_scratch = nullptr;
+        ctx->dim_scratch_bytes = 0;
+    }
+    DAB_CUDA(ctx, cudaMalloc(&ctx->dim_scratch, bytes));
+    ctx->dim_scratch_bytes = bytes;
+    return DAB_OK;
+}
+
+int ceil_log2(size_t v) {
+    int l = 0;
+    while (((size_t)1 << l) < v) ++l;
+    return l;
+}
+
+template <typename T, int VEC>
+int32_t launch_n(dab_ctx* ctx, const T* A, size_t m, size_t n, const T* x, T* y) {
+    using Acc = typename GvAcc<T>::type;
+    constexpr int U = 4;
+    const size_t rvecs = (m + VEC - 1) / VEC;
+    int lrt = ceil_log2(rvecs);
+    if (lrt > 8) lrt = 8;
+    const int RT = 1 << lrt, CL = GV_THREADS >> lrt;
+    const size_t gx = (rvecs + RT - 1) / RT;
+    // enough CTAs for ~8 per SM, but every CTA keeps >= 16 column steps per lane
+    const size_t want = ((size_t)ctx->sm_count * 8 + gx - 1) / gx;
+    size_t max_split = n / ((size_t)CL * U * 4);
+    if (max_split < 1) max_split = 1;
+    size_t nsplit = want < max_split ? want : max_split;
+    if (nsplit > 65535) nsplit = 65535;
+    size_t cps = (n + nsplit - 1) / nsplit;
+    nsplit = (n + cps - 1) / cps;
+    Acc* part = nullptr;
+    if (nsplit > 1) {
+        int32_t st = gv_scratch(ctx, nsplit * m * sizeof(Acc));
+        if (st != DAB_OK) return st;
+        part = (Acc*)ctx->dim_scratch;
+    }
+    DAB_REQUIRE(ctx, gx <= 0x7fffffffull, DAB_ERR_ARG, "dab_gemv: too many row tiles");
+    dim3 grid((unsigned)gx, (unsigned)nsplit);
+    gemv_n_kernel<T, VEC, U><<<grid, GV_THREADS, 0, ctx->stream>>>(A, m, n, x, lrt, cps, part, y);
+    DAB_LAUNCHED(ctx);
+    if (part) {
+        gemv_finish_kernel<T><<<(unsigned)((m + GV_THREADS - 1) / GV_THREADS), GV_THREADS, 0, ctx->stream>>>(part, m, (int)nsplit, y);
+        DAB_LAUNCHED(ctx);
+    }
+    return DAB_OK;
+}
+
+template <typename T, int VEC>
+int32_t launch_t(dab_ctx* ctx, const T* A, size_t m, size_t n, const T* x, T* y) {
+    using Acc = typename GvAcc<T>::type;
+    constexpr int COLS = 4;
+    const size_t rvecs = (m + VEC - 1) / VEC;
+    int lli = ceil_log2(rvecs);
+    if (lli > 8) lli = 8;
+    const int LI = 1 << lli, CB = GV_THREADS >> lli;
+    const size_t cols_per_cta = (size_t)CB * COLS;
+    const size_t gx = (n + cols_per_cta - 1) / cols_per_cta;
+    const size_t want = ((size_t)ctx->sm_count * 8 + gx - 1) / gx;
+    const size_t unit = (size_t)LI * VEC;  // rows one sweep step covers; splits start on a multiple of it (keeps 16-B alignment)
+    size_t max_split = m / (unit * 16);
+    if (max_split < 1) max_split = 1;
+    size_t nsplit = want < max_split ? want : max_split;
+    if (nsplit > 65535) nsplit = 65535;
+    size_t rps = (m + nsplit - 1) / nsplit;
+    rps = (rps + unit - 1) / unit * unit;
+    nsplit = (m + rps - 1) / rps;
+    Acc* part = nullptr;
+    if (nsplit > 1) {
+        int32_t st = gv_scratch(ctx, nsplit * n * sizeof(Acc));
+        if (st != DAB_OK) return st;
+        part = (Acc*)ctx->dim_scratch;
+    }
+    DAB_REQUIRE(ctx, gx <= 0x7fffffffull, DAB_ERR_ARG, "dab_gemv: too many column tiles");
+    dim3 grid((unsigned)gx, (unsigned)nsplit);
+    gemv_t_kernel<T, VEC, COLS><<<grid, GV_THREADS, 0, ctx->stream>>>(A, m, n, x, lli, rps, part, y);
+    DAB_LAUNCHED(ctx);
+    if (part) {
+        gemv_finish_kernel<T><<<(unsigned)((n + GV_THREADS - 1) / GV_THREADS), GV_THREADS, 0, ctx->stream>>>(part, n, (int)nsplit, y);
+        DAB_LAUNCHED(ctx);
+    }
+    return DAB_OK;
+}
+
+template <typename T>
+__global__ void gv_zero_kernel(T* y, size_t n) {
+    const size_t k = (size_t)blockIdx.x * GV_THREADS + threadIdx.x;
+    if (k < n) y[k] = T(0);
+}
+
+template <typename T>
+int32_t gemv_t(dab_ctx* ctx, int32_t trans, const T* A, size_t m, size_t n, const T* x, T* y) {
+    constexpr int VEC = 16 / sizeof(T);
+    const size_t nout = trans ? n : m, nred = trans ? m : n;
+    if (nout == 0) return DAB_OK;
+    if (nred == 0) {  // empty sum: zeros(T, nout), as Base's generic and BLAS matvec both give
+        gv_zero_kernel<T><<<(unsigned)((nout + GV_THREADS - 1) / GV_THREADS), GV_THREADS, 0, ctx->stream>>>(y, nout);
+        DAB_LAUNCHED(ctx);
+        return DAB_OK;
+    }
+    // 16-byte loads need every column start 16-byte aligned: base aligned and m a multiple of VEC (x too for the A' x sweep)
+    const bool vec = ((uintptr_t)A % 16 == 0) && (m % VEC == 0) && (!trans || (uintptr_t)x % 16 == 0);
+    if (!trans) return vec ? launch_n<T, VEC>(ctx, A, m, n, x, y) : launch_n<T, 1>(ctx, A, m, n, x, y);
+    return vec ? launch_t<T, VEC>(ctx, A, m, n, x, y) : launch_t<T, 1>(ctx, A, m, n, x, y);
+}
+
+}  // namespace
+
+extern "C" int32_t dab_gemv(dab_ctx* ctx, int32_t dtype, int32_t trans, const void* A, size_t m, size_t n, const void* x, void* r) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, trans == 0 || trans == 1, DAB_ERR_ARG, "dab_gemv: trans %d", trans);
+    DAB_REQUIRE(ctx, (A || m * n == 0) && (x || (trans ? m : n) == 0) && (r || (trans ? n : m) == 0), DAB_ERR_ARG, "dab_gemv: null pointer");
+    switch (dtype) {
+        case DAB_F32: return gemv_t<float>(ctx, trans, (const float*)A, m, n, (const float*)x, (float*)r);
+        case DAB_F64: return gemv_t<double>(ctx, trans, (const double*)A, m, n, (const double*)x, (double*)r);
+        case DAB_I32: return gemv_t<int32_t>(ctx, trans, (const int32_t*)A, m, n, (const int32_t*)x, (int32_t*)r);
+        case DAB_I64: return gemv_t<int64_t>(ctx, trans, (const int64_t*)A, m, n, (const int64_t*)x, (int64_t*)r);
+        default: return dab_fail(ctx, DAB_ERR_UNSUPPORTED, "dab_gemv: dtype %d", dtype);
+    }
+}
+
+// ---- transpose of one box (K10) -----------------------------------------------------------------------------------------------
+namespace {
+
+// TR_TILE x TR_TILE element tile (64 for units up to 4 bytes, 32 above: static shared memory budget); 256 threads = TR_TILE x TY
+template <typename U, int TR_TILE>
+__global__ void __launch_bounds__(256) transpose_box_kernel(U* __restrict__ dst, size_t dst_ld, const U* __restrict__ src, size_t src_ld,
+                                                            size_t rows, size_t cols, unsigned tiles_r) {
+    // +1 padding: the transposed read walks a tile column, i.e. stride TR_TILE+1 words -> conflict-free for 4-byte units
+    __shared__ U tile[TR_TILE][TR_TILE + 1];
+    const size_t tr = blockIdx.x % tiles_r, tc = blockIdx.x / tiles_r;  // consecutive CTAs walk down the source rows (address order)
+    const size_t r0 = tr * TR_TILE, c0 = tc * TR_TILE;
+    constexpr int TY = 256 / TR_TILE;
+    const int tx = threadIdx.x & (TR_TILE - 1), ty = threadIdx.x / TR_TILE;
+#pragma unroll 4
+    for (int k = ty; k < TR_TILE; k += TY) {
+        const size_t r = r0 + tx, c = c0 + k;
+        if (r < rows && c < cols) tile[k][tx] = src[r + c * src_ld];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = ty; k < TR_TILE; k += TY) {
+        const size_t c = c0 + tx, r = r0 + k;  // dst is (cols x rows): element (c, r)
+        if (r < rows && c < cols) dst[c + r * dst_ld] = tile[tx][k];
+    }
+}
+
+template <typename U>
+int32_t launch_transpose(dab_ctx* ctx, void* dst, size_t dst_ld, const void* src, size_t src_ld, size_t rows, size_t cols) {
+    constexpr int TR_TILE = sizeof(U) <= 4 ? 64 : 32;
+    const size_t tiles_r = (rows + TR_TILE - 1) / TR_TILE, tiles_c = (cols + TR_TILE - 1) / TR_TILE;
+    DAB_REQUIRE(ctx, tiles_r * tiles_c <= 0x7fffffffull && tiles_r <= 0xffffffffull, DAB_ERR_ARG, "dab_transpose_box: too many tiles");
+    transpose_box_kernel<U, TR_TILE><<<(unsigned)(tiles_r * tiles_c), 256, 0, ctx->stream>>>((U*)dst, dst_ld, (const U*)src, src_ld, rows, cols,
+                                                                                   (unsigned)tiles_r);
+    DAB_LAUNCHED(ctx);
+    return DAB_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t dab_transpose_box(dab_ctx* ctx, int32_t elem_bytes, void* dst, size_t dst_ld, const void* src, size_t src_ld, size_t rows,
+                                     size_t cols) {
+    DAB_ENTER(ctx);
+    if (rows == 0 || cols == 0) return DAB_OK;
+    DAB_REQUIRE(ctx, dst && src, DAB_ERR_ARG, "dab_transpose_box: null pointer");
+    DAB_REQUIRE(ctx, src_ld >= rows && dst_ld >= cols, DAB_ERR_DIM_MISMATCH, "dab_transpose_box: leading dimension smaller than the box");
+    switch (elem_bytes) {
+        case 1: return launch_transpose<uint8_t>(ctx, dst, dst_ld, src, src_ld, rows, cols);
+        case 2: return launch_transpose<uint16_t>(ctx, dst, dst_ld, src, src_ld, rows, cols);
+        case 4: return launch_transpose<uint32_t>(ctx, dst, dst_ld, src, src_ld, rows, cols);
+        case 8: return launch_transpose<uint64_t>(ctx, dst, dst_ld, src, src_ld, rows, cols);
+        case 16: return launch_transpose<int4>(ctx, dst, dst_ld, src, src_ld, rows, cols);
+        default: return dab_fail(ctx, DAB_ERR_ARG, "dab_transpose_box: elem_bytes %d", elem_bytes);
+    }
+}

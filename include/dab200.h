@@ -233,6 +233,21 @@ int32_t dab_reducedim(dab_ctx* ctx, int32_t dtype, int32_t op, int32_t map, cons
 int32_t dab_copy_box(dab_ctx* ctx, int32_t elem_bytes, void* dst, const size_t dst_shape[4], const size_t dst_off[4],
                      const void* src, const size_t src_shape[4], const size_t src_off[4], const size_t extent[4]);
 
+/* ==== Level-2 linear algebra K9 (widening row f4; HBM-bound) ==============================
+ * r = op(A) * x on ONE column-major chunk A (m x n, leading dimension m): trans = 0 -> r[m] = A x[n];
+ * trans = 1 -> r[n] = A' x[m].  Replaces  localpart(A)*convert(localtype(x), xj)  (src/linalg.jl:95-97)
+ * and  localpart(A)'*...  (:141) inside mul!(y::DVector, A::DMatrix, x, a, b); the tile results are then
+ * combined into y by the caller exactly as the reference does (scale y by b, add a*R[i,j] in j order,
+ * :101-117).  Float products accumulate in fp64 and round once; Int32/Int64 wrap.  dtypes: F32 F64 I32 I64. */
+int32_t dab_gemv(dab_ctx* ctx, int32_t dtype, int32_t trans, const void* A, size_t m, size_t n, const void* x, void* r);
+
+/* dst[j + i*dst_ld] = src[i + j*src_ld] for i < rows, j < cols (both column-major): the per-piece body of
+ * copy(::Transpose/Adjoint{T,<:DArray{T,2}}) (src/linalg.jl:1-17: transpose!(lp, Array(D[reverse(I)...]))).
+ * src may be a PEER pointer: rows are pulled coalesced over NVLink and written coalesced locally through a
+ * shared-memory tile, so the fetched block is never materialised untransposed.  elem_bytes in {1,2,4,8,16}. */
+int32_t dab_transpose_box(dab_ctx* ctx, int32_t elem_bytes, void* dst, size_t dst_ld, const void* src, size_t src_ld, size_t rows,
+                          size_t cols);
+
 /* ==== cross-worker combine: NCCL over NVLink (replaces Distributed.remotecall_fetch on
  *      this path only; src/mapreduce.jl:30-34, 72-80; src/darray.jl:809-815) ============== */
 /* 128-byte ncclUniqueId; rank 0 creates it, the host runtime ships it to the other workers. */

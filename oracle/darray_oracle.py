@@ -702,3 +702,89 @@ def rand_u01_ksum(seed: int, start: int, n: int, block: int = 1 << 24) -> int:
         idx = np.arange(s, s + m, dtype=np.uint64)
         tot += int((hash_u32(seed, idx) >> np.uint32(8)).astype(np.uint64).sum())
     return tot
+
+
+# --------------------------------------------------------------------------
+# Level-2 linear algebra and transposes  (src/linalg.jl:1-17, 78-187, 278-311)
+# --------------------------------------------------------------------------
+
+
+def _tile_matvec(A: np.ndarray, x: np.ndarray, trans: bool) -> np.ndarray:
+    """``localpart(A)*xj`` / ``localpart(A)'*xj`` (src/linalg.jl:95-97, 141).  Julia dispatches Float32/Float64 to BLAS gemv
+    (summation order unspecified -> parity unpinned, tolerance contract) and integers to the generic wrap-around loop.  The
+    restatement: floats summed in fp64 and rounded once; integers exactly, modulo 2^bits."""
+    M = A.T if trans else A
+    if A.dtype.kind == "f":
+        return (M.astype(np.float64) @ x.astype(np.float64)).astype(A.dtype)
+    with np.errstate(over="ignore"):
+        return (M * x[None, :].astype(A.dtype)).sum(axis=1, dtype=A.dtype)
+
+
+def _add_scaled(dest: np.ndarray, src: np.ndarray, scale) -> np.ndarray:
+    """``add!(dest, src, scale)`` src/linalg.jl:62-76: ``dest[i] += src[i]`` when scale == 1, else ``dest[i] += scale*src[i]``
+    (two roundings, no FMA)."""
+    dt = dest.dtype
+    if scale == 1:
+        return (dest + src).astype(dt)
+    return (dest + (dt.type(scale) * src).astype(dt)).astype(dt)
+
+
+def darray_mul_vec(y: ODArray, A: ODArray, x: np.ndarray, alpha=1, beta=0, trans: bool = False) -> ODArray:
+    """``mul!(y::DVector, A::DMatrix, x, α, β)`` src/linalg.jl:78-118 and the adjoint/transpose form :120-167.
+
+    Tile products R[i,j]; y scaled by β (``fill!(0)`` when β == 0, untouched when β == 1); then ``add!(localpart(y), R[i,j], α)``
+    for j = 1..  The reference issues those adds as @async tasks, so their order is not fixed; j order is used here."""
+    rd, cd = (1, 0) if trans else (0, 1)          # A's dim that indexes y / that is contracted with x
+    if A.dims[cd] != len(x):
+        raise ValueError("DimensionMismatch")
+    if list(y.cuts[0]) != list(A.cuts[rd]):
+        raise ValueError("ArgumentError: cuts of output vector must match cuts of matrix")
+    gi, gj = A.grid[rd], A.grid[cd]
+    dt = y.chunks[0].dtype if y.chunks else A.chunks[0].dtype
+    out = []
+    for i in range(gi):
+        yi = y.chunks[i].copy()
+        if beta != 1:
+            yi = (yi * dt.type(beta)).astype(dt) if beta != 0 else np.zeros_like(yi)
+        for j in range(gj):
+            lin = (j + i * A.grid[0]) if trans else (i + j * A.grid[0])   # procs(A)[j,i] / procs(A)[i,j]
+            lo, hi = A.cuts[cd][j], A.cuts[cd][j + 1] - 1
+            r = _tile_matvec(A.chunks[lin], np.asarray(x[lo - 1:hi]), trans)
+            yi = _add_scaled(yi, r.astype(dt), alpha)
+        out.append(yi)
+    return ODArray(y.dims, y.grid, y.pids, y.indices, y.cuts, out)
+
+
+def darray_matvec(A: ODArray, x: np.ndarray, trans: bool = False) -> ODArray:
+    """``A*x`` src/linalg.jl:280-284 / ``A'*x`` :293-301: y over procs(A)[:,1] (resp. procs(A)[1,:]), one chunk per grid row
+    (resp. column), then ``mul!(y, A, x)``."""
+    rd = 1 if trans else 0
+    g0 = A.grid[0]
+    pids = [A.pids[j * g0] for j in range(A.grid[1])] if trans else [A.pids[i] for i in range(g0)]
+    dt = np.result_type(A.chunks[0].dtype, np.asarray(x).dtype)
+    y = make_layout((A.dims[rd],), pids, [A.grid[rd]])
+    y.chunks = [np.zeros(rlen(ix[0]), dtype=dt) for ix in y.indices]   # uninitialised in the reference; β = 0 overwrites
+    return darray_mul_vec(y, A, np.asarray(x), 1, 0, trans)
+
+
+def darray_transpose(D: ODArray) -> ODArray:
+    """``copy(::Transpose{T,<:DArray{T,2}})`` / Adjoint for real T, src/linalg.jl:1-17:
+    ``DArray(reverse(size(D)), procs(D)) do I; transpose!(lp, Array(D[reverse(I)...]))``."""
+    full = to_array(D)
+    R = make_layout((D.dims[1], D.dims[0]), D.pids)
+    R.chunks = [np.asfortranarray(full[I[1][0] - 1:I[1][1], I[0][0] - 1:I[0][1]].T) for I in R.indices]
+    return R
+
+
+def darray_scale_diag(DA: ODArray, d: np.ndarray, side: str) -> ODArray:
+    """``lmul!(D::Diagonal, DA)`` (side 'l': rows scaled, ``d[i]*A[i,j]``) and ``rmul!(DA, D::Diagonal)`` (side 'r':
+    ``A[i,j]*d[j]``), src/linalg.jl:169-187."""
+    out = []
+    for ch, I in zip(DA.chunks, DA.indices):
+        if side == "l":
+            s = np.asarray(d[I[0][0] - 1:I[0][1]]).astype(ch.dtype)[:, None]
+            out.append(np.asfortranarray((s * ch).astype(ch.dtype)))
+        else:
+            s = np.asarray(d[I[1][0] - 1:I[1][1]]).astype(ch.dtype)[None, :]
+            out.append(np.asfortranarray((ch * s).astype(ch.dtype)))
+    return ODArray(DA.dims, DA.grid, DA.pids, DA.indices, DA.cuts, out)

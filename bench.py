@@ -295,6 +295,18 @@ def main():
                                            "peak_GBs": 770.0, "what": "every rank pulls a 256 MiB slab of its right neighbour's chunk over NVLink (CUDA-IPC peer loads)"}
                 extras["halo_getindex"]["frac_of_peak"] = extras["halo_getindex"]["GBs_per_reader"] / 770.0
                 dst.free()
+            # Level-2 widening (K9): y = A*x and y = A'*x on the same matrix, through the public API (tile products, exchange of the
+            # tile results to y's owners, ordered accumulate); x is a DVector so no host copy sits inside the timed region
+            xv = dab.dfill(1.0, (dimsA[1],), dtype=np.float32)
+            xt = dab.dfill(1.0, (dimsA[0],), dtype=np.float32)
+            for key, W, v in (("matvec_A_x", A, xv), ("matvec_At_x", A.T, xt)):
+                ms_m, _ = timed(lambda: (W @ v).close(), reps)
+                ms_m = max_over_ranks(ms_m)
+                extras[key] = {"GBs": 4.0 * dimsA[0] * dimsA[1] * reps / (ms_m * 1e-3) / 1e9, "ms": ms_m / reps, "bytes_per_elem": 4,
+                               "what": "mul!(y, A, x) on the sum_dims1 matrix: dab_gemv per chunk (fp64 carriers) + NCCL send/recv of the tile "
+                                       "results to the owners of y + ordered add!"}
+            xv.close()
+            xt.close()
             A.close()
         except Exception as ex:
             extras["error"] = repr(ex)[:300]

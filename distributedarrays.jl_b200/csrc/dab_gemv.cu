@@ -118,61 +118,84 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_n_kernel(const T* __restrict_
 }
 
 // ---- r = A' x ---------------------------------------------------------------------------------------------------------------
-// grid (column tiles, row splits); lli = log2(LI); a CTA covers (256 / LI) * COLS columns
+// grid (column tiles, row splits); lli = log2(LI); a CTA covers G consecutive groups of (256 / LI) * COLS columns
 template <typename T, int VEC, int COLS>
 __global__ void __launch_bounds__(GV_THREADS) gemv_t_kernel(const T* __restrict__ A, size_t m, size_t n, const T* __restrict__ x, int lli,
-                                                            size_t rows_per_split, typename GvAcc<T>::type* __restrict__ part,
+                                                            int G, size_t rows_per_split, typename GvAcc<T>::type* __restrict__ part,
                                                             T* __restrict__ y) {
     using Acc = typename GvAcc<T>::type;
-    __shared__ Acc sh[GV_THREADS * COLS];
+    __shared__ Acc sh[(GV_THREADS / 32) * COLS];
     const int LI = 1 << lli, CB = GV_THREADS >> lli;
     const int li = threadIdx.x & (LI - 1), cb = threadIdx.x >> lli;
-    const size_t col0 = ((size_t)blockIdx.x * CB + cb) * COLS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ilo = (size_t)blockIdx.y * rows_per_split;
     const size_t ihi = (ilo + rows_per_split < m) ? ilo + rows_per_split : m;
-    Acc acc[COLS];
+    const size_t step = (size_t)LI * VEC;
+    for (int g = 0; g < G; ++g) {
+        const size_t col0 = (((size_t)blockIdx.x * G + g) * CB + cb) * COLS;
+        Acc acc[COLS];
 #pragma unroll
-    for (int c = 0; c < COLS; ++c) acc[c] = Acc(0);
-    if (col0 < n) {
-        const int nc = (n - col0 < (size_t)COLS) ? (int)(n - col0) : COLS;
-        const size_t step = (size_t)LI * VEC;
-        if (nc == COLS) {
-            for (size_t i = ilo + (size_t)li * VEC; i < ihi; i += step) {
-                GvVec<T, VEC> a[COLS];
+        for (int c = 0; c < COLS; ++c) acc[c] = Acc(0);
+        if (col0 < n) {
+            const int nc = (n - col0 < (size_t)COLS) ? (int)(n - col0) : COLS;
+            // UI sweep steps per batch: the unit-wise (unaligned) variant needs the extra loads in flight
+            constexpr int UI = (VEC == 1) ? 4 : 1;
+            size_t i = ilo + (size_t)li * VEC;
+            if (nc == COLS) {
+                const T* p0 = A + col0 * m;
+                for (; i + (UI - 1) * step < ihi; i += UI * step) {
+                    GvVec<T, VEC> a[UI][COLS], xv[UI];
 #pragma unroll
-                for (int c = 0; c < COLS; ++c) a[c] = gv_load_stream<T, VEC>(A + (col0 + c) * m + i);
+                    for (int u = 0; u < UI; ++u) {
+#pragma unroll
+                        for (int c = 0; c < COLS; ++c) a[u][c] = gv_load_stream<T, VEC>(p0 + c * m + i + u * step);
+                        xv[u] = gv_load_cached<T, VEC>(x + i + u * step);
+                    }
+#pragma unroll
+                    for (int u = 0; u < UI; ++u)
+#pragma unroll
+                        for (int c = 0; c < COLS; ++c)
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) gv_mac(acc[c], (Acc)a[u][c].v[v], (Acc)xv[u].v[v]);
+                }
+            }
+            for (; i < ihi; i += step) {  // sweep tail, and the last (partial) column group
                 const GvVec<T, VEC> xv = gv_load_cached<T, VEC>(x + i);
 #pragma unroll
                 for (int c = 0; c < COLS; ++c)
+                    if (c < nc) {
+                        GvVec<T, VEC> a = gv_load_stream<T, VEC>(A + (col0 + c) * m + i);
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) gv_mac(acc[c], (Acc)a[c].v[v], (Acc)xv.v[v]);
-            }
-        } else {
-            for (size_t i = ilo + (size_t)li * VEC; i < ihi; i += step) {
-                const GvVec<T, VEC> xv = gv_load_cached<T, VEC>(x + i);
-                for (int c = 0; c < nc; ++c) {
-                    GvVec<T, VEC> a = gv_load_stream<T, VEC>(A + (col0 + c) * m + i);
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) gv_mac(acc[c], (Acc)a.v[v], (Acc)xv.v[v]);
-                }
+                        for (int v = 0; v < VEC; ++v) gv_mac(acc[c], (Acc)a.v[v], (Acc)xv.v[v]);
+                    }
             }
         }
-    }
-    // fold the LI lanes of each column group: fixed binary tree through shared memory (lanes of one group are contiguous threads)
+        // fold the LI lanes of each column group: fixed shuffle tree inside a warp (a group never straddles warps unless it is a
+        // whole number of them), then the group's warps in warp order through shared memory
+        const int W = LI < 32 ? LI : 32;
+        for (int s = W >> 1; s > 0; s >>= 1)
 #pragma unroll
-    for (int c = 0; c < COLS; ++c) sh[threadIdx.x * COLS + c] = acc[c];
-    __syncthreads();
-    for (int s = LI >> 1; s > 0; s >>= 1) {
-        if (li < s)
+            for (int c = 0; c < COLS; ++c) acc[c] += __shfl_down_sync(0xffffffffu, acc[c], s, W);
+        if (LI > 32) {
+            if (lane == 0)
 #pragma unroll
-            for (int c = 0; c < COLS; ++c) sh[threadIdx.x * COLS + c] += sh[(threadIdx.x + s) * COLS + c];
-        __syncthreads();
-    }
-    if (li == 0 && col0 < n) {
-        for (int c = 0; c < COLS && col0 + c < n; ++c) {
-            const Acc r = sh[threadIdx.x * COLS + c];
-            if (part) part[(size_t)blockIdx.y * n + col0 + c] = r;
-            else y[col0 + c] = (T)r;
+                for (int c = 0; c < COLS; ++c) sh[warp * COLS + c] = acc[c];
+            __syncthreads();
+            if (li == 0) {
+                const int nw = LI >> 5;
+                for (int w = 1; w < nw; ++w)
+#pragma unroll
+                    for (int c = 0; c < COLS; ++c) acc[c] += sh[(warp + w) * COLS + c];
+            }
+            __syncthreads();
+        }
+        if (li == 0 && col0 < n) {
+#pragma unroll
+            for (int c = 0; c < COLS; ++c)
+                if (col0 + c < n) {
+                    if (part) part[(size_t)blockIdx.y * n + col0 + c] = acc[c];
+                    else y[col0 + c] = (T)acc[c];
+                }
         }
     }
 }
@@ -216,8 +239,9 @@ int32_t launch_n(dab_ctx* ctx, const T* A, size_t m, size_t n, const T* x, T* y)
     if (lrt > 8) lrt = 8;
     const int RT = 1 << lrt, CL = GV_THREADS >> lrt;
     const size_t gx = (rvecs + RT - 1) / RT;
-    // enough CTAs for ~8 per SM, but every CTA keeps >= 16 column steps per lane
-    const size_t want = ((size_t)ctx->sm_count * 8 + gx - 1) / gx;
+    // one full wave of resident CTAs (no partial second wave), but every CTA keeps >= 16 column steps per lane
+    const size_t slots = (size_t)ctx->sm_count * (size_t)dab_resident_ctas((const void*)gemv_n_kernel<T, VEC, U>, GV_THREADS);
+    const size_t want = slots / gx > 0 ? slots / gx : 1;
     size_t max_split = n / ((size_t)CL * U * 4);
     if (max_split < 1) max_split = 1;
     size_t nsplit = want < max_split ? want : max_split;
@@ -249,9 +273,16 @@ int32_t launch_t(dab_ctx* ctx, const T* A, size_t m, size_t n, const T* x, T* y)
     int lli = ceil_log2(rvecs);
     if (lli > 8) lli = 8;
     const int LI = 1 << lli, CB = GV_THREADS >> lli;
-    const size_t cols_per_cta = (size_t)CB * COLS;
+    // short columns: a CTA walks G consecutive column groups so that it still moves >= 64 KiB
+    const size_t group_bytes = (size_t)CB * COLS * m * sizeof(T);
+    size_t Gs = group_bytes ? (65536 + group_bytes - 1) / group_bytes : 1;
+    if (Gs > 16) Gs = 16;
+    if (Gs < 1) Gs = 1;
+    const int G = (int)Gs;
+    const size_t cols_per_cta = (size_t)CB * COLS * G;
     const size_t gx = (n + cols_per_cta - 1) / cols_per_cta;
-    const size_t want = ((size_t)ctx->sm_count * 8 + gx - 1) / gx;
+    const size_t slots = (size_t)ctx->sm_count * (size_t)dab_resident_ctas((const void*)gemv_t_kernel<T, VEC, COLS>, GV_THREADS);
+    const size_t want = slots / gx > 0 ? slots / gx : 1;
     const size_t unit = (size_t)LI * VEC;  // rows one sweep step covers; splits start on a multiple of it (keeps 16-B alignment)
     size_t max_split = m / (unit * 16);
     if (max_split < 1) max_split = 1;
@@ -268,7 +299,7 @@ int32_t launch_t(dab_ctx* ctx, const T* A, size_t m, size_t n, const T* x, T* y)
     }
     DAB_REQUIRE(ctx, gx <= 0x7fffffffull, DAB_ERR_ARG, "dab_gemv: too many column tiles");
     dim3 grid((unsigned)gx, (unsigned)nsplit);
-    gemv_t_kernel<T, VEC, COLS><<<grid, GV_THREADS, 0, ctx->stream>>>(A, m, n, x, lli, rps, part, y);
+    gemv_t_kernel<T, VEC, COLS><<<grid, GV_THREADS, 0, ctx->stream>>>(A, m, n, x, lli, G, rps, part, y);
     DAB_LAUNCHED(ctx);
     if (part) {
         gemv_finish_kernel<T><<<(unsigned)((n + GV_THREADS - 1) / GV_THREADS), GV_THREADS, 0, ctx->stream>>>(part, n, (int)nsplit, y);
@@ -340,11 +371,58 @@ __global__ void __launch_bounds__(256) transpose_box_kernel(U* __restrict__ dst,
     }
 }
 
+// 4-byte units with everything 16-byte aligned: 16-byte global loads down the source rows and 16-byte global stores down the
+// destination rows (4x fewer LSU instructions than the unit-wise kernel); the 64 x 64 tile is transposed through shared memory
+// with scalar accesses (pitch 65 words: at most 2-way bank conflicts on either side).
+__global__ void __launch_bounds__(256) transpose_box_vec4_kernel(uint32_t* __restrict__ dst, size_t dst_ld, const uint32_t* __restrict__ src,
+                                                                 size_t src_ld, size_t rows, size_t cols, unsigned tiles_r) {
+    __shared__ uint32_t tile[64][65];
+    const size_t tr = blockIdx.x % tiles_r, tc = blockIdx.x / tiles_r;
+    const size_t r0 = tr * 64, c0 = tc * 64;
+    const int q = threadIdx.x & 15, k0 = threadIdx.x >> 4;
+    uint4 v[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const size_t r = r0 + 4 * q, c = c0 + k0 + 16 * it;
+        if (r < rows && c < cols) v[it] = __ldcs(reinterpret_cast<const uint4*>(src + r + c * src_ld));
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int k = k0 + 16 * it;
+        tile[k][4 * q + 0] = v[it].x;
+        tile[k][4 * q + 1] = v[it].y;
+        tile[k][4 * q + 2] = v[it].z;
+        tile[k][4 * q + 3] = v[it].w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int k = k0 + 16 * it;                       // source row inside the tile = destination column
+        const size_t c = c0 + 4 * q, r = r0 + k;
+        if (r < rows && c < cols) {
+            uint4 o;
+            o.x = tile[4 * q + 0][k];
+            o.y = tile[4 * q + 1][k];
+            o.z = tile[4 * q + 2][k];
+            o.w = tile[4 * q + 3][k];
+            __stcs(reinterpret_cast<uint4*>(dst + c + r * dst_ld), o);
+        }
+    }
+}
+
 template <typename U>
 int32_t launch_transpose(dab_ctx* ctx, void* dst, size_t dst_ld, const void* src, size_t src_ld, size_t rows, size_t cols) {
     constexpr int TR_TILE = sizeof(U) <= 4 ? 64 : 32;
     const size_t tiles_r = (rows + TR_TILE - 1) / TR_TILE, tiles_c = (cols + TR_TILE - 1) / TR_TILE;
     DAB_REQUIRE(ctx, tiles_r * tiles_c <= 0x7fffffffull && tiles_r <= 0xffffffffull, DAB_ERR_ARG, "dab_transpose_box: too many tiles");
+    if constexpr (sizeof(U) == 4) {
+        if (rows % 4 == 0 && cols % 4 == 0 && src_ld % 4 == 0 && dst_ld % 4 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0) {
+            transpose_box_vec4_kernel<<<(unsigned)(tiles_r * tiles_c), 256, 0, ctx->stream>>>((uint32_t*)dst, dst_ld, (const uint32_t*)src,
+                                                                                            src_ld, rows, cols, (unsigned)tiles_r);
+            DAB_LAUNCHED(ctx);
+            return DAB_OK;
+        }
+    }
     transpose_box_kernel<U, TR_TILE><<<(unsigned)(tiles_r * tiles_c), 256, 0, ctx->stream>>>((U*)dst, dst_ld, (const U*)src, src_ld, rows, cols,
                                                                                    (unsigned)tiles_r);
     DAB_LAUNCHED(ctx);

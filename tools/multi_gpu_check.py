@@ -92,6 +92,30 @@ def main():
     rt.barrier()
     log("ok: halo getindex / makelocal over peer memory")
 
+    # ---- Level-2: A*x, A'*x (tile products + NCCL send/recv to the owners of y), mul! with a DVector x, copy(transpose(A))
+    for grid in (None, (P, 1), (1, P)):
+        Mx = orc.rand_u01(21, 0, 203 * 157).reshape((203, 157), order="F")
+        dM = dab.distribute(Mx, dist=grid)
+        oM = orc.distribute(Mx, nworkers=P) if grid is None else orc.distribute(Mx, procs=list(range(1, P + 1)), dist=list(grid))
+        for trans in (False, True):
+            xv = orc.rand_u01(22 + trans, 0, 203 if trans else 157)
+            W = dM.T if trans else dM
+            yv = W @ xv
+            oy = orc.darray_matvec(oM, xv, trans)
+            assert list(yv.layout.pids) == oy.pids and list(yv.layout.indices) == oy.indices
+            want = (Mx.T if trans else Mx).astype(np.float64) @ xv.astype(np.float64)
+            got = dab.to_array(yv)
+            assert np.all(np.abs(got - want) <= 1e-6 * want) and np.all(np.abs(got - orc.to_array(oy)) <= 1e-6 * want)
+            y2 = W @ dab.distribute(xv)                         # x as a DVector: blocks halo-fetched from their owners
+            assert np.array_equal(dab.to_array(y2), got)
+            dab.mul_(yv, W, xv, 2, 1)                           # y = 2*A*x + y
+            assert np.all(np.abs(dab.to_array(yv) - 3 * want) <= 3e-6 * want)
+        Tm = dM.T.copy()
+        oT = orc.darray_transpose(oM)
+        assert list(Tm.layout.indices) == oT.indices and np.array_equal(dab.to_array(Tm), Mx.T)
+    rt.barrier()
+    log("ok: A*x, A'*x, mul!, copy(transpose(A)) across ranks")
+
     # ---- C5: 256 MiB slab owned by the next rank, contiguous and 2-D strided, bandwidth vs NVLink
     m = 1 << 26
     big = dab.drand((P * (1 << 28),), dtype=F32, seed=3)      # 1 GiB chunk per GPU

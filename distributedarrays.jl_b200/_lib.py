@@ -95,6 +95,8 @@ _SIGS = {
     "dab_copy_box": (_i32, [_vp, _i32, _vp, C.POINTER(_sz), C.POINTER(_sz), _vp, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
     "dab_gemv": (_i32, [_vp, _i32, _i32, _vp, _sz, _sz, _vp, _vp]),
     "dab_transpose_box": (_i32, [_vp, _i32, _vp, _sz, _vp, _sz, _sz, _sz]),
+    "dab_sort": (_i32, [_vp, _i32, _vp, _vp, _vp, _sz]),
+    "dab_sorted_split": (_i32, [_vp, _i32, _vp, _sz, _vp, _i32, C.POINTER(C.c_ulonglong)]),
     "dab_comm_unique_id": (_i32, [_vp]),
     "dab_comm_init_rank": (_i32, [_vp, _vp, _i32, _i32]),
     "dab_comm_destroy": (_i32, [_vp]),

@@ -1,0 +1,222 @@
+"""``sort(d::DVector; sample=...)``: the reference's samplesort (src/sort.jl) with every data-sized step on the GPU.
+
+Reference step                                                   here
+---------------------------------------------------------------  ------------------------------------------------------------------
+``sort(localpart(d))`` on every worker (:8, :22)                  K11 ``dab_sort`` (LSD radix sort of the chunk)
+``sorted[collect(1:div(llp,ss):llp)]`` sample, ss = min(512,llp)  strided ``dab_copy_box`` gather + D2H of <= 1023 keys per worker
+sort the samples, pick ``np`` boundaries (:66-88, :127-155)        host (a few hundred keys; identical index arithmetic)
+scan each sorted chunk for the first ``x > boundaries[i+1]``       ``dab_sorted_split`` (binary searches on the device)
+``put!`` piece i into worker i's RemoteChannel (:42-48)            one grouped NCCL send/recv (device-to-device inside a rank)
+``sort!(lp_sorting)`` of what a worker received (:52-61)           K11 again
+``DArray(local_sorted_refs)`` without the empty parts (:163-169)   irregular layout from the received sizes
+
+The result is bit-identical to the reference's for NaN-free input (a sorted vector has one representation once -0.0 < +0.0 is
+fixed); chunk sizes follow from the same boundaries, so the layout matches too.  NaNs sort last; inside the NaN block the
+reference keeps input order, the radix sort orders by payload.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List
+
+import numpy as np
+
+from . import _lib
+from ._darray import B200Array, DArray, dab_dtype
+from .layout import layout_from_chunk_shapes
+
+_SORT_DTYPES = (np.dtype(np.float32), np.dtype(np.float64), np.dtype(np.int32), np.dtype(np.int64))
+SAMPLE_SIZE_ON_WORKER = 512                                    # src/sort.jl:69
+
+
+def _typemin(dt):
+    return -np.inf if dt.kind == "f" else np.iinfo(dt).min
+
+
+def _typemax(dt):
+    return np.inf if dt.kind == "f" else np.iinfo(dt).max
+
+
+def _host_sort(v: np.ndarray) -> np.ndarray:
+    """isless order for the (tiny) sample vector."""
+    if v.dtype.kind != "f":
+        return np.sort(v, kind="stable")
+    nan = np.isnan(v)
+    body = v[~nan]
+    return np.concatenate([body[np.lexsort((~np.signbit(body), body))], v[nan]])
+
+
+def boundaries_from_samples(samples: np.ndarray, nparts: int, dt: np.dtype) -> np.ndarray:
+    """src/sort.jl:78-85 and :149-153."""
+    s = _host_sort(np.asarray(samples).astype(dt)).copy()
+    if len(s) == 0:
+        raise _lib.ArgumentError(_lib.ERR_ARG, "sort: empty sample")
+    s[0] = _typemin(dt)
+    step = len(s) // nparts
+    b = [s[(x - 1) * step] for x in range(1, nparts + 1)]
+    b.append(_typemax(dt))
+    return np.asarray(b, dtype=dt)
+
+
+def uniform_sample(lb, ub, nparts: int, dt: np.dtype) -> np.ndarray:
+    """The ``sample::Tuple`` branch, src/sort.jl:127-145."""
+    if not lb <= ub:
+        raise AssertionError("AssertionError: lb <= ub")
+    if isinstance(lb, np.float32) and isinstance(ub, np.float32):
+        part = np.float32(abs(ub - lb)) / np.float32(nparts)
+        vals = [np.float32(lb + np.float32(n) * part) for n in range(nparts)]
+    else:
+        if dt.kind == "f" or not (isinstance(lb, (int, np.integer)) and isinstance(ub, (int, np.integer))):
+            part = abs(float(ub) - float(lb)) / nparts
+        else:  # abs(ub - lb) in T's wrap-around machine arithmetic (a full-range Int sample overflows, as in the reference)
+            bits = 8 * dt.itemsize
+            diff = (int(ub) - int(lb) + (1 << (bits - 1))) % (1 << bits) - (1 << (bits - 1))
+            part = float(diff if diff == -(1 << (bits - 1)) else abs(diff)) / nparts
+        vals = [float(lb) + n * part for n in range(nparts)]
+    if np.isnan(part) or np.isinf(part):
+        raise _lib.ArgumentError(_lib.ERR_ARG, "lower and upper bounds must not be infinities")
+    if dt.kind != "f":
+        vals = [np.rint(v) for v in vals]
+    return np.asarray(vals).astype(dt)
+
+
+def _sort_chunk(rt, src_ptr: int, n: int, dt: np.dtype, out: B200Array):
+    tmp = B200Array.empty(rt, (n,), dt, temp=True) if n > 1024 or src_ptr == out.ptr else None
+    _lib.call("dab_sort", rt.ctx, dab_dtype(dt), C.c_void_p(src_ptr), C.c_void_p(out.ptr), C.c_void_p(tmp.ptr if tmp else None), n)
+    if tmp is not None:
+        tmp.free()
+
+
+def sort(d: DArray, sample=True, by=None, alg=None, **kwargs) -> DArray:  # noqa: A001 - mirrors Base.sort
+    """``sort(d::DVector; sample=true, alg, by)`` (reference src/sort.jl:107-170).  ``sample``: True (<= 512 sampled keys per
+    worker balance the parts), False (uniform between min(d) and max(d)), a ``(min, max)`` tuple, or an array used as the sample.
+    ``alg`` is accepted and ignored: a keys-only sort has one result whatever the algorithm."""
+    return sort_with_boundaries(d, sample, by, alg, **kwargs)[0]
+
+
+def sort_with_boundaries(d: DArray, sample=True, by=None, alg=None, **kwargs):
+    """``sort`` plus the ``boundaries`` vector it partitioned with (what compute_boundaries returns, src/sort.jl:66-88)."""
+    if kwargs:
+        raise _lib.ArgumentError(_lib.ERR_ARG, "Only `alg`, `by` and `sample` are supported as keyword arguments")
+    if by is not None:
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "sort(d; by=f): key functions are not served by the B200 backend")
+    if d.ndim != 1:
+        raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, "sort is defined for a DVector")
+    dt = d.dtype
+    if dt not in _SORT_DTYPES:
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"sort: eltype {dt} (served: Float32 Float64 Int32 Int64)")
+    rt = d.rt
+    pids = list(d.layout.pids)
+    nparts = len(pids)
+    if nparts > 256:
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "sort over more than 256 workers")
+    isz = dt.itemsize
+    if sample is True and any(hi < lo for ((lo, hi),) in d.layout.indices):
+        raise ZeroDivisionError("DivideError: integer division error")            # div(llp, 0) on an empty localpart, src/sort.jl:9
+
+    # ---- boundaries that do not need the sorted chunks (src/sort.jl:118-155)
+    presample = None
+    if sample is False:
+        from ._mapreduce import maximum, minimum
+        sample = (minimum(d), maximum(d))
+    if isinstance(sample, tuple):
+        if len(sample) != 2:
+            raise _lib.ArgumentError(_lib.ERR_ARG, "keyword arg `sample` must be Boolean, Tuple(Min,Max) or an actual sample of data")
+        presample = uniform_sample(sample[0], sample[1], nparts, dt)
+    elif isinstance(sample, (np.ndarray, list)):
+        presample = np.asarray(sample)
+    elif sample is not True:
+        raise _lib.ArgumentError(_lib.ERR_ARG, f"keyword arg `sample` must be Boolean, Tuple(Min,Max) or an actual sample of data : {sample}")
+
+    # ---- sort(localpart(d)) on every worker
+    srt: Dict[int, B200Array] = {}
+    for pid, ch in d.chunks.items():
+        out = B200Array.empty(rt, (ch.size,), dt, temp=True)
+        _sort_chunk(rt, ch.ptr, ch.size, dt, out)
+        srt[pid] = out
+
+    # ---- boundaries
+    if presample is not None:
+        boundaries = boundaries_from_samples(presample, nparts, dt)
+    else:
+        mine = {}
+        for pid, s in srt.items():
+            llp = s.size
+            ss = SAMPLE_SIZE_ON_WORKER if llp > SAMPLE_SIZE_ON_WORKER else llp
+            if ss == 0:
+                raise ZeroDivisionError("DivideError: integer division error")        # div(llp, 0), src/sort.jl:9
+            step = llp // ss
+            cnt = len(range(0, llp, step))
+            g = B200Array.empty(rt, (cnt,), dt, temp=True)
+            # sorted[1:step:llp]: row 0 of the (step x cnt) column-major view of the sorted chunk
+            _lib.call("dab_copy_box", rt.ctx, isz, C.c_void_p(g.ptr), _lib.sz4((1, cnt)), _lib.sz4((0, 0, 0, 0)), C.c_void_p(s.ptr),
+                      _lib.sz4((step, cnt)), _lib.sz4((0, 0, 0, 0)), _lib.sz4((1, cnt)))
+            mine[pid] = g.to_numpy()
+            g.free()
+        everyone = {}
+        for part in (rt.allgather_object(mine) if rt.world > 1 else [mine]):
+            everyone.update(part)
+        boundaries = boundaries_from_samples(np.concatenate([everyone[p] for p in pids]), nparts, dt)
+
+    # ---- split every sorted chunk at the boundaries (src/sort.jl:26-40): sizes[src pid][destination index]
+    sizes_mine: Dict[int, List[int]] = {}
+    ends: Dict[int, List[int]] = {}
+    bnd = np.ascontiguousarray(boundaries[1:])
+    for pid, s in srt.items():
+        cnt = (C.c_ulonglong * nparts)()
+        _lib.call("dab_sorted_split", rt.ctx, dab_dtype(dt), C.c_void_p(s.ptr), s.size, C.c_void_p(bnd.ctypes.data), nparts, cnt)
+        e, prev = [], 0
+        for i in range(nparts):
+            prev = max(prev, int(cnt[i]))                   # the scan for piece i starts where piece i-1 ended
+            e.append(prev)
+        ends[pid] = e
+        sizes_mine[pid] = [e[0]] + [e[i] - e[i - 1] for i in range(1, nparts)]
+    sizes: Dict[int, List[int]] = {}
+    for part in (rt.allgather_object(sizes_mine) if rt.world > 1 else [sizes_mine]):
+        sizes.update(part)
+
+    # ---- ship piece i to worker i
+    totals = [sum(sizes[p][j] for p in pids) for j in range(nparts)]
+    recv: Dict[int, B200Array] = {}
+    for j, pid in enumerate(pids):
+        if rt.is_local(pid) and totals[j]:
+            recv[j] = B200Array.empty(rt, (totals[j],), dt, temp=True)
+    sends, recvs = [], []
+    for j in range(nparts):
+        dst_local = rt.is_local(pids[j])
+        off = 0
+        for p in pids:
+            n = sizes[p][j]
+            if n:
+                src_local = p in srt
+                if src_local:
+                    sptr = srt[p].ptr + (ends[p][j] - n) * isz
+                if src_local and dst_local:
+                    _lib.call("dab_d2d", rt.ctx, C.c_void_p(recv[j].ptr + off * isz), C.c_void_p(sptr), n * isz)
+                elif src_local:
+                    sends.append((sptr, n * isz, rt.rank_of(pids[j])))
+                elif dst_local:
+                    recvs.append((recv[j].ptr + off * isz, n * isz, rt.rank_of(p)))
+            off += n
+    if sends or recvs:
+        _lib.call("dab_group_start", rt.ctx)
+        for ptr, nb, peer in sends:
+            _lib.call("dab_send", rt.ctx, C.c_void_p(ptr), nb, peer)
+        for ptr, nb, peer in recvs:
+            _lib.call("dab_recv", rt.ctx, C.c_void_p(ptr), nb, peer)
+        _lib.call("dab_group_end", rt.ctx)
+    for s in srt.values():
+        s.free()
+
+    # ---- sort!(lp_sorting) on every receiver and DArray(local_sorted_refs) without the empty parts (src/sort.jl:52-61, 163-169)
+    keep = [j for j in range(nparts) if totals[j] > 0]
+    if not keep:
+        raise _lib.ArgumentError(_lib.ERR_EMPTY, "sort: empty DVector")
+    chunks: Dict[int, B200Array] = {}
+    for j, buf in recv.items():
+        out = B200Array.empty(rt, (totals[j],), dt)
+        _sort_chunk(rt, buf.ptr, totals[j], dt, out)
+        buf.free()
+        chunks[pids[j]] = out
+    layout = layout_from_chunk_shapes([(totals[j],) for j in keep], (len(keep),), [pids[j] for j in keep])
+    return DArray(layout, dt, chunks, rt), boundaries

@@ -36,6 +36,9 @@ struct dab_ctx {
     unsigned long long mbox_seq;
     int fuse_op;            // >= 0: the next launch_reduce appends the cross-rank combine for this DAB_* op
     struct dab_alloc_cache* cache;  // size-bucketed reuse of small cudaMalloc blocks (dab_core.cu)
+    void* sort_dev;         // radix-sort scratch: digit histograms + per-tile counts (dab_sort.cu)
+    size_t sort_dev_bytes;
+    void* sort_host;        // pinned: histograms read back by the host, split-point staging
     int opt_ew_tma;         // dab_set_option("ew_tma"): route aligned unary elementwise launches through the TMA-staged kernel
     char err[512];
 };

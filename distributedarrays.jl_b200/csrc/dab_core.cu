@@ -152,6 +152,8 @@ int32_t dab_shutdown(dab_ctx* ctx) {
     cudaFree(ctx->result_slot);
     cudaFree(ctx->gather_slots);
     if (ctx->dim_scratch) cudaFree(ctx->dim_scratch);
+    if (ctx->sort_dev) cudaFree(ctx->sort_dev);
+    if (ctx->sort_host) cudaFreeHost(ctx->sort_host);
     if (ctx->cache) {
         for (auto& kv : ctx->cache->free_blocks) cudaFree(kv.second);
         delete ctx->cache;

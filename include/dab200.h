@@ -248,6 +248,23 @@ int32_t dab_gemv(dab_ctx* ctx, int32_t dtype, int32_t trans, const void* A, size
 int32_t dab_transpose_box(dab_ctx* ctx, int32_t elem_bytes, void* dst, size_t dst_ld, const void* src, size_t src_ld, size_t rows,
                           size_t cols);
 
+/* ==== sort K11 (widening row f4; HBM-bound integer work) ===================================
+ * out = sort(in) for one chunk: the  sort(lp; kwargs...)  of sample_n_setup_ref (src/sort.jl:8) and the
+ * sort!(lp_sorting)  of scatter_n_sort_localparts (:61).  Ascending in Julia's isless order (-0.0 < 0.0,
+ * NaNs last, bit patterns preserved).  LSD radix sort, 8-bit digits; passes whose digit is constant over
+ * the chunk are skipped.  tmp: scratch of n elements, distinct from in/out (may be NULL when n <= 1024 and
+ * in != out); in == out sorts in place.  Synchronises the ctx stream once (digit histogram read-back).
+ * dtypes: F32 F64 I32 I64. */
+int32_t dab_sort(dab_ctx* ctx, int32_t dtype, const void* in, void* out, void* tmp, size_t n);
+
+/* Split points of a sorted chunk for the boundaries of the samplesort (src/sort.jl:28-40): for each of the
+ * nb (<= 256) host values bounds[i] (dtype elements), counts_host[i] = the number of leading elements the
+ * reference's scan would pass before the first x > bounds[i] had it started at element 1 -- the count of
+ * non-NaN elements <= bounds[i], or n when nothing exceeds the bound (NaNs compare false and stay).
+ * Synchronous (returns with counts_host filled). */
+int32_t dab_sorted_split(dab_ctx* ctx, int32_t dtype, const void* sorted, size_t n, const void* bounds_host, int32_t nb,
+                         unsigned long long* counts_host);
+
 /* ==== cross-worker combine: NCCL over NVLink (replaces Distributed.remotecall_fetch on
  *      this path only; src/mapreduce.jl:30-34, 72-80; src/darray.jl:809-815) ============== */
 /* 128-byte ncclUniqueId; rank 0 creates it, the host runtime ships it to the other workers. */

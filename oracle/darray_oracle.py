@@ -788,3 +788,113 @@ def darray_scale_diag(DA: ODArray, d: np.ndarray, side: str) -> ODArray:
             s = np.asarray(d[I[1][0] - 1:I[1][1]]).astype(ch.dtype)[None, :]
             out.append(np.asfortranarray((ch * s).astype(ch.dtype)))
     return ODArray(DA.dims, DA.grid, DA.pids, DA.indices, DA.cuts, out)
+
+
+# --------------------------------------------------------------------------
+# Samplesort of a DVector  (src/sort.jl)
+# --------------------------------------------------------------------------
+
+
+def jl_sort(v: np.ndarray) -> np.ndarray:
+    """``sort(v)`` in Julia's ``isless`` order: -0.0 before +0.0, NaNs last (Julia keeps the NaNs in input order)."""
+    v = np.asarray(v)
+    if v.dtype.kind != "f":
+        return np.sort(v, kind="stable")
+    nan = np.isnan(v)
+    body = v[~nan]
+    order = np.lexsort((~np.signbit(body), body))
+    return np.concatenate([body[order], v[nan]])
+
+
+def _typemin(dt):
+    return -np.inf if np.dtype(dt).kind == "f" else np.iinfo(dt).min
+
+
+def _typemax(dt):
+    return np.inf if np.dtype(dt).kind == "f" else np.iinfo(dt).max
+
+
+def sort_sample_indices(llp: int, sample_size: int = 512) -> range:
+    """0-based indices of ``sorted[collect(1:div(llp,sample_size):llp)]`` with ``sample_size = min(sample_size, llp)``
+    (src/sort.jl:3-9).  An empty localpart divides by zero in the reference."""
+    ss = sample_size if llp > sample_size else llp
+    if ss == 0:
+        raise ZeroDivisionError("DivideError: integer division error")
+    return range(0, llp, llp // ss)
+
+
+def sort_boundaries_from_samples(samples: np.ndarray, nparts: int, dt) -> np.ndarray:
+    """``sort!(samples); samples[1] = typemin(T); boundaries = samples[[1+(x-1)*div(length(samples), np) for x in 1:np]];
+    push!(boundaries, typemax(T))`` (src/sort.jl:78-85, 149-153)."""
+    s = jl_sort(np.asarray(samples, dtype=dt)).copy()
+    s[0] = _typemin(dt)
+    step = len(s) // nparts
+    b = [s[(x - 1) * step] for x in range(1, nparts + 1)]
+    b.append(_typemax(dt))
+    return np.asarray(b, dtype=dt)
+
+
+def sort_uniform_sample(lb, ub, nparts: int, dt) -> np.ndarray:
+    """The ``sample::Tuple`` branch (src/sort.jl:127-145): ``s[n] = lb + (n-1)*abs(ub-lb)/np`` (rounded for integer T)."""
+    assert lb <= ub
+    if isinstance(lb, np.float32) and isinstance(ub, np.float32):
+        part = np.float32(abs(ub - lb)) / np.float32(nparts)
+        vals = [np.float32(lb + np.float32(n) * part) for n in range(nparts)]
+    else:
+        if np.dtype(dt).kind == "f" or not (isinstance(lb, (int, np.integer)) and isinstance(ub, (int, np.integer))):
+            part = abs(float(ub) - float(lb)) / nparts
+        else:  # abs(ub - lb) in T's wrap-around machine arithmetic (a full-range Int sample overflows, as in the reference)
+            bits = 8 * np.dtype(dt).itemsize
+            diff = (int(ub) - int(lb) + (1 << (bits - 1))) % (1 << bits) - (1 << (bits - 1))
+            part = float(diff if diff == -(1 << (bits - 1)) else abs(diff)) / nparts
+        vals = [float(lb) + n * part for n in range(nparts)]
+    if np.isnan(part) or np.isinf(part):
+        raise ValueError("ArgumentError: lower and upper bounds must not be infinities")
+    if np.dtype(dt).kind != "f":
+        vals = [np.rint(v) for v in vals]
+    return np.asarray(vals).astype(dt)
+
+
+def sort_split_points(sorted_lp: np.ndarray, boundaries: np.ndarray) -> List[int]:
+    """The scan of scatter_n_sort_localparts (src/sort.jl:26-50): piece i = sorted[p_sorted : first x > boundaries[i+1])."""
+    ends, p = [], 0
+    n = len(sorted_lp)
+    for i in range(len(boundaries) - 1):
+        with np.errstate(invalid="ignore"):
+            gt = sorted_lp[p:] > boundaries[i + 1]
+        p_till = p + int(np.argmax(gt)) if gt.any() else n
+        ends.append(p_till)
+        p = p_till
+    return ends
+
+
+def darray_sort(d: ODArray, sample=True):
+    """``sort(d::DVector; sample)`` (src/sort.jl:107-170).  Returns (ODArray of the sorted vector, boundaries)."""
+    nparts = len(d.pids)
+    dt = d.chunks[0].dtype
+    srt = [jl_sort(c) for c in d.chunks]
+    if sample is True:
+        samples = np.concatenate([s[list(sort_sample_indices(len(s)))] for s in srt])
+        boundaries = sort_boundaries_from_samples(samples, nparts, dt)
+    else:
+        if sample is False:
+            lo = min(c.min() for c in d.chunks)
+            hi = max(c.max() for c in d.chunks)
+            sample = (lo, hi)
+        if isinstance(sample, tuple):
+            sample = sort_uniform_sample(sample[0], sample[1], nparts, dt)
+        boundaries = sort_boundaries_from_samples(np.asarray(sample), nparts, dt)
+    recv = [[] for _ in range(nparts)]
+    for s in srt:
+        p = 0
+        for i, e in enumerate(sort_split_points(s, boundaries)):
+            recv[i].append(s[p:e])
+            p = e
+    parts = [jl_sort(np.concatenate(r)) for r in recv]
+    keep = [i for i, p in enumerate(parts) if len(p) > 0]       # zero-length parts are dropped (src/sort.jl:163-168)
+    sizes = [len(parts[i]) for i in keep]
+    starts = np.concatenate([[1], 1 + np.cumsum(sizes)]).astype(int)
+    out = ODArray((int(sum(sizes)),), (len(keep),), [d.pids[i] for i in keep],
+                  [((int(starts[k]), int(starts[k + 1] - 1)),) for k in range(len(keep))], [list(map(int, starts))],
+                  [parts[i] for i in keep])
+    return out, boundaries

@@ -116,6 +116,21 @@ def main():
     rt.barrier()
     log("ok: A*x, A'*x, mul!, copy(transpose(A)) across ranks")
 
+    # ---- samplesort across ranks: pieces travel by grouped NCCL send/recv; layout and boundaries equal the oracle's
+    for T in (np.int64, np.float64):
+        rs = np.random.default_rng(77)
+        av = rs.integers(-10 ** 12, 10 ** 12, 300007).astype(T) if T is np.int64 else rs.standard_normal(300007)
+        dv = dab.distribute(av)
+        ov = orc.distribute(av, nworkers=P)
+        for sample in (True, False, av[:400]):
+            d2, bnd = dab.sort_with_boundaries(dv, sample=sample)
+            o2, ob = orc.darray_sort(ov, sample)
+            assert np.array_equal(bnd, ob) and list(d2.layout.pids) == o2.pids and list(d2.layout.indices) == o2.indices
+            assert np.array_equal(dab.to_array(d2), np.sort(av))
+            d2.close()
+    rt.barrier()
+    log("ok: sort(d::DVector) across ranks")
+
     # ---- C5: 256 MiB slab owned by the next rank, contiguous and 2-D strided, bandwidth vs NVLink
     m = 1 << 26
     big = dab.drand((P * (1 << 28),), dtype=F32, seed=3)      # 1 GiB chunk per GPU

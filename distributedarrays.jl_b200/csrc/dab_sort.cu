@@ -12,7 +12,7 @@
 //   sort_count_kernel   per-tile digit counts                               (read n keys)
 //   sort_scan_kernel    exclusive scan of the counts along the tiles, one CTA per digit value
 //   sort_scatter_kernel stable multi-split of each tile and scatter          (read n keys, write n keys)
-//                       a warp owns a contiguous run of the tile; __match_any_sync groups equal digits inside each 32-key step,
+//                       a warp owns a contiguous run of the tile; ballots group equal digits inside each 32-key step,
 //                       per-warp shared counters carry the running rank, so equal digits keep their input order (LSD needs it).
 // Algorithmic bytes: elem * (1 + 3 * passes) per key.  Tiles are 256 threads x 16 keys.
 #include <type_traits>
@@ -65,6 +65,45 @@ template <> struct SortKey<double> {
 
 struct SortBases { uint32_t b[256]; };
 
+// Lanes of the warp whose 8-bit digit equals mine (dg = 256 marks "no key"; those lanes group together): 9 ballots.  On sm_100a
+// __match_any_sync costs one round per DISTINCT value in the warp (measured ~45 clk per warp-step on random digits); the bitwise
+// form is flat.
+__device__ __forceinline__ unsigned int match_digit(unsigned int dg) {
+    unsigned int m = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) {
+        const bool bit = (dg >> b) & 1u;
+        const unsigned int bal = __ballot_sync(0xffffffffu, bit);
+        m &= bit ? bal : ~bal;
+    }
+    return m;
+}
+
+// A thread's ST_KPT CONSECUTIVE keys (blocked arrangement: 128 contiguous bytes of 8-byte keys), 16-byte loads when the tile is full
+// and aligned.  Returns how many of them exist.  Used by the counting kernels: runs of equal digits (sorted or narrow-range input)
+// collapse into one shared-memory atomic per run instead of serialising a whole warp on one bin.
+template <typename U>
+__device__ __forceinline__ int load_blocked(const U* __restrict__ in, size_t first, size_t n, U (&key)[ST_KPT]) {
+    if (first + ST_KPT <= n && (reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
+        constexpr int PER = 16 / sizeof(U);
+        const int4* p = reinterpret_cast<const int4*>(in + first);
+#pragma unroll
+        for (int q = 0; q < ST_KPT / PER; ++q) {
+            const int4 v = __ldcs(p + q);
+            memcpy(&key[q * PER], &v, 16);
+        }
+        return ST_KPT;
+    }
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < ST_KPT; ++k)
+        if (first + k < n) {
+            key[k] = __ldcs(in + first + k);
+            cnt = k + 1;
+        }
+    return cnt;
+}
+
 // ---- all-digit histogram ------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(ST_THREADS) sort_hist_kernel(const typename SortKey<T>::U* __restrict__ in, size_t n,
@@ -76,14 +115,34 @@ __global__ void __launch_bounds__(ST_THREADS) sort_hist_kernel(const typename So
     __syncthreads();
     // grid-stride over tiles: a few CTAs per SM accumulate privately, so the global histogram sees gridDim.x flushes, not n / 4096
     for (size_t base = (size_t)blockIdx.x * ST_TILE; base < n; base += (size_t)gridDim.x * ST_TILE) {
-#pragma unroll 4
-        for (int k = 0; k < ST_KPT; ++k) {
-            const size_t i = base + (size_t)k * ST_THREADS + threadIdx.x;
-            if (i < n) {
-                const U key = K::enc(__ldcs(in + i));
+        U key[ST_KPT];
+        const int cnt = load_blocked<U>(in, base + (size_t)threadIdx.x * ST_KPT, n, key);
+        if (cnt > 0) {
+            unsigned int cur[K::DIGITS], run[K::DIGITS];
+            const U k0 = K::enc(key[0]);
 #pragma unroll
-                for (int d = 0; d < K::DIGITS; ++d) atomicAdd(&sh[d][(unsigned)(key >> (8 * d)) & 255u], 1u);
+            for (int d = 0; d < K::DIGITS; ++d) {
+                cur[d] = (unsigned)(k0 >> (8 * d)) & 255u;
+                run[d] = 1;
             }
+#pragma unroll
+            for (int k = 1; k < ST_KPT; ++k)
+                if (k < cnt) {
+                    const U kk = K::enc(key[k]);
+#pragma unroll
+                    for (int d = 0; d < K::DIGITS; ++d) {
+                        const unsigned int dg = (unsigned)(kk >> (8 * d)) & 255u;
+                        if (dg == cur[d]) {
+                            ++run[d];
+                        } else {
+                            atomicAdd(&sh[d][cur[d]], run[d]);
+                            cur[d] = dg;
+                            run[d] = 1;
+                        }
+                    }
+                }
+#pragma unroll
+            for (int d = 0; d < K::DIGITS; ++d) atomicAdd(&sh[d][cur[d]], run[d]);
         }
     }
     __syncthreads();
@@ -102,15 +161,23 @@ __global__ void __launch_bounds__(ST_THREADS) sort_count_kernel(const typename S
     __shared__ unsigned int sh[256];
     sh[threadIdx.x] = 0;
     __syncthreads();
-    const size_t base = (size_t)blockIdx.x * ST_TILE;
-#pragma unroll 4
-    for (int k = 0; k < ST_KPT; ++k) {
-        const size_t i = base + (size_t)k * ST_THREADS + threadIdx.x;
-        if (i < n) {
-            U key = __ldcs(in + i);
-            if (RAW) key = K::enc(key);
-            atomicAdd(&sh[(unsigned)(key >> shift) & 255u], 1u);
-        }
+    U key[ST_KPT];
+    const int cnt = load_blocked<U>(in, (size_t)blockIdx.x * ST_TILE + (size_t)threadIdx.x * ST_KPT, n, key);
+    if (cnt > 0) {
+        unsigned int cur = (unsigned)((RAW ? K::enc(key[0]) : key[0]) >> shift) & 255u, run = 1;
+#pragma unroll
+        for (int k = 1; k < ST_KPT; ++k)
+            if (k < cnt) {
+                const unsigned int dg = (unsigned)((RAW ? K::enc(key[k]) : key[k]) >> shift) & 255u;
+                if (dg == cur) {
+                    ++run;
+                } else {
+                    atomicAdd(&sh[cur], run);
+                    cur = dg;
+                    run = 1;
+                }
+            }
+        atomicAdd(&sh[cur], run);
     }
     __syncthreads();
     counts[(size_t)threadIdx.x * nblocks + blockIdx.x] = sh[threadIdx.x];   // digit-major: row d holds the tiles' counts of digit d
@@ -176,19 +243,26 @@ __global__ void __launch_bounds__(ST_THREADS) sort_scatter_kernel(const typename
         const size_t i = wbase + (size_t)k * 32 + lane;
         key[k] = i < n ? __ldcs(in + i) : U(0);
     }
+    // phase A: group equal digits inside each 32-key step (independent across steps, so the matches overlap)
+    unsigned int grp[ST_KPT];
+#pragma unroll
+    for (int k = 0; k < ST_KPT; ++k) {
+        const size_t i = wbase + (size_t)k * 32 + lane;
+        if (RAW_IN) key[k] = K::enc(key[k]);
+        const unsigned int dg = (i < n) ? ((unsigned)(key[k] >> shift) & 255u) : 256u;   // invalid lanes form their own group
+        grp[k] = match_digit(dg);
+    }
+    // phase B: running per-warp digit counters; the group's lowest lane bumps the counter once and hands the old value round.
+    // Steps are issued in order by the one warp that owns this counter row, so equal digits keep their input order.
 #pragma unroll
     for (int k = 0; k < ST_KPT; ++k) {
         const size_t i = wbase + (size_t)k * 32 + lane;
         const bool valid = i < n;
-        if (RAW_IN) key[k] = K::enc(key[k]);
-        const unsigned int dg = valid ? ((unsigned)(key[k] >> shift) & 255u) : 256u;   // invalid lanes form their own group
-        const unsigned int grp = __match_any_sync(0xffffffffu, dg);
-        const unsigned int before = __popc(grp & lt);
+        const unsigned int before = __popc(grp[k] & lt);
+        const int leader = __ffs(grp[k]) - 1;
         unsigned int old = 0;
-        if (valid) old = wc[warp][dg];
-        __syncwarp();
-        if (valid && before == 0) wc[warp][dg] = old + __popc(grp);
-        __syncwarp();
+        if (valid && before == 0) old = atomicAdd(&wc[warp][(unsigned)(key[k] >> shift) & 255u], (unsigned int)__popc(grp[k]));
+        old = __shfl_sync(0xffffffffu, old, leader);
         rank[k] = (unsigned short)(old + before);
     }
     __syncthreads();

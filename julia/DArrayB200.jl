@@ -17,9 +17,13 @@
 #   src/darray.jl:815    localpart(d)[idxs...]            Base.getindex(::B200Array, ranges...)      dab_copy_box
 #   src/darray.jl:824,831 fill! / rand!                   Base.fill! / Random.rand!                  dab_fill / dab_rand_u01
 #   src/mapreduce.jl:34  reduce(op, results)              (DArray method below)                      dab_mapreduce_all
+#   src/linalg.jl:95-97,141 localpart(A)*xj, localpart(A)'*xj   Base.:*                                 dab_gemv
+#   src/linalg.jl:1-17   transpose!(lp, rp)               LinearAlgebra.transpose! / adjoint!        dab_transpose_box
+#   src/sort.jl:8,22,61  sort(localpart(d)), sort!(lp)    Base.sort / Base.sort!                     dab_sort
 module DArrayB200
 
-using Distributed, DistributedArrays
+using Distributed, DistributedArrays, LinearAlgebra
+using LinearAlgebra: Adjoint, Transpose
 import Base.Broadcast: Broadcasted, BroadcastStyle, AbstractArrayStyle
 
 const libdab = get(ENV, "LIBDAB200", "libdab200.so")
@@ -228,6 +232,42 @@ function init_comm(pids = workers())
             check(ccall((:dab_mailbox_attach, libdab), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), ctx(), allh, r - 1, length(pids)), ctx())
         end
     end
+end
+
+# ---- Level-2 and sort on the chunk type (widening rows): the generic code of src/linalg.jl and src/sort.jl then runs unchanged ------
+# localpart(A)*xj  /  localpart(A)'*xj  inside mul!(y::DVector, A::DMatrix, x, α, β)  (src/linalg.jl:95-97, 141)
+function gemv(trans::Bool, A::B200Array{T,2}, x::B200Array{T,1}) where {T}
+    m, n = size(A)
+    r = B200Array{T,1}(undef, (trans ? n : m,))
+    check(ccall((:dab_gemv, libdab), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Cvoid}, Csize_t, Csize_t, Ptr{Cvoid}, Ptr{Cvoid}),
+                ctx(), dab_dtype(T), trans ? 1 : 0, A.ptr, m, n, x.ptr, r.ptr), ctx())
+    r
+end
+Base.:*(A::B200Array{T,2}, x::B200Array{T,1}) where {T} = gemv(false, A, x)
+Base.:*(A::Adjoint{T,<:B200Array{T,2}}, x::B200Array{T,1}) where {T<:Real} = gemv(true, parent(A), x)
+Base.:*(A::Transpose{T,<:B200Array{T,2}}, x::B200Array{T,1}) where {T} = gemv(true, parent(A), x)
+
+# transpose!(lp, rp) / adjoint!(lp, rp) of copy(::Transpose{T,<:DArray{T,2}})  (src/linalg.jl:1-17), real T
+function LinearAlgebra.transpose!(dst::B200Array{T,2}, src::B200Array{T,2}) where {T}
+    rows, cols = size(src)
+    check(ccall((:dab_transpose_box, libdab), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}, Csize_t, Csize_t, Csize_t),
+                ctx(), sizeof(T), dst.ptr, cols, src.ptr, rows, rows, cols), ctx())
+    dst
+end
+LinearAlgebra.adjoint!(dst::B200Array{T,2}, src::B200Array{T,2}) where {T<:Real} = transpose!(dst, src)
+
+# sort(localpart(d)) / sort!(lp_sorting)  (src/sort.jl:8, 22, 61); keys only, isless order
+function Base.sort!(a::B200Array{T,1}; kw...) where {T}
+    tmp = B200Array{T,1}(undef, size(a))
+    check(ccall((:dab_sort, libdab), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t),
+                ctx(), dab_dtype(T), a.ptr, a.ptr, tmp.ptr, length(a)), ctx())
+    a
+end
+function Base.sort(a::B200Array{T,1}; kw...) where {T}
+    out = B200Array{T,1}(undef, size(a)); tmp = B200Array{T,1}(undef, size(a))
+    check(ccall((:dab_sort, libdab), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t),
+                ctx(), dab_dtype(T), a.ptr, out.ptr, tmp.ptr, length(a)), ctx())
+    out
 end
 
 # user code is then unchanged:

@@ -14,7 +14,7 @@
 //   sort_scatter_kernel stable multi-split of each tile and scatter          (read n keys, write n keys)
 //                       a warp owns a contiguous run of the tile; ballots group equal digits inside each 32-key step,
 //                       per-warp shared counters carry the running rank, so equal digits keep their input order (LSD needs it).
-// Algorithmic bytes: elem * (1 + 3 * passes) per key.  Tiles are 256 threads x 16 keys.
+// Algorithmic bytes: elem * (1 + 3 * passes) per key.  Tiles are 256 threads x 8 keys.
 #include <type_traits>
 
 #include "dab_common.cuh"
@@ -22,8 +22,8 @@
 namespace {
 
 constexpr int ST_THREADS = 256;
-constexpr int ST_KPT = 16;                       // keys per thread
-constexpr int ST_TILE = ST_THREADS * ST_KPT;     // 4096 keys per CTA
+constexpr int ST_KPT = 8;                        // keys per thread (16 left the scatter at 111 registers = 2 CTAs per SM, latency-bound)
+constexpr int ST_TILE = ST_THREADS * ST_KPT;     // 2048 keys per CTA
 constexpr int ST_WARPS = ST_THREADS / 32;
 
 // ---- order-preserving bijection raw bits <-> unsigned key ----------------------------------------------------------------------
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(unsigned int* __restric
 
 // ---- stable scatter of one digit -------------------------------------------------------------------------------------------------------
 template <typename T, bool RAW_IN, bool RAW_OUT>
-__global__ void __launch_bounds__(ST_THREADS) sort_scatter_kernel(const typename SortKey<T>::U* __restrict__ in,
+__global__ void __launch_bounds__(ST_THREADS, 4) sort_scatter_kernel(const typename SortKey<T>::U* __restrict__ in,
                                                                   typename SortKey<T>::U* __restrict__ out, size_t n, int shift,
                                                                   unsigned int nblocks, const unsigned int* __restrict__ offsets,
                                                                   SortBases bases) {
@@ -243,25 +243,20 @@ __global__ void __launch_bounds__(ST_THREADS) sort_scatter_kernel(const typename
         const size_t i = wbase + (size_t)k * 32 + lane;
         key[k] = i < n ? __ldcs(in + i) : U(0);
     }
-    // phase A: group equal digits inside each 32-key step (independent across steps, so the matches overlap)
-    unsigned int grp[ST_KPT];
-#pragma unroll
-    for (int k = 0; k < ST_KPT; ++k) {
-        const size_t i = wbase + (size_t)k * 32 + lane;
-        if (RAW_IN) key[k] = K::enc(key[k]);
-        const unsigned int dg = (i < n) ? ((unsigned)(key[k] >> shift) & 255u) : 256u;   // invalid lanes form their own group
-        grp[k] = match_digit(dg);
-    }
-    // phase B: running per-warp digit counters; the group's lowest lane bumps the counter once and hands the old value round.
-    // Steps are issued in order by the one warp that owns this counter row, so equal digits keep their input order.
+    // Running per-warp digit counters.  Equal digits inside a 32-key step are grouped by ballots; the group's lowest lane bumps the
+    // counter once and hands the old value round.  Steps are issued in order by the one warp that owns this counter row, so equal
+    // digits keep their input order.
 #pragma unroll
     for (int k = 0; k < ST_KPT; ++k) {
         const size_t i = wbase + (size_t)k * 32 + lane;
         const bool valid = i < n;
-        const unsigned int before = __popc(grp[k] & lt);
-        const int leader = __ffs(grp[k]) - 1;
+        if (RAW_IN) key[k] = K::enc(key[k]);
+        const unsigned int dg = valid ? ((unsigned)(key[k] >> shift) & 255u) : 256u;   // invalid lanes form their own group
+        const unsigned int grp = match_digit(dg);
+        const unsigned int before = __popc(grp & lt);
+        const int leader = __ffs(grp) - 1;
         unsigned int old = 0;
-        if (valid && before == 0) old = atomicAdd(&wc[warp][(unsigned)(key[k] >> shift) & 255u], (unsigned int)__popc(grp[k]));
+        if (valid && before == 0) old = atomicAdd(&wc[warp][dg], (unsigned int)__popc(grp));
         old = __shfl_sync(0xffffffffu, old, leader);
         rank[k] = (unsigned short)(old + before);
     }

@@ -87,6 +87,29 @@ def _sort_chunk(rt, src_ptr: int, n: int, dt: np.dtype, out: B200Array):
         tmp.free()
 
 
+def sort_exchange_plan(pids, sizes, rank_of, my_rank: int):
+    """Who ships which piece where: piece j of source worker p (``sizes[p][j]`` keys, the run ending at split point j of p's sorted
+    chunk) goes to worker ``pids[j]`` and lands at offset ``sum of the earlier sources' pieces`` of its receive buffer (the
+    reference appends in arrival order and sorts afterwards, src/sort.jl:42-61; source order is used here).  Pure function of
+    the size matrix, so every rank derives matching send/recv lists in the same (j, p) order."""
+    plan = {"local": [], "sends": [], "recvs": []}
+    for j in range(len(pids)):
+        drank = rank_of(pids[j])
+        off = 0
+        for p in pids:
+            n = sizes[p][j]
+            if n:
+                srank = rank_of(p)
+                if srank == my_rank and drank == my_rank:
+                    plan["local"].append((j, p, off, n))
+                elif srank == my_rank:
+                    plan["sends"].append((j, p, n, drank))
+                elif drank == my_rank:
+                    plan["recvs"].append((j, p, off, n, srank))
+            off += n
+    return plan
+
+
 def sort(d: DArray, sample=True, by=None, alg=None, **kwargs) -> DArray:  # noqa: A001 - mirrors Base.sort
     """``sort(d::DVector; sample=true, alg, by)`` (reference src/sort.jl:107-170).  ``sample``: True (<= 512 sampled keys per
     worker balance the parts), False (uniform between min(d) and max(d)), a ``(min, max)`` tuple, or an array used as the sample.
@@ -181,23 +204,11 @@ def sort_with_boundaries(d: DArray, sample=True, by=None, alg=None, **kwargs):
     for j, pid in enumerate(pids):
         if rt.is_local(pid) and totals[j]:
             recv[j] = B200Array.empty(rt, (totals[j],), dt, temp=True)
-    sends, recvs = [], []
-    for j in range(nparts):
-        dst_local = rt.is_local(pids[j])
-        off = 0
-        for p in pids:
-            n = sizes[p][j]
-            if n:
-                src_local = p in srt
-                if src_local:
-                    sptr = srt[p].ptr + (ends[p][j] - n) * isz
-                if src_local and dst_local:
-                    _lib.call("dab_d2d", rt.ctx, C.c_void_p(recv[j].ptr + off * isz), C.c_void_p(sptr), n * isz)
-                elif src_local:
-                    sends.append((sptr, n * isz, rt.rank_of(pids[j])))
-                elif dst_local:
-                    recvs.append((recv[j].ptr + off * isz, n * isz, rt.rank_of(p)))
-            off += n
+    plan = sort_exchange_plan(pids, sizes, rt.rank_of, rt.rank)
+    for j, p, off, n in plan["local"]:
+        _lib.call("dab_d2d", rt.ctx, C.c_void_p(recv[j].ptr + off * isz), C.c_void_p(srt[p].ptr + (ends[p][j] - n) * isz), n * isz)
+    sends = [(srt[p].ptr + (ends[p][j] - n) * isz, n * isz, peer) for j, p, n, peer in plan["sends"]]
+    recvs = [(recv[j].ptr + off * isz, n * isz, peer) for j, p, off, n, peer in plan["recvs"]]
     if sends or recvs:
         _lib.call("dab_group_start", rt.ctx)
         for ptr, nb, peer in sends:

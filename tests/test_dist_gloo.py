@@ -115,3 +115,130 @@ def test_world2_exchange_plans_and_ordered_fold(wpr):
         p.join(timeout=30)
     for rank, msg in results:
         assert msg == "ok", f"rank {rank}:\n{msg}"
+
+
+def _worker_level2_sort(rank, world, port, wpr, q):
+    """mul!(y, A, x) and sort(d) across 2 ranks: the product's plans (``_linalg.matvec_exchange_plan``, ``_sort.sort_exchange_plan``,
+    ``_sort.boundaries_from_samples``) executed with NumPy + gloo in the TEST; per-chunk work (tile products, chunk sorts, split
+    points) comes from the oracle.  The result must equal the oracle's distributed restatement chunk by chunk."""
+    try:
+        sys.path.insert(0, ROOT)
+        import torch
+        import torch.distributed as dist
+
+        import darray_b200 as dab
+        from darray_b200._linalg import matvec_exchange_plan
+        from darray_b200._sort import boundaries_from_samples, sort_exchange_plan
+        from oracle import darray_oracle as orc
+
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        P = world * wpr
+        rank_of = lambda pid: (pid - 1) // wpr                                                  # noqa: E731
+        rng = np.random.default_rng(7)
+        # ---- mul!(y, A, x, 3, 2) and its transposed form
+        for grid in [(P, 1), (1, P)] + ([(2, 2)] if P == 4 else []):
+            for trans in (False, True):
+                A = rng.integers(-9, 9, (23, 17)).astype(np.int64)
+                x = rng.integers(-9, 9, 23 if trans else 17).astype(np.int64)
+                pids = list(range(1, P + 1))
+                L = dab.make_layout(A.shape, pids, list(grid))
+                oA = orc.distribute(A, procs=pids, dist=list(grid))
+                rd, cd = (1, 0) if trans else (0, 1)
+                g0 = grid[0]
+                ypids = [pids[j * g0] for j in range(grid[1])] if trans else pids[:g0]
+                y0 = rng.integers(-9, 9, A.shape[rd]).astype(np.int64)
+                yl = dab.make_layout((A.shape[rd],), ypids, [grid[rd]])
+                oy = orc.distribute(y0, procs=ypids, dist=[grid[rd]])
+                want = orc.darray_mul_vec(oy, oA, x, 3, 2, trans)
+                gi, gj = (grid[1], grid[0]) if trans else grid
+                plan = matvec_exchange_plan(L, yl, trans, rank_of, rank)
+                tile = {}
+                for i in range(gi):
+                    for j in range(gj):
+                        lin = (j + i * g0) if trans else (i + j * g0)
+                        if rank_of(L.pids[lin]) == rank:
+                            lo, hi = L.cuts[cd][j], L.cuts[cd][j + 1] - 1
+                            tile[(i, j)] = orc._tile_matvec(oA.chunks[lin], x[lo - 1:hi], trans)
+                stacks = {i: [None] * gj for i in plan["owned"]}
+                for i, j, plen in plan["local"]:
+                    stacks[i][j] = tile[(i, j)]
+                reqs = [dist.isend(torch.from_numpy(np.ascontiguousarray(tile[(i, j)])), peer) for i, j, plen, peer in plan["sends"]]
+                for i, j, plen, peer in plan["recvs"]:
+                    buf = torch.empty(plen, dtype=torch.int64)
+                    dist.recv(buf, peer)
+                    stacks[i][j] = buf.numpy()
+                for r in reqs:
+                    r.wait()
+                for i, parts in stacks.items():
+                    yi = 2 * oy.chunks[i]
+                    for p in parts:
+                        yi = yi + 3 * p
+                    assert np.array_equal(yi, want.chunks[i]), (grid, trans, i)
+                dist.barrier()
+        # ---- sort(d; sample=true)
+        for n in (P, 1000, 30011):
+            a = rng.integers(-10 ** 6, 10 ** 6, n).astype(np.int64)
+            pids = list(range(1, P + 1))
+            od = orc.distribute(a, procs=pids)
+            want, wantb = orc.darray_sort(od, True)
+            mine = {pid: orc.jl_sort(od.chunks[k]) for k, pid in enumerate(od.pids) if rank_of(pid) == rank}
+            samples = {pid: s[list(orc.sort_sample_indices(len(s)))] for pid, s in mine.items()}
+            gathered = [None] * world
+            dist.all_gather_object(gathered, samples)
+            allsamples = {}
+            for g in gathered:
+                allsamples.update(g)
+            b = boundaries_from_samples(np.concatenate([allsamples[p] for p in od.pids]), len(od.pids), np.dtype(np.int64))
+            assert np.array_equal(b, wantb)
+            ends = {pid: orc.sort_split_points(s, b) for pid, s in mine.items()}
+            sizes_mine = {pid: [e[0]] + [e[k] - e[k - 1] for k in range(1, len(e))] for pid, e in ends.items()}
+            dist.all_gather_object(gathered, sizes_mine)
+            sizes = {}
+            for g in gathered:
+                sizes.update(g)
+            plan = sort_exchange_plan(od.pids, sizes, rank_of, rank)
+            allplans = [None] * world
+            dist.all_gather_object(allplans, plan)
+            for peer in range(world):
+                if peer != rank:
+                    assert [(j, p, m) for j, p, m, dst in plan["sends"] if dst == peer] == \
+                           [(j, p, m) for j, p, off, m, src in allplans[peer]["recvs"] if src == rank]
+            totals = [sum(sizes[p][j] for p in od.pids) for j in range(len(od.pids))]
+            recv = {j: np.empty(totals[j], dtype=np.int64) for j, pid in enumerate(od.pids) if rank_of(pid) == rank}
+            for j, p, off, m in plan["local"]:
+                recv[j][off:off + m] = mine[p][ends[p][j] - m:ends[p][j]]
+            reqs = [dist.isend(torch.from_numpy(np.ascontiguousarray(mine[p][ends[p][j] - m:ends[p][j]])), peer) for j, p, m, peer in plan["sends"]]
+            for j, p, off, m, peer in plan["recvs"]:
+                buf = torch.empty(m, dtype=torch.int64)
+                dist.recv(buf, peer)
+                recv[j][off:off + m] = buf.numpy()
+            for r in reqs:
+                r.wait()
+            for j, buf in recv.items():
+                pid = od.pids[j]
+                if totals[j]:
+                    assert np.array_equal(np.sort(buf), want.chunks[want.pids.index(pid)]), (n, j)
+                else:
+                    assert pid not in want.pids
+            dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception:
+        q.put((rank, traceback.format_exc()))
+
+
+@pytest.mark.parametrize("wpr", [1, 2])
+def test_world2_matvec_and_sort_exchange(wpr):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_level2_sort, args=(r, 2, port, wpr, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}:\n{msg}"

@@ -39,8 +39,6 @@ _CT = {"bool": "bool", "i32": "int", "i64": "long long", "f32": "float", "f64": 
 
 def tag_of(dtype) -> str:
     dt = np.dtype(dtype)
-    if dt == np.dtype(np.uint8):
-        return "bool"
     if dt not in _TAG:
         raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"element type {dt} not served by the B200 backend")
     return _TAG[dt]
@@ -122,12 +120,16 @@ class Expr:
         return unop("abs", self)
 
     def __pow__(self, p):
-        if isinstance(p, (int, np.integer)) and 1 <= int(p) <= 4:  # Base.literal_pow: x^2 == x*x, x^3 == x*x*x
+        if isinstance(p, (int, np.integer)) and not isinstance(p, (bool, np.bool_)) and 1 <= int(p) <= 3:  # Base.literal_pow: x^2 == x*x, x^3 == x*x*x
             r = self
             for _ in range(int(p) - 1):
                 r = binop("mul", r, self)
             return r
-        return binop("pow", self, Expr.wrap(p))
+        pe = Expr.wrap(p)
+        if promote(self.jt, pe.jt)[0] != "f":
+            # Julia's integer ^ is power_by_squaring and throws DomainError for negative exponents: no kernel serves it
+            raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "integer ^ integer is not served by the B200 backend")
+        return binop("pow", self, pe)
 
     def __bool__(self):
         raise TypeError("data-dependent Python control flow cannot be traced; use dab.ifelse(cond, a, b)")
@@ -388,6 +390,10 @@ def run_local(rt, expr: Expr, out: B200Array, largs: List[LocalArg]):
         return
     # ---- general fused kernel (NVRTC)
     rt.last_kernel = "dab_broadcast_expr"
+    if expr.jt[0] == "f" and out_tag[0] != "f":
+        # dest .= f.(...) with an integer/Bool destination and float values: Julia converts exactly or throws InexactError per
+        # element; a C cast would silently truncate
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"broadcast of {expr.jt} values into a {out_tag} destination (InexactError semantics) is not served")
     src = codegen(convert(expr, out_tag)).encode()
     oshape = _pad4(out.shape)
     nargs = len(largs)
@@ -492,12 +498,22 @@ def _prepare_remote_reads(dest_layout, rt, args):
     data (makelocal's non-local branch, reference src/darray.jl:361-366).  Every rank takes the same decision from the layouts
     alone, shares the CUDA-IPC handles and fences the producers' streams before the one-sided peer reads."""
     if rt.world == 1:
-        return
+        return False
     need = [a for a in args if isinstance(a, DArray) and not (a.layout.pids == dest_layout.pids and a.layout.indices == dest_layout.indices)]
     for a in need:
         if a._handles is None:
             a.share()
     if need:
+        rt.barrier()
+    return bool(need)
+
+
+def _finish_remote_reads(rt, had_remote: bool):
+    """Collective counterpart of ``_prepare_remote_reads``: the owners of the chunks that were read one-sidedly may not overwrite
+    or free them before EVERY reader's copy kernel has finished (freed blocks go straight back to the allocator cache).  The
+    reference's ``remotecall_fetch`` is synchronous for the same reason.  Stream sync + host barrier, as copy_transposed / mul!."""
+    if had_remote:
+        rt.sync()
         rt.barrier()
 
 
@@ -513,15 +529,15 @@ def broadcast_into(dest: DArray, f: Callable, *args) -> DArray:
                 raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"destination axes {dest.dims} are not compatible with source axes {tuple(shp)}")
     expr = trace(f, [_arg_tag(a) for a in args])
     rt = dest.rt
-    _prepare_remote_reads(dest.layout, rt, args)
+    remote = _prepare_remote_reads(dest.layout, rt, args)
     for pid, out in dest.chunks.items():
         I = dest.layout.localindices(pid)
         largs = [_localise(rt, a, I, pid) for a in args]
         run_local(rt, expr, out, largs)
         for la in largs:
             if la.temp and la.arr is not None:
-                rt.sync()
-                la.arr.free()
+                la.arr.free()                                  # stream-ordered: the block is only reused by later launches
+    _finish_remote_reads(rt, remote)
     return dest
 
 
@@ -534,15 +550,15 @@ def broadcast(f: Callable, *args, rt=None) -> DArray:
     expr = trace(f, [_arg_tag(a) for a in args])
     out_dt = _NPT[expr.jt]
     dest = darray(lambda I: B200Array.empty(rt, shape_of(I), out_dt), dims, dtype=out_dt, rt=rt)
-    _prepare_remote_reads(dest.layout, rt, args)
+    remote = _prepare_remote_reads(dest.layout, rt, args)
     for pid, out in dest.chunks.items():
         I = dest.layout.localindices(pid)
         largs = [_localise(rt, a, I, pid) for a in args]
         run_local(rt, expr, out, largs)
         for la in largs:
             if la.temp and la.arr is not None:
-                rt.sync()
-                la.arr.free()
+                la.arr.free()                                  # stream-ordered: the block is only reused by later launches
+    _finish_remote_reads(rt, remote)
     return dest
 
 
@@ -556,15 +572,15 @@ def map_inplace(f: Callable, dest: DArray, src: DArray) -> DArray:
     ``map!(f, localpart(dest), makelocal(src, localindices(dest)...))``."""
     expr = trace(f, [tag_of(src.dtype)])
     rt = dest.rt
-    _prepare_remote_reads(dest.layout, rt, [src])
+    remote = _prepare_remote_reads(dest.layout, rt, [src])
     for pid, out in dest.chunks.items():
         I = dest.layout.localindices(pid)
         arr = makelocal(src, I, pid)
         temp = arr is not src.chunks.get(pid)
         run_local(rt, expr, out, [LocalArg(arr, None, tag_of(src.dtype))])
         if temp:
-            rt.sync()
             arr.free()
+    _finish_remote_reads(rt, remote)
     return dest
 
 
@@ -594,13 +610,13 @@ def map_localparts(f: Callable, A, B=None) -> DArray:
     out_dt = _NPT[expr.jt]
     from ._darray import darray_like
     dest = darray_like(lambda I: B200Array.empty(rt, shape_of(I), out_dt), lead, dtype=out_dt)
-    _prepare_remote_reads(dest.layout, rt, args)
+    remote = _prepare_remote_reads(dest.layout, rt, args)
     for pid, out in dest.chunks.items():
         I = dest.layout.localindices(pid)
         largs = [_localise(rt, a, I, pid) for a in args]
         run_local(rt, expr, out, largs)
         for la in largs:
             if la.temp and la.arr is not None:
-                rt.sync()
-                la.arr.free()
+                la.arr.free()                                  # stream-ordered: the block is only reused by later launches
+    _finish_remote_reads(rt, remote)
     return dest

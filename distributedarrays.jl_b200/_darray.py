@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import itertools
+import weakref
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -24,7 +25,7 @@ from .layout import Layout, Range, default_procs, layout_from_chunk_shapes, make
 from .runtime import Runtime, runtime
 
 _DT = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64, np.dtype(np.int32): _lib.I32,
-       np.dtype(np.int64): _lib.I64, np.dtype(np.bool_): _lib.U8, np.dtype(np.uint8): _lib.U8}
+       np.dtype(np.int64): _lib.I64, np.dtype(np.bool_): _lib.U8}   # UInt8 is NOT Bool: unserved eltypes raise (no silent reinterpretation)
 _NP = {_lib.F32: np.dtype(np.float32), _lib.F64: np.dtype(np.float64), _lib.I32: np.dtype(np.int32),
        _lib.I64: np.dtype(np.int64), _lib.U8: np.dtype(np.bool_)}
 
@@ -149,7 +150,21 @@ def _next_did(rt: Runtime) -> Tuple[int, int]:
     return (1, _did[0])
 
 
-_REGISTRY: Dict[Tuple[int, int], "DArray"] = {}
+# id -> WeakRef(d), exactly like the reference's registry (src/core.jl:1-30, src/darray.jl:46-49): a DArray that becomes garbage
+# releases its localparts through its finalizer, so `x = A @ x` loops do not grow HBM; close(d) / d_closeall() release eagerly.
+_REGISTRY: Dict[Tuple[int, int], "weakref.ReferenceType[DArray]"] = {}
+
+
+def _release_chunks(chunks: Dict[int, "B200Array"], did):
+    """``release_localpart`` (src/core.jl:77-82).  Frees are ordered on the ctx stream; every op that let OTHER ranks read these
+    chunks ended with a collective fence (``_finish_remote_reads``), so nobody is still reading when a finalizer runs."""
+    for ch in list(chunks.values()):
+        try:
+            ch.free()
+        except Exception:  # interpreter shutdown / runtime already gone: the driver reclaims the memory
+            pass
+    chunks.clear()
+    _REGISTRY.pop(did, None)
 
 
 class DArray:
@@ -169,7 +184,8 @@ class DArray:
             if ch.shape != want:
                 raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"chunk of worker {pid} has shape {ch.shape}, layout says {want}")
         self._handles: Optional[Dict[int, bytes]] = None
-        _REGISTRY[self.id] = self
+        _REGISTRY[self.id] = weakref.ref(self)
+        self._fin = weakref.finalize(self, _release_chunks, chunks, self.id)   # finalizer(close, d)  (src/darray.jl:47-49)
 
     # ---- metadata (same names as the reference struct) ---------------------------------------------------------
     @property
@@ -206,10 +222,7 @@ class DArray:
 
     # ---- lifetime (src/core.jl:68-105) ----------------------------------------------------------------------------
     def close(self):
-        for ch in self.chunks.values():
-            ch.free()
-        self.chunks = {}
-        _REGISTRY.pop(self.id, None)
+        self._fin()                      # runs _release_chunks once (the chunks dict is emptied in place)
 
     # ---- peer handles for one-sided halo reads ------------------------------------------------------------------------
     def peer_ptr(self, pid: int) -> int:
@@ -602,10 +615,13 @@ def fill_(d: DArray, x) -> DArray:
 
 def d_closeall():
     """``d_closeall()`` (src/core.jl:97-105)."""
-    for d in list(_REGISTRY.values()):
-        d.close()
+    for ref in list(_REGISTRY.values()):
+        d = ref()
+        if d is not None:
+            d.close()
+    _REGISTRY.clear()
 
 
 def registry_size() -> int:
     """Leak check used by the tests (reference test/runtests.jl:28-37, test/darray.jl:1079-1086)."""
-    return len(_REGISTRY)
+    return sum(1 for ref in list(_REGISTRY.values()) if ref() is not None)

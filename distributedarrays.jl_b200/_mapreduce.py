@@ -161,7 +161,8 @@ def _mapreduce_expr(expr: Expr, opc: int, d: DArray, others: Sequence, return_pa
         opc_k = opc
     rdt = np.dtype(np.int64) if val_tag in ("bool", "i32", "i64") and opc in (_lib.SUM, _lib.PROD, _lib.ALL, _lib.ANY, _lib.COUNT) else NPT[val_tag]
     src = codegen(expr).encode()
-    _prepare_remote_reads(d.layout, rt, [a for a in others if isinstance(a, DArray)])
+    from ._broadcast import _finish_remote_reads
+    remote = _prepare_remote_reads(d.layout, rt, [a for a in others if isinstance(a, DArray)])
     temps = []
 
     def launch(pid, ch, slot_ptr):
@@ -185,6 +186,7 @@ def _mapreduce_expr(expr: Expr, opc: int, d: DArray, others: Sequence, return_pa
     finally:
         for t in temps:
             t.free()
+        _finish_remote_reads(rt, remote)
     res, vals = _fold(host, d.layout.pids, rdt, opc if opc != _lib.COUNT else _lib.SUM)
     return (res, vals) if return_partials else res
 

@@ -39,6 +39,7 @@ struct dab_ctx {
     void* sort_dev;         // radix-sort scratch: digit histograms + per-tile counts (dab_sort.cu)
     size_t sort_dev_bytes;
     void* sort_host;        // pinned: histograms read back by the host, split-point staging
+    long long opt_combine_timeout_ms;  // dab_set_option("combine_timeout_ms"): how long the fused combine waits for a peer (default 120 s)
     int opt_ew_tma;         // dab_set_option("ew_tma"): route aligned unary elementwise launches through the TMA-staged kernel
     char err[512];
 };
@@ -90,10 +91,16 @@ struct FusedComm {
     void* const* peers;        // device array of the nranks mailboxes
     void* host_out;            // pinned host slot: [0,8) folded result, [8,16) status (0 ok, 1 timed out)
     unsigned long long seq;
+    unsigned long long timeout_ns;   // wall-clock bound of the mailbox poll (%globaltimer), dab_set_option("combine_timeout_ms")
     int rank, nranks, op;
 };
 
 // ---- device helpers --------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long dab_globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 // 16-byte streaming load/store (evict-first: every element of the hot path is touched once).
 __device__ __forceinline__ int4 ld_stream(const int4* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(int4* p, int4 v) { __stcs(p, v); }

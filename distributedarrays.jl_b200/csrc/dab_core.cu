@@ -101,6 +101,7 @@ int32_t dab_init(int32_t device, dab_ctx** out) {
     ctx->rank = 0;
     ctx->nranks = 1;
     ctx->fuse_op = -1;
+    ctx->opt_combine_timeout_ms = 120000;
     ctx->cache = new (std::nothrow) dab_alloc_cache();
 #define INIT_CUDA(call)                                                     \
     do {                                                                    \
@@ -196,6 +197,11 @@ int32_t dab_set_option(dab_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return dab_fail(ctx, DAB_ERR_ARG, "null argument");
     if (strcmp(key, "ew_tma") == 0) {
         ctx->opt_ew_tma = value != 0;
+        return DAB_OK;
+    }
+    if (strcmp(key, "combine_timeout_ms") == 0) {
+        if (value < 1) return dab_fail(ctx, DAB_ERR_ARG, "combine_timeout_ms must be >= 1");
+        ctx->opt_combine_timeout_ms = value;
         return DAB_OK;
     }
     return dab_fail(ctx, DAB_ERR_ARG, "dab_set_option: unknown key %s", key);

@@ -164,9 +164,13 @@ __global__ void __launch_bounds__(RD_THREADS, 8) reduce_kernel(const T* __restri
         dst[2] = fc.seq;
         volatile unsigned long long* src =
             reinterpret_cast<volatile unsigned long long*>((char*)fc.peers[fc.rank] + bank + (size_t)threadIdx.x * DAB_MBOX_SLOT);
-        const long long t0 = clock64();
+        // SPMD ranks are not in lockstep (a first-time NVRTC compile, a large H2D copy or GC can hold one back for seconds), so the
+        // bound is generous wall-clock time (default 120 s, dab_set_option "combine_timeout_ms") and only exists so that a DEAD
+        // peer surfaces as an error instead of a hung GPU; a timeout leaves the communicator unusable, like a failed collective.
+        const unsigned long long t0 = dab_globaltimer_ns();
+        unsigned int spins = 0;
         while (src[2] != fc.seq) {
-            if (clock64() - t0 > 6000000000ll) {  // ~3 s at 1.9 GHz: a peer never called -> report instead of hanging the GPU
+            if ((++spins & 1023u) == 0 && dab_globaltimer_ns() - t0 > fc.timeout_ns) {
                 timed_out = 1;
                 break;
             }
@@ -216,6 +220,7 @@ int32_t launch_reduce(dab_ctx* ctx, const T* x, size_t n, Map map, void* out, in
         fc.peers = ctx->peer_mbox_dev;
         fc.host_out = ctx->host_slot;
         fc.seq = ++ctx->mbox_seq;
+        fc.timeout_ns = (unsigned long long)ctx->opt_combine_timeout_ms * 1000000ull;
         fc.rank = ctx->rank;
         fc.nranks = ctx->mbox_ranks;
         fc.op = ctx->fuse_op;

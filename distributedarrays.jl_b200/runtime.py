@@ -117,7 +117,7 @@ class Runtime:
         return int(p.value)
 
     def free(self, ptr: int):
-        if ptr:
+        if ptr and self.ctx:
             _lib.call("dab_free", self.ctx, C.c_void_p(ptr))
 
     def alloc_temp(self, nbytes: int) -> int:
@@ -127,7 +127,7 @@ class Runtime:
         return int(p.value)
 
     def free_temp(self, ptr: int):
-        if ptr:
+        if ptr and self.ctx:
             _lib.call("dab_free_async", self.ctx, C.c_void_p(ptr))
 
     def set_option(self, key: str, value: int):

@@ -113,7 +113,7 @@ int32_t dab_sync(dab_ctx* ctx);
 int32_t dab_device_info(dab_ctx* ctx, int32_t* device, int32_t* sm_count, size_t* free_bytes, size_t* total_bytes);
 /* the ctx's cudaStream_t (as void*), so a host runtime can order its own work after ours. */
 int32_t dab_stream(dab_ctx* ctx, void** stream);
-/* tuning switches; "ew_tma" = 1 routes aligned unary elementwise launches through the TMA-staged (cp.async.bulk + mbarrier
+/* tuning switches; "combine_timeout_ms" = wall-clock bound of the fused combine's wait for a peer; "ew_tma" = 1 routes aligned unary elementwise launches through the TMA-staged (cp.async.bulk + mbarrier
  * ring) kernel instead of the default flat LDG/STG kernel -- identical results, measured slower. */
 int32_t dab_set_option(dab_ctx* ctx, const char* key, int64_t value);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches claim). */
@@ -288,7 +288,7 @@ int32_t dab_mapreduce_all(dab_ctx* ctx, int32_t dtype, int32_t op, int32_t map, 
  * 64-byte CUDA IPC handle), exchanged the handles through the host runtime and attached them (handles = nranks * 64 bytes, in
  * rank order), dab_mapreduce_all runs as ONE kernel: the last CTA of the chunk reduction pushes the chunk result into every
  * peer's mailbox with peer stores, waits for the P results, folds them left to right in rank order and writes the scalar into
- * pinned host memory -- no NCCL call, no D2H copy.  A rank that never calls makes the others time out (~3 s) with DAB_ERR_NCCL
+ * pinned host memory -- no NCCL call, no D2H copy.  A rank that never calls makes the others time out (wall clock, default 120 s, dab_set_option "combine_timeout_ms") with DAB_ERR_NCCL
  * instead of hanging the GPU.  All ranks must call dab_mapreduce_all in the same order (as with any collective). */
 int32_t dab_mailbox_create(dab_ctx* ctx, void* handle64);
 int32_t dab_mailbox_attach(dab_ctx* ctx, const void* handles, int32_t rank, int32_t nranks);

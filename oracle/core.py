@@ -51,6 +51,8 @@ def lib():
                                       C.c_int, f32p, f64p]
         L.orc_workers_run.restype = C.c_double
         L.orc_num_procs.restype = C.c_int
+        L.orc_num_usable_procs.restype = C.c_int
+        L.orc_rand_stats_mt.argtypes = [C.c_uint64, C.c_uint64, C.c_size_t, C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -124,3 +126,16 @@ def workers_run(op: int, nworkers: int, n_per: int, seed: int, a: float, b: floa
 
 def num_procs() -> int:
     return int(lib().orc_num_procs())
+
+
+def num_usable_procs() -> int:
+    return int(lib().orc_num_usable_procs())
+
+
+def rand_stats(seed: int, start: int, n: int, a: float, b: float, yscale: int = 25, nthreads: int = 0) -> dict:
+    """Exact statistics of x = rand_u01(seed, start..start+n) and y = fl(fl(a*x)+b) (multi-threaded, integer accumulation):
+    ``ksum`` (sum x = ksum * 2^-24), ``ysum`` (sum y = ysum * 2^-yscale, valid when ``inexact == 0``), ``ymax``, ``xmax``."""
+    out = (C.c_uint64 * 5)()
+    lib().orc_rand_stats_mt(seed, start, n, a, b, yscale, nthreads or num_usable_procs(), out)
+    return {"ksum": int(out[0]), "ysum": int(out[1]), "yscale": yscale, "inexact": int(out[3]),
+            "ymax": np.array([out[2]], dtype=np.uint32).view(np.float32)[0], "xmax": np.array([out[4]], dtype=np.uint32).view(np.float32)[0]}

@@ -25,6 +25,7 @@
  * Parity status: float reduction ORDER is a model of Julia Base ("parity unpinned" at the bit
  * level; see oracle/darray_oracle.py header).  Everything else is exact.
  */
+#include <sched.h>
 #include <math.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -316,3 +317,91 @@ double orc_workers_run(int op, int nworkers, size_t n_per, uint64_t seed, float 
 }
 
 int orc_num_procs(void) { return (int)sysconf(_SC_NPROCESSORS_ONLN); }
+
+/* ---------------------------------------------------------------- exact statistics of the synthetic bench inputs (multi-threaded)
+ * The checker behind bench.py's in-run `parity` block: for x_i = (hash>>8) * 2^-24 (the generator above) and
+ * y_i = fl(fl(a*x_i) + b) (the broadcast y .= a .* x .+ b, two roundings) it returns, over [start, start+n):
+ *   out[0] = sum of k_i            (the exact sum of x is out[0] * 2^-24)
+ *   out[1] = sum of y_i * 2^yscale (exact integer when every y_i is a multiple of 2^-yscale; out[3] counts the ones that were not)
+ *   out[2] = bits of max(y) (Julia max), out[4] = bits of max(x)
+ * Pure integer / per-element IEEE arithmetic, so it is an exact ground truth, independent of any summation order. */
+typedef struct {
+    uint64_t seed, start;
+    size_t n;
+    float a, b;
+    int yscale;
+    uint64_t ksum, ysum, inexact;
+    float ymax, xmax;
+} stats_arg;
+
+static void* stats_main(void* p) {
+    stats_arg* g = (stats_arg*)p;
+    uint64_t ks = 0, ys = 0, bad = 0;
+    float ym = -INFINITY, xm = -INFINITY;
+    for (size_t i = 0; i < g->n; ++i) {
+        const uint32_t k = hash_u32(g->seed, g->start + i) >> 8;
+        const float x = (float)k * 0x1p-24f;
+        const float t = g->a * x;
+        const float y = t + g->b;
+        ks += k;
+        const double sc = ldexp((double)y, g->yscale);
+        const uint64_t q = (uint64_t)sc;
+        bad += ((double)q != sc);
+        ys += q;
+        ym = jl_max_f32(ym, y);
+        xm = jl_max_f32(xm, x);
+    }
+    g->ksum = ks;
+    g->ysum = ys;
+    g->inexact = bad;
+    g->ymax = ym;
+    g->xmax = xm;
+    return NULL;
+}
+
+void orc_rand_stats_mt(uint64_t seed, uint64_t start, size_t n, float a, float b, int yscale, int nthreads, uint64_t* out) {
+    if (nthreads < 1) nthreads = 1;
+    if ((size_t)nthreads > n) nthreads = n ? (int)n : 1;
+    pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
+    stats_arg* args = (stats_arg*)calloc((size_t)nthreads, sizeof(stats_arg));
+    const size_t per = n / (size_t)nthreads;
+    for (int t = 0; t < nthreads; ++t) {
+        const size_t lo = (size_t)t * per, hi = (t == nthreads - 1) ? n : lo + per;
+        stats_arg g = {seed, start + lo, hi - lo, a, b, yscale, 0, 0, 0, 0.0f, 0.0f};
+        args[t] = g;
+        pthread_create(&th[t], NULL, stats_main, &args[t]);
+    }
+    uint64_t ks = 0, ys = 0, bad = 0;
+    float ym = -INFINITY, xm = -INFINITY;
+    for (int t = 0; t < nthreads; ++t) {
+        pthread_join(th[t], NULL);
+        ks += args[t].ksum;
+        ys += args[t].ysum;
+        bad += args[t].inexact;
+        ym = jl_max_f32(ym, args[t].ymax);
+        xm = jl_max_f32(xm, args[t].xmax);
+    }
+    uint32_t yb, xb;
+    memcpy(&yb, &ym, 4);
+    memcpy(&xb, &xm, 4);
+    out[0] = ks;
+    out[1] = ys;
+    out[2] = yb;
+    out[3] = bad;
+    out[4] = xb;
+    free(th);
+    free(args);
+}
+
+/* usable CPUs of THIS process (cgroup/affinity aware), for sizing the checker's thread pool */
+int orc_num_usable_procs(void) {
+#ifdef __linux__
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+        int c = CPU_COUNT(&set);
+        if (c > 0) return c;
+    }
+#endif
+    return orc_num_procs();
+}

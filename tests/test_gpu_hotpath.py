@@ -625,3 +625,101 @@ def test_full_size_c2_affine_and_sum(dab, rt1):
     sy = float(dab.sum(y))
     assert abs(sy - (1.5 * float(s) + 0.25 * n)) <= 2e-6 * sy
     assert dab.maximum(y) <= a * F32(1) + b and dab.minimum(y) >= b
+
+
+@pytest.mark.parametrize("log2n", [30, 31])
+def test_full_size_reduce_exact_1e6(dab, rt1, log2n):
+    """The headline reduce_kernel (dab_reduce / dab_mapreduce_all, hand-written path) at the BASELINE sizes -- 2^30 (4 GiB chunk) and
+    2^31 (the north star's 8 GiB chunk) -- against the EXACT value at 1e-6 rel: the inputs are multiples of 2^-24 (x) / 2^-25 (y), so
+    the oracle's uint64 accumulation over every element is a rounding-free ground truth.  Also maximum bit-exact."""
+    n = 1 << log2n
+    if rt1.device_info()["free_bytes"] < (9 << 30) * (n >> 30):
+        pytest.skip("not enough free HBM")
+    x = dab.drand((n,), dtype=F32, seed=4321)
+    st = ocore.rand_stats(4321, 0, n, 1.5, 0.25)
+    sx = dab.sum(x)
+    exact_x = st["ksum"] * 2.0 ** -24
+    assert abs(float(sx) - exact_x) <= TOL * exact_x, (sx, exact_x)
+    assert dab.maximum(x) == st["xmax"]
+    y = dab.similar(x)
+    a, b = F32(1.5), F32(0.25)
+    dab.broadcast_into(y, lambda v: a * v + b, x)
+    assert st["inexact"] == 0
+    exact_y = st["ysum"] * 2.0 ** -25
+    sy = dab.sum(y)
+    assert abs(float(sy) - exact_y) <= TOL * exact_y, (sy, exact_y)
+    assert dab.maximum(y) == st["ymax"]
+    # the fp64 carrier of the chunk result is far tighter than the Float32 result
+    from darray_b200 import _lib
+    out = np.zeros(2, dtype=np.uint64)
+    ch = y.chunks[1]
+    _lib.call("dab_reduce_host", rt1.ctx, _lib.F32, _lib.SUM, _lib.MAP_ID, None, C.c_void_p(ch.ptr), n, C.c_void_p(out.ctypes.data))
+    assert abs(out.view(np.float64)[1] - exact_y) <= 1e-9 * exact_y
+    assert out.view(np.float32)[0] == sy
+    x.close()
+    y.close()
+
+
+# ---------------------------------------------------------------------------------------------- f1: fill! / copyto! / dfill / dzeros / dones
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64, np.bool_])
+def test_fill_copyto_dfill(dab, rt8, dtype):
+    """``fill!(A, x)`` (src/darray.jl:822-827), ``copyto!(dest::DArray, src::Array)`` (:679-687), ``dfill/dzeros/dones`` (:468-494)
+    on a multi-chunk, uneven layout; every result gathered and compared bit-exactly."""
+    dims = (37, 53)
+    v = np.asarray(3 if dtype != np.bool_ else True, dtype=dtype)
+    d = dab.dfill(v[()], dims, dtype=dtype)
+    assert d.dtype == np.dtype(dtype) and d.dims == dims
+    assert np.array_equal(dab.to_array(d), np.full(dims, v, dtype=dtype))
+    z, o = dab.dzeros(dims, dtype=dtype), dab.dones(dims, dtype=dtype)
+    assert np.array_equal(dab.to_array(z), np.zeros(dims, dtype)) and np.array_equal(dab.to_array(o), np.ones(dims, dtype))
+    rng = np.random.default_rng(5)
+    H = (rng.integers(-100, 100, dims) if dtype != np.bool_ else rng.integers(0, 2, dims)).astype(dtype)
+    r = dab.copyto(d, H)
+    assert r is d and same_bits(dab.to_array(d), H)
+    # non-contiguous host source (a transposed view) and a second layout
+    e = dab.dzeros(dims, dist=(4, 2), dtype=dtype)
+    Ht = np.ascontiguousarray(H.T).T
+    dab.copyto(e, Ht)
+    assert same_bits(dab.to_array(e), H)
+    with pytest.raises(dab.DimensionMismatch):
+        dab.copyto(e, H[:, :-1])
+    w = np.asarray(7 if dtype != np.bool_ else False, dtype=dtype)
+    assert dab.fill_(e, w[()]) is e
+    assert np.array_equal(dab.to_array(e), np.full(dims, w, dtype=dtype))
+    assert np.array_equal(dab.to_array(d), H)               # fill! of e did not touch d
+
+
+def test_copyto_pinned_large_and_pageable(dab, rt1):
+    """The e2e leg of bench.py: copyto!(x::DArray, host) from pinned and from pageable memory, 2^26 Float32, bit-exact."""
+    n = 1 << 26
+    x = dab.dzeros((n,), dtype=F32)
+    hp = dab.pinned_empty(rt1, (n,), F32)
+    hp[:] = orc.rand_u01(77, 0, n)
+    dab.copyto(x, hp)
+    assert np.array_equal(dab.to_array(x), hp)
+    pg = orc.rand_u01(78, 0, n)
+    dab.copyto(x, pg)
+    assert np.array_equal(dab.to_array(x), pg)
+    st = ocore.rand_stats(78, 0, n, 1.0, 0.0)
+    assert abs(float(dab.sum(x)) - st["ksum"] * 2.0 ** -24) <= TOL * st["ksum"] * 2.0 ** -24
+
+
+def test_finalizer_releases_hbm(dab, rt1):
+    """DArrays register a WeakRef + finalizer like the reference (src/darray.jl:46-49): dropping the last reference returns the
+    localparts, so an iterative ``x = f(x)`` loop does not grow HBM."""
+    import gc
+    gc.collect()
+    base = dab.registry_size()
+    x = dab.dones((1 << 20,), dtype=F32)
+    for _ in range(50):
+        x = dab.map_(lambda v: v + 1, x)                   # each iteration drops the previous array
+    gc.collect()
+    assert dab.registry_size() == base + 1
+    assert float(dab.sum(x)) == 51.0 * (1 << 20)
+    x.close()
+    assert dab.registry_size() == base
+
+
+def test_uint8_is_not_bool(dab, rt1):
+    with pytest.raises(dab.UnsupportedError):
+        dab.distribute(np.array([2, 3, 4], dtype=np.uint8))

@@ -88,7 +88,16 @@ def main():
     dB = dab.distribute(A, dist=(P, 1))
     dC = dab.distribute(A, dist=(1, P))
     Z = dab.broadcast(lambda u, v: u * v + 1, dB, dC)
+    # the sources are overwritten right after the op returns: the op's trailing fence guarantees that no other rank's one-sided
+    # copy kernel is still reading them (a missing fence shows up as NaNs in Z)
+    dab.fill_(dB, np.nan)
+    dab.fill_(dC, np.nan)
     assert np.array_equal(dab.to_array(Z), A * A + 1)
+    dD = dab.distribute(A, dist=(P, 1))
+    dE = dab.dzeros(A.shape, dist=(1, P), dtype=F32)
+    dab.map_inplace(lambda u: 2 * u, dE, dD)                    # map! across layouts, then clobber the source at once
+    dab.fill_(dD, np.nan)
+    assert np.array_equal(dab.to_array(dE), 2 * A)
     rt.barrier()
     log("ok: halo getindex / makelocal over peer memory")
 

@@ -38,7 +38,9 @@ struct dab_ctx {
     struct dab_alloc_cache* cache;  // size-bucketed reuse of small cudaMalloc blocks (dab_core.cu)
     void* sort_dev;         // radix-sort scratch: digit histograms + per-tile counts (dab_sort.cu)
     size_t sort_dev_bytes;
-    void* sort_host;        // pinned: histograms read back by the host, split-point staging
+    void* sort_host;        // pinned: split-point staging of dab_sorted_split
+    unsigned long long sort_epoch;  // one per digit pass ever launched: tags the look-back words so the scratch is never re-cleared
+    int opt_sort_variant;   // dab_set_option("sort_variant"): tile shape of the onesweep kernel (tuning sweeps)
     long long opt_combine_timeout_ms;  // dab_set_option("combine_timeout_ms"): how long the fused combine waits for a peer (default 120 s)
     int opt_ew_tma;         // dab_set_option("ew_tma"): route aligned unary elementwise launches through the TMA-staged kernel
     char err[512];

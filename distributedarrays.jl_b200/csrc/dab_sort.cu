@@ -4,18 +4,18 @@
 // Keys only, ascending in Julia's `isless` order: integers by value; floats with -0.0 < +0.0 and every NaN after +Inf (bit
 // patterns preserved; the reference keeps NaNs in their original relative order, here they are ordered by payload).
 //
-// Algorithm: least-significant-digit radix sort, 8-bit digits, hand-written for sm_100a.  HBM-bound integer work:
-//   sort_hist_kernel    one read of the keys -> the 256-bin histogram of EVERY digit position (global atomics on per-CTA shared
-//                       histograms).  The host reads it back (16 KiB) and drops the passes whose digit is constant -- Int64 data in a
-//                       small range needs 2-3 of 8 passes -- and derives each pass's bucket bases.
-//   per remaining pass:
-//   sort_count_kernel   per-tile digit counts                               (read n keys)
-//   sort_scan_kernel    exclusive scan of the counts along the tiles, one CTA per digit value
-//   sort_scatter_kernel stable multi-split of each tile and scatter          (read n keys, write n keys)
-//                       a warp owns a contiguous run of the tile; ballots group equal digits inside each 32-key step,
-//                       per-warp shared counters carry the running rank, so equal digits keep their input order (LSD needs it).
-// Algorithmic bytes: elem * (1 + 3 * passes) per key.  Tiles are 256 threads x 8 keys.
+// Algorithm: least-significant-digit radix sort, 8-bit digits, hand-written for sm_100a, "onesweep" structure.  HBM-bound integer work:
+//   sort_hist_kernel      one read of the keys -> the 256-bin histogram of EVERY digit position
+//   sort_plan_kernel      (1 CTA) bucket bases per digit, which passes run (a digit that is constant over the chunk is skipped: Int64 data
+//                         in a small range needs 2-3 of 8 passes), buffer ping-pong -- on the DEVICE: dab_sort never synchronises the stream
+//   sort_onesweep_kernel  per remaining pass: ONE sweep = read the keys once, rank them inside the tile (ballots + per-warp shared counters,
+//                         stable), resolve the tile's bucket offsets by decoupled look-back over the earlier tiles, reorder the tile by digit
+//                         in shared memory and write it out in runs
+// Algorithmic bytes: elem * (1 + 2 * passes) per key.
+#include <map>
+#include <mutex>
 #include <type_traits>
+#include <utility>
 
 #include "dab_common.cuh"
 
@@ -24,7 +24,6 @@ namespace {
 constexpr int ST_THREADS = 256;
 constexpr int ST_KPT = 8;                        // keys per thread (16 left the scatter at 111 registers = 2 CTAs per SM, latency-bound)
 constexpr int ST_TILE = ST_THREADS * ST_KPT;     // 2048 keys per CTA
-constexpr int ST_WARPS = ST_THREADS / 32;
 
 // ---- order-preserving bijection raw bits <-> unsigned key ----------------------------------------------------------------------
 template <typename T> struct SortKey;
@@ -63,19 +62,35 @@ template <> struct SortKey<double> {
     }
 };
 
-struct SortBases { uint32_t b[256]; };
-
 // Lanes of the warp whose 8-bit digit equals mine (dg = 256 marks "no key"; those lanes group together): 9 ballots.  On sm_100a
 // __match_any_sync costs one round per DISTINCT value in the warp (measured ~45 clk per warp-step on random digits); the bitwise
 // form is flat.
+template <int B>
+__device__ __forceinline__ unsigned int match_bit(unsigned int dg, unsigned int m) {
+    // 4 instructions per bit (LOP3 -> predicate, VOTE, SEL, LOP3); the C++ spelling compiles to 6
+    unsigned int bal, inv;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 t;\n\t"
+        "and.b32 t, %2, %3;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+        "selp.u32 %1, 0, 0xffffffff, p;\n\t}"
+        : "=r"(bal), "=r"(inv)
+        : "r"(dg), "n"(1u << B));
+    return m & (bal ^ inv);
+}
+template <int BITS>
 __device__ __forceinline__ unsigned int match_digit(unsigned int dg) {
     unsigned int m = 0xffffffffu;
-#pragma unroll
-    for (int b = 0; b < 9; ++b) {
-        const bool bit = (dg >> b) & 1u;
-        const unsigned int bal = __ballot_sync(0xffffffffu, bit);
-        m &= bit ? bal : ~bal;
-    }
+    m = match_bit<0>(dg, m);
+    m = match_bit<1>(dg, m);
+    m = match_bit<2>(dg, m);
+    m = match_bit<3>(dg, m);
+    m = match_bit<4>(dg, m);
+    m = match_bit<5>(dg, m);
+    m = match_bit<6>(dg, m);
+    m = match_bit<7>(dg, m);
+    if (BITS > 8) m = match_bit<8>(dg, m);
     return m;
 }
 
@@ -152,134 +167,263 @@ __global__ void __launch_bounds__(ST_THREADS) sort_hist_kernel(const typename So
     }
 }
 
-// ---- per-tile counts of one digit --------------------------------------------------------------------------------------------------
-template <typename T, bool RAW>
-__global__ void __launch_bounds__(ST_THREADS) sort_count_kernel(const typename SortKey<T>::U* __restrict__ in, size_t n, int shift,
-                                                                unsigned int nblocks, unsigned int* __restrict__ counts) {
-    using K = SortKey<T>;
-    using U = typename K::U;
-    __shared__ unsigned int sh[256];
-    sh[threadIdx.x] = 0;
+// ---- the device-side plan: which digit passes run, and from/to which buffer -----------------------------------------------------------
+// Everything the round-1 host code decided after reading the histograms back is decided here on the device, so dab_sort never
+// synchronises the stream: constant digits are skipped (Int64 keys in 0:10^6 need 3 of 8 passes), the buffers ping-pong so that the
+// LAST active pass writes `out`, an in-place sort with an odd number of passes stages its input in `tmp` first.
+enum { SEL_IN = 0, SEL_OUT = 1, SEL_TMP = 2 };
+struct SortPlan {
+    unsigned long long hist[8][256];   // all-digit histograms (sort_hist_kernel)
+    unsigned int base[8][256];         // exclusive scan of each histogram: first output slot of every bucket
+    unsigned int tile_ticket[8];       // per pass: the next tile to hand out (tiles are taken in address order)
+    int active[8], src_sel[8], dst_sel[8];
+    int raw_in[8], raw_out[8];         // first active pass reads raw keys, last one writes raw keys; in between the keys stay encoded
+    int n_active, precopy;             // precopy: in-place sort, odd pass count -> copy in to tmp before the first pass
+};
+
+template <int DIGITS>
+__global__ void __launch_bounds__(256) sort_plan_kernel(SortPlan* plan, unsigned long long n, int inplace) {
+    __shared__ unsigned long long wsum[8];
+    __shared__ int constant[8];
+    const int b = threadIdx.x, lane = b & 31, warp = b >> 5;
+    if (b < 8) constant[b] = 0;
     __syncthreads();
-    U key[ST_KPT];
-    const int cnt = load_blocked<U>(in, (size_t)blockIdx.x * ST_TILE + (size_t)threadIdx.x * ST_KPT, n, key);
-    if (cnt > 0) {
-        unsigned int cur = (unsigned)((RAW ? K::enc(key[0]) : key[0]) >> shift) & 255u, run = 1;
+    for (int d = 0; d < DIGITS; ++d) {
+        const unsigned long long h = plan->hist[d][b];
+        if (h == n) constant[d] = 1;
+        unsigned long long inc = h;
 #pragma unroll
-        for (int k = 1; k < ST_KPT; ++k)
-            if (k < cnt) {
-                const unsigned int dg = (unsigned)((RAW ? K::enc(key[k]) : key[k]) >> shift) & 255u;
-                if (dg == cur) {
-                    ++run;
-                } else {
-                    atomicAdd(&sh[cur], run);
-                    cur = dg;
-                    run = 1;
-                }
-            }
-        atomicAdd(&sh[cur], run);
+        for (int s = 1; s < 32; s <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, s);
+            if (lane >= s) inc += t;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        unsigned long long carry = 0;
+        for (int w = 0; w < warp; ++w) carry += wsum[w];
+        plan->base[d][b] = (unsigned int)(carry + inc - h);
+        __syncthreads();
     }
-    __syncthreads();
-    counts[(size_t)threadIdx.x * nblocks + blockIdx.x] = sh[threadIdx.x];   // digit-major: row d holds the tiles' counts of digit d
+    if (b == 0) {
+        int na = 0;
+        for (int d = 0; d < DIGITS; ++d) na += !constant[d];
+        int q = 0, prev = SEL_IN, pre = 0;
+        for (int d = 0; d < 8; ++d) {
+            plan->tile_ticket[d] = 0;
+            const int act = d < DIGITS && !constant[d];
+            plan->active[d] = act;
+            if (!act) continue;
+            const int dst = ((na - 1 - q) % 2 == 0) ? SEL_OUT : SEL_TMP;
+            int src = prev;
+            if (q == 0 && inplace && dst == SEL_OUT) {   // in == out and the first pass would overwrite its own input
+                pre = 1;
+                src = SEL_TMP;
+            }
+            plan->src_sel[d] = src;
+            plan->dst_sel[d] = dst;
+            plan->raw_in[d] = q == 0;
+            plan->raw_out[d] = q == na - 1;
+            prev = dst;
+            ++q;
+        }
+        plan->n_active = na;
+        plan->precopy = pre;
+    }
 }
 
-// ---- exclusive scan of each digit's row over the tiles (one CTA per digit value) -----------------------------------------------------
-__global__ void __launch_bounds__(1024) sort_scan_kernel(unsigned int* __restrict__ counts, unsigned int nblocks) {
-    __shared__ unsigned int wsum[32];
-    __shared__ unsigned int carry_s;
-    unsigned int* row = counts + (size_t)blockIdx.x * nblocks;
+// mode 0: copy in -> tmp when the plan asks for the staging copy; mode 1: copy in -> out when NO pass runs (all keys equal)
+template <typename U>
+__global__ void __launch_bounds__(256) sort_copy_if_kernel(const SortPlan* __restrict__ plan, const U* __restrict__ src, U* __restrict__ dst,
+                                                           size_t n, int mode) {
+    if (mode == 0 ? !plan->precopy : plan->n_active != 0) return;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) dst[i] = src[i];
+}
+
+// ---- one digit pass, "onesweep": count + look-back + stable scatter in ONE sweep over the keys ------------------------------------------
+// Per pass each key is read once and written once (round 1: read twice, written once, plus a scan launch).  A persistent CTA takes tiles
+// by ticket (address order, so the look-back below always waits on a tile that is already running):
+//   1. all KPT loads of a thread are issued before any use (full tiles: unpredicated, so ptxas does not sink them into the ranking loop)
+//   2. ranking: warp w owns a contiguous run; equal digits inside a 32-key step are grouped by ballots, a per-warp shared counter row
+//      carries the running rank -> stable
+//   3. thread d publishes the tile's count of digit d (PARTIAL), then walks back over the predecessors' words until it meets an INCLUSIVE
+//      one: decoupled look-back, one 64-bit word = flag | epoch | count, so no fence is needed and the scratch is never cleared (a word of
+//      an older pass carries an older epoch and reads as "not ready")
+//   4. the tile is reordered by digit in shared memory, then written out: consecutive threads -> consecutive addresses inside each
+//      bucket run (full 32-byte sectors instead of one sector request per key)
+constexpr unsigned long long LB_PARTIAL = 1ull << 62, LB_INCLUSIVE = 2ull << 62, LB_FLAGS = 3ull << 62;
+constexpr unsigned long long LB_EPOCH_MASK = ((1ull << 30) - 1ull) << 32;
+constexpr int LB_WINDOW = 4;   // predecessor words fetched per look-back round (independent L2 reads in flight instead of a serial walk)
+
+struct OsShared {              // carved out of dynamic shared memory
+    unsigned int (*wc)[256];   // [WARPS][256] per-warp digit counters -> per-warp start offsets inside the sorted tile
+    unsigned int* dbase;       // [256] digit -> (first output slot of this tile's run) - (start of the digit inside the tile)
+    unsigned int* wtot;        // [8]
+};
+
+template <typename T, int THREADS, int KPT, bool FULL, bool MATCH>
+__device__ __forceinline__ void onesweep_tile(const typename SortKey<T>::U* __restrict__ src, typename SortKey<T>::U* __restrict__ dst,
+                                              typename SortKey<T>::U* __restrict__ skeys, const OsShared& sh, size_t n, unsigned int tile,
+                                              int shift, bool raw_in, bool raw_out, const unsigned int* __restrict__ gbase,
+                                              unsigned long long* __restrict__ lookback, unsigned long long ep) {
+    using K = SortKey<T>;
+    using U = typename K::U;
+    constexpr int WARPS = THREADS / 32;
+    constexpr int TILE = THREADS * KPT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
+    const unsigned int lt = (1u << lane) - 1u;
+    const size_t tbase = (size_t)tile * TILE;
+    const size_t wbase = tbase + (size_t)warp * (KPT * 32);
+    const unsigned int nvalid = FULL ? (unsigned)TILE : (unsigned)(n - tbase);
+    unsigned int (*wc)[256] = sh.wc;
+    U key[KPT];
+    unsigned short rank[KPT];
+    // all loads of the thread in flight before the first use (full tiles: unpredicated, so ptxas keeps them together)
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+        const size_t i = wbase + (size_t)k * 32 + lane;
+        key[k] = (FULL || i < n) ? __ldcs(src + i) : U(0);
+    }
+    const unsigned int wc_row = (unsigned int)__cvta_generic_to_shared(&wc[warp][0]);
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+        const bool valid = FULL || (wbase + (size_t)k * 32 + lane < n);
+        if (raw_in) key[k] = K::enc(key[k]);
+        const unsigned int dg = valid ? ((unsigned)(key[k] >> shift) & 255u) : 256u;   // missing keys form their own group
+        const unsigned int grp = MATCH ? __match_any_sync(0xffffffffu, dg) : match_digit<FULL ? 8 : 9>(dg);
+        const unsigned int before = __popc(grp & lt);
+        const int leader = __ffs(grp) - 1;
+        // the group's lowest lane bumps the warp's counter of this digit once and hands the old value round (predicated ATOMS, no
+        // divergent branch); steps are issued in order by the one warp that owns this counter row -> equal digits keep their order
+        unsigned int old = 0;
+        const unsigned int gsize = __popc(grp);
+        const unsigned int doit = (valid && before == 0) ? 1u : 0u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.u32 p, %3, 0;\n\t"
+            "@p atom.shared.add.u32 %0, [%1], %2;\n\t}"
+            : "+r"(old)
+            : "r"(wc_row + dg * 4u), "r"(gsize), "r"(doit)
+            : "memory");
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[k] = (unsigned short)(old + before);
+    }
     __syncthreads();
-    for (unsigned int base = 0; base < nblocks; base += 1024) {
-        const unsigned int i = base + threadIdx.x;
-        const unsigned int v = i < nblocks ? row[i] : 0;
-        unsigned int inc = v;
+    unsigned int cnt = 0, tstart = 0;
+    unsigned long long* myword = nullptr;
+    if (threadIdx.x < 256) {
+        const int dd = threadIdx.x;
+        // running prefix of digit dd over the warps; the tile's count goes out at once so that successors can make progress
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const unsigned int c = wc[w][dd];
+            wc[w][dd] = cnt;
+            cnt += c;
+        }
+        myword = lookback + (size_t)tile * 256 + dd;
+        *(volatile unsigned long long*)myword = (tile == 0 ? LB_INCLUSIVE : LB_PARTIAL) | ep | (unsigned long long)cnt;
+        // exclusive scan of the 256 digit counts -> where digit dd starts inside the sorted tile
+        unsigned int inc = cnt;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) {
             const unsigned int t = __shfl_up_sync(0xffffffffu, inc, s);
             if (lane >= s) inc += t;
         }
-        if (lane == 31) wsum[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned int w = wsum[lane];
+        if (lane == 31) sh.wtot[warp] = inc;
+        tstart = inc - cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+        for (int w = 0; w < warp; ++w) tstart += sh.wtot[w];
+        const int dd = threadIdx.x;
 #pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                const unsigned int t = __shfl_up_sync(0xffffffffu, w, s);
-                if (lane >= s) w += t;
-            }
-            wsum[lane] = w;  // inclusive over warps
+        for (int w = 0; w < WARPS; ++w) wc[w][dd] += tstart;
+    }
+    __syncthreads();
+    // the tile, sorted by this digit, in shared memory
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+        if (FULL || (wbase + (size_t)k * 32 + lane < n)) {
+            const unsigned int dg = (unsigned)(key[k] >> shift) & 255u;
+            skeys[wc[warp][dg] + rank[k]] = key[k];
         }
-        __syncthreads();
-        const unsigned int carry = carry_s;
-        const unsigned int excl = carry + (warp ? wsum[warp - 1] : 0) + inc - v;
-        if (i < nblocks) row[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = carry + wsum[31];
-        __syncthreads();
+    }
+    if (threadIdx.x < 256) {
+        const int dd = threadIdx.x;
+        unsigned int excl = 0;
+        if (tile > 0) {
+            long long t = (long long)tile - 1;   // next predecessor to consume
+            bool done = false;
+            while (!done) {
+                unsigned long long v[LB_WINDOW];
+#pragma unroll
+                for (int j = 0; j < LB_WINDOW; ++j)
+                    v[j] = (t - j >= 0) ? *(const volatile unsigned long long*)(lookback + (size_t)(t - j) * 256 + dd) : LB_INCLUSIVE | ep;
+#pragma unroll
+                for (int j = 0; j < LB_WINDOW; ++j) {
+                    if (done) break;
+                    if ((v[j] & LB_FLAGS) == 0 || (v[j] & LB_EPOCH_MASK) != ep) break;   // not published yet: fetch again from here
+                    excl += (unsigned int)v[j];
+                    --t;
+                    if (v[j] & LB_INCLUSIVE) done = true;
+                }
+            }
+            *(volatile unsigned long long*)myword = LB_INCLUSIVE | ep | (unsigned long long)(excl + cnt);
+        }
+        sh.dbase[dd] = gbase[dd] + excl - tstart;
+    }
+    __syncthreads();
+    if (FULL) {
+#pragma unroll
+        for (int k = 0; k < KPT; ++k) {
+            const unsigned int i = (unsigned)k * THREADS + threadIdx.x;
+            const U kk = skeys[i];
+            const unsigned int dg = (unsigned)(kk >> shift) & 255u;
+            dst[sh.dbase[dg] + i] = raw_out ? K::dec(kk) : kk;
+        }
+    } else {
+        for (unsigned int i = threadIdx.x; i < nvalid; i += THREADS) {
+            const U kk = skeys[i];
+            const unsigned int dg = (unsigned)(kk >> shift) & 255u;
+            dst[sh.dbase[dg] + i] = raw_out ? K::dec(kk) : kk;
+        }
     }
 }
 
-// ---- stable scatter of one digit -------------------------------------------------------------------------------------------------------
-template <typename T, bool RAW_IN, bool RAW_OUT>
-__global__ void __launch_bounds__(ST_THREADS, 4) sort_scatter_kernel(const typename SortKey<T>::U* __restrict__ in,
-                                                                  typename SortKey<T>::U* __restrict__ out, size_t n, int shift,
-                                                                  unsigned int nblocks, const unsigned int* __restrict__ offsets,
-                                                                  SortBases bases) {
+template <typename T, int THREADS, int KPT, int MINB, bool MATCH>
+__global__ void __launch_bounds__(THREADS, MINB) sort_onesweep_kernel(const typename SortKey<T>::U* __restrict__ in, typename SortKey<T>::U* __restrict__ out,
+                                                                      typename SortKey<T>::U* __restrict__ tmp, size_t n, int d, SortPlan* __restrict__ plan,
+                                                                      unsigned long long* __restrict__ lookback, unsigned int ntiles,
+                                                                      unsigned long long epoch) {
     using K = SortKey<T>;
     using U = typename K::U;
-    __shared__ unsigned int wc[ST_WARPS][256];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < ST_WARPS * 256; i += ST_THREADS) (&wc[0][0])[i] = 0;
-    __syncthreads();
-    // warp `warp` owns keys [base + warp*KPT*32, +KPT*32) of the tile; step k takes 32 consecutive keys
-    const size_t wbase = (size_t)blockIdx.x * ST_TILE + (size_t)warp * (ST_KPT * 32);
-    const unsigned int lt = (1u << lane) - 1u;
-    U key[ST_KPT];
-    unsigned short rank[ST_KPT];
-#pragma unroll
-    for (int k = 0; k < ST_KPT; ++k) {
-        const size_t i = wbase + (size_t)k * 32 + lane;
-        key[k] = i < n ? __ldcs(in + i) : U(0);
-    }
-    // Running per-warp digit counters.  Equal digits inside a 32-key step are grouped by ballots; the group's lowest lane bumps the
-    // counter once and hands the old value round.  Steps are issued in order by the one warp that owns this counter row, so equal
-    // digits keep their input order.
-#pragma unroll
-    for (int k = 0; k < ST_KPT; ++k) {
-        const size_t i = wbase + (size_t)k * 32 + lane;
-        const bool valid = i < n;
-        if (RAW_IN) key[k] = K::enc(key[k]);
-        const unsigned int dg = valid ? ((unsigned)(key[k] >> shift) & 255u) : 256u;   // invalid lanes form their own group
-        const unsigned int grp = match_digit(dg);
-        const unsigned int before = __popc(grp & lt);
-        const int leader = __ffs(grp) - 1;
-        unsigned int old = 0;
-        if (valid && before == 0) old = atomicAdd(&wc[warp][dg], (unsigned int)__popc(grp));
-        old = __shfl_sync(0xffffffffu, old, leader);
-        rank[k] = (unsigned short)(old + before);
-    }
-    __syncthreads();
-    {   // digit d: global base of the bucket + this tile's offset inside it, then running prefix over the warps
-        const int d = threadIdx.x;
-        unsigned int run = bases.b[d] + offsets[(size_t)d * nblocks + blockIdx.x];
-#pragma unroll
-        for (int w = 0; w < ST_WARPS; ++w) {
-            const unsigned int c = wc[w][d];
-            wc[w][d] = run;
-            run += c;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < ST_KPT; ++k) {
-        const size_t i = wbase + (size_t)k * 32 + lane;
-        if (i < n) {
-            const unsigned int dg = (unsigned)(key[k] >> shift) & 255u;
-            const unsigned int pos = wc[warp][dg] + rank[k];
-            out[pos] = RAW_OUT ? K::dec(key[k]) : key[k];
-        }
+    constexpr int WARPS = THREADS / 32;
+    constexpr int TILE = THREADS * KPT;
+    static_assert(THREADS >= 256 && THREADS % 32 == 0, "thread d serves digit d");
+    if (!plan->active[d]) return;
+    extern __shared__ __align__(16) unsigned char os_smem[];
+    U* skeys = reinterpret_cast<U*>(os_smem);                                                   // [TILE]
+    OsShared sh;
+    sh.wc = reinterpret_cast<unsigned int (*)[256]>(os_smem + (size_t)TILE * sizeof(U));
+    sh.dbase = &sh.wc[WARPS][0];
+    sh.wtot = sh.dbase + 256;
+    __shared__ unsigned int s_tile;
+    const int ssel = plan->src_sel[d], dsel = plan->dst_sel[d];
+    const U* __restrict__ src = ssel == SEL_IN ? in : (ssel == SEL_OUT ? out : tmp);
+    U* __restrict__ dst = dsel == SEL_OUT ? out : tmp;
+    const bool raw_in = plan->raw_in[d] != 0, raw_out = plan->raw_out[d] != 0;   // buffers between passes hold ENCODED keys
+    const unsigned int* gbase = plan->base[d];
+    const int shift = 8 * d;
+    const unsigned long long ep = (epoch << 32) & LB_EPOCH_MASK;
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(&plan->tile_ticket[d], 1u);
+        for (int i = threadIdx.x; i < WARPS * 256; i += THREADS) (&sh.wc[0][0])[i] = 0;
+        __syncthreads();
+        const unsigned int tile = s_tile;
+        if (tile >= ntiles) return;
+        if ((size_t)(tile + 1) * TILE <= n) onesweep_tile<T, THREADS, KPT, true, MATCH>(src, dst, skeys, sh, n, tile, shift, raw_in, raw_out, gbase, lookback, ep);
+        else onesweep_tile<T, THREADS, KPT, false, MATCH>(src, dst, skeys, sh, n, tile, shift, raw_in, raw_out, gbase, lookback, ep);
+        // the next iteration's zeroing of wc / reuse of skeys must wait for every reader of this tile
+        __syncthreads();
     }
 }
 
@@ -313,7 +457,73 @@ int32_t sort_scratch(dab_ctx* ctx, size_t dev_bytes) {
             ctx->sort_dev_bytes = 0;
         }
         DAB_CUDA(ctx, cudaMalloc(&ctx->sort_dev, dev_bytes));
+        // the look-back words carry an epoch, so the scratch is cleared ONCE, here (epoch 0 is never used by a pass)
+        DAB_CUDA(ctx, cudaMemsetAsync(ctx->sort_dev, 0, dev_bytes, ctx->stream));
         ctx->sort_dev_bytes = dev_bytes;
+    }
+    return DAB_OK;
+}
+
+constexpr size_t SORT_PLAN_BYTES = 65536;   // SortPlan + the staging areas of dab_sorted_split, ahead of the look-back words
+static_assert(sizeof(SortPlan) + 8192 <= SORT_PLAN_BYTES, "plan area");
+
+template <typename T, int THREADS, int KPT, int MINB, bool MATCH>
+int32_t sort_passes(dab_ctx* ctx, const typename SortKey<T>::U* in, typename SortKey<T>::U* out, typename SortKey<T>::U* tmp, size_t n) {
+    using K = SortKey<T>;
+    using U = typename K::U;
+    constexpr int TILE = THREADS * KPT;
+    const unsigned int ntiles = (unsigned int)((n + TILE - 1) / TILE);
+    {
+        int32_t st = sort_scratch(ctx, SORT_PLAN_BYTES + (size_t)ntiles * 256 * sizeof(unsigned long long));
+        if (st != DAB_OK) return st;
+    }
+    SortPlan* plan = (SortPlan*)ctx->sort_dev;
+    unsigned long long* lookback = (unsigned long long*)((char*)ctx->sort_dev + SORT_PLAN_BYTES);
+    DAB_CUDA(ctx, cudaMemsetAsync(plan->hist, 0, sizeof(plan->hist), ctx->stream));
+    {
+        const unsigned int htiles = (unsigned int)((n + ST_TILE - 1) / ST_TILE);
+        const unsigned int hgrid = htiles < (unsigned)ctx->sm_count * 4u ? htiles : (unsigned)ctx->sm_count * 4u;
+        sort_hist_kernel<T><<<hgrid, ST_THREADS, 0, ctx->stream>>>(in, n, &plan->hist[0][0]);
+        DAB_LAUNCHED(ctx);
+    }
+    const int inplace = (const void*)in == (const void*)out;
+    sort_plan_kernel<K::DIGITS><<<1, 256, 0, ctx->stream>>>(plan, (unsigned long long)n, inplace);
+    DAB_LAUNCHED(ctx);
+    const int cgrid = dab_grid_for(ctx, (n + 1023) / 1024, 8);
+    if (inplace) {
+        sort_copy_if_kernel<U><<<cgrid, 256, 0, ctx->stream>>>(plan, in, tmp, n, 0);
+        DAB_LAUNCHED(ctx);
+    } else {
+        sort_copy_if_kernel<U><<<cgrid, 256, 0, ctx->stream>>>(plan, in, out, n, 1);   // acts only when every key is equal
+        DAB_LAUNCHED(ctx);
+    }
+    auto kern = sort_onesweep_kernel<T, THREADS, KPT, MINB, MATCH>;
+    constexpr size_t smem = (size_t)TILE * sizeof(U) + (size_t)(THREADS / 32) * 1024 + 1024 + 32;
+    int per_sm = 0;
+    {   // >48 KiB of dynamic shared memory is an opt-in attribute of the (kernel, device) pair; the occupancy query needs it set
+        static std::mutex mu;
+        static std::map<std::pair<const void*, int>, int> seen;
+        std::lock_guard<std::mutex> lk(mu);
+        auto key = std::make_pair((const void*)kern, ctx->device);
+        auto it = seen.find(key);
+        if (it == seen.end()) {
+            DAB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int nb = 0;
+            DAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, THREADS, smem));
+            it = seen.emplace(key, nb < 1 ? 1 : nb).first;
+        }
+        per_sm = it->second;
+    }
+    const int grid = dab_grid_for(ctx, ntiles, per_sm);
+    for (int d = 0; d < K::DIGITS; ++d) {
+        const unsigned long long epoch = (++ctx->sort_epoch) & ((1ull << 30) - 1ull);
+        if (epoch == 0) {   // wrapped (2^30 passes): start a new era with clean words
+            DAB_CUDA(ctx, cudaMemsetAsync(lookback, 0, ctx->sort_dev_bytes - SORT_PLAN_BYTES, ctx->stream));
+            --d;
+            continue;
+        }
+        kern<<<grid, THREADS, smem, ctx->stream>>>(in, out, tmp, n, d, plan, lookback, ntiles, epoch);
+        DAB_LAUNCHED(ctx);
     }
     return DAB_OK;
 }
@@ -339,66 +549,24 @@ int32_t sort_t(dab_ctx* ctx, const void* in_v, void* out_v, void* tmp_v, size_t 
     }
     DAB_REQUIRE(ctx, tmp != nullptr && tmp != out && tmp != in, DAB_ERR_ARG, "dab_sort: tmp must be a distinct buffer of n elements");
     DAB_REQUIRE(ctx, n < 0xFFFFF000ull, DAB_ERR_UNSUPPORTED, "dab_sort: chunks of 2^32 or more elements are not served");
-    const unsigned int nblocks = (unsigned int)((n + ST_TILE - 1) / ST_TILE);
-    const size_t hist_bytes = (size_t)K::DIGITS * 256 * sizeof(unsigned long long);
-    const size_t counts_bytes = (size_t)256 * nblocks * sizeof(unsigned int);
-    {
-        int32_t st = sort_scratch(ctx, 16384 + counts_bytes);
-        if (st != DAB_OK) return st;
-    }
-    unsigned long long* ghist = (unsigned long long*)ctx->sort_dev;
-    unsigned int* counts = (unsigned int*)((char*)ctx->sort_dev + 16384);
-    unsigned long long* hhist = (unsigned long long*)ctx->sort_host;
-    DAB_CUDA(ctx, cudaMemsetAsync(ghist, 0, hist_bytes, ctx->stream));
-    {
-        const unsigned int hgrid = nblocks < (unsigned)ctx->sm_count * 4u ? nblocks : (unsigned)ctx->sm_count * 4u;
-        sort_hist_kernel<T><<<hgrid, ST_THREADS, 0, ctx->stream>>>(in, n, ghist);
-    }
-    DAB_LAUNCHED(ctx);
-    DAB_CUDA(ctx, cudaMemcpyAsync(hhist, ghist, hist_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    DAB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    int active[8], na = 0;
-    for (int d = 0; d < K::DIGITS; ++d) {
-        bool constant = false;
-        for (int b = 0; b < 256; ++b)
-            if (hhist[d * 256 + b] == n) constant = true;
-        if (!constant) active[na++] = d;
-    }
-    if (na == 0) {  // every key equal
-        if (in != out) DAB_CUDA(ctx, cudaMemcpyAsync(out, in, n * sizeof(U), cudaMemcpyDeviceToDevice, ctx->stream));
-        return DAB_OK;
-    }
-    // ping-pong so that the LAST pass writes `out`; `in` is never written unless it is `out`
-    const U* src = in;
-    for (int p = 0; p < na; ++p) {
-        const int d = active[p];
-        const bool first = (p == 0), last = (p == na - 1);
-        U* dst = ((na - 1 - p) % 2 == 0) ? out : tmp;
-        if (dst == (U*)src) {
-            // only possible on the first pass of an in-place sort with an odd number of passes: stage the input in tmp
-            DAB_CUDA(ctx, cudaMemcpyAsync(tmp, src, n * sizeof(U), cudaMemcpyDeviceToDevice, ctx->stream));
-            src = tmp;
+    // tile shape: 32 KiB of keys per CTA in shared memory -> ~128-byte bucket runs per tile on random digits
+    if constexpr (sizeof(U) == 8) {
+        switch (ctx->opt_sort_variant) {
+            case 1: return sort_passes<T, 256, 16, 4, false>(ctx, in, out, tmp, n);
+            case 2: return sort_passes<T, 256, 16, 3, true>(ctx, in, out, tmp, n);
+            case 3: return sort_passes<T, 512, 8, 2, false>(ctx, in, out, tmp, n);
+            case 4: return sort_passes<T, 256, 12, 4, false>(ctx, in, out, tmp, n);
+            default: return sort_passes<T, 256, 16, 3, false>(ctx, in, out, tmp, n);
         }
-        SortBases bases;
-        unsigned long long run = 0;
-        for (int b = 0; b < 256; ++b) {
-            bases.b[b] = (uint32_t)run;
-            run += hhist[d * 256 + b];
+    } else {
+        switch (ctx->opt_sort_variant) {
+            case 1: return sort_passes<T, 256, 32, 3, false>(ctx, in, out, tmp, n);
+            case 2: return sort_passes<T, 256, 32, 2, true>(ctx, in, out, tmp, n);
+            case 3: return sort_passes<T, 512, 16, 2, false>(ctx, in, out, tmp, n);
+            case 4: return sort_passes<T, 256, 24, 3, false>(ctx, in, out, tmp, n);
+            default: return sort_passes<T, 256, 32, 2, false>(ctx, in, out, tmp, n);
         }
-        const int shift = 8 * d;
-        if (first) sort_count_kernel<T, true><<<nblocks, ST_THREADS, 0, ctx->stream>>>(src, n, shift, nblocks, counts);
-        else sort_count_kernel<T, false><<<nblocks, ST_THREADS, 0, ctx->stream>>>(src, n, shift, nblocks, counts);
-        DAB_LAUNCHED(ctx);
-        sort_scan_kernel<<<256, 1024, 0, ctx->stream>>>(counts, nblocks);
-        DAB_LAUNCHED(ctx);
-        if (first && last) sort_scatter_kernel<T, true, true><<<nblocks, ST_THREADS, 0, ctx->stream>>>(src, dst, n, shift, nblocks, counts, bases);
-        else if (first) sort_scatter_kernel<T, true, false><<<nblocks, ST_THREADS, 0, ctx->stream>>>(src, dst, n, shift, nblocks, counts, bases);
-        else if (last) sort_scatter_kernel<T, false, true><<<nblocks, ST_THREADS, 0, ctx->stream>>>(src, dst, n, shift, nblocks, counts, bases);
-        else sort_scatter_kernel<T, false, false><<<nblocks, ST_THREADS, 0, ctx->stream>>>(src, dst, n, shift, nblocks, counts, bases);
-        DAB_LAUNCHED(ctx);
-        src = dst;
     }
-    return DAB_OK;
 }
 
 // ---- split points in a sorted chunk ----------------------------------------------------------------------------------------------------
@@ -449,10 +617,10 @@ template <typename T>
 int32_t bounds_t(dab_ctx* ctx, const void* sorted, size_t n, const void* bounds_host, int nb, unsigned long long* counts_host) {
     using U = typename SortKey<T>::U;
     DAB_REQUIRE(ctx, nb >= 1 && nb <= 256, DAB_ERR_ARG, "dab_sorted_split: 1..256 bounds");
-    int32_t st = sort_scratch(ctx, 16384);
+    int32_t st = sort_scratch(ctx, SORT_PLAN_BYTES);
     if (st != DAB_OK) return st;
-    U* dbounds = (U*)ctx->sort_dev;                                             // [0, 2 KiB)
-    unsigned long long* dcounts = (unsigned long long*)((char*)ctx->sort_dev + 4096);
+    U* dbounds = (U*)((char*)ctx->sort_dev + SORT_PLAN_BYTES - 8192);           // staging behind the SortPlan
+    unsigned long long* dcounts = (unsigned long long*)((char*)ctx->sort_dev + SORT_PLAN_BYTES - 4096);
     unsigned long long* hc = (unsigned long long*)((char*)ctx->sort_host + 8 * 256 * sizeof(unsigned long long));
     DAB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));                         // the staging areas may still be in use by a sort
     memcpy(hc, bounds_host, (size_t)nb * sizeof(U));

@@ -199,6 +199,14 @@ int32_t dab_set_option(dab_ctx* ctx, const char* key, int64_t value) {
         ctx->opt_ew_tma = value != 0;
         return DAB_OK;
     }
+    if (strcmp(key, "gemm_kc") == 0) {
+        ctx->opt_gemm_kc = value;
+        return DAB_OK;
+    }
+    if (strcmp(key, "gemm_simt") == 0) {
+        ctx->opt_gemm_simt = value != 0;
+        return DAB_OK;
+    }
     if (strcmp(key, "sort_variant") == 0) {
         ctx->opt_sort_variant = (int)value;
         return DAB_OK;

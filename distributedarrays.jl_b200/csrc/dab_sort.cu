@@ -252,48 +252,26 @@ __global__ void __launch_bounds__(256) sort_copy_if_kernel(const SortPlan* __res
 //      bucket run (full 32-byte sectors instead of one sector request per key)
 constexpr unsigned long long LB_PARTIAL = 1ull << 62, LB_INCLUSIVE = 2ull << 62, LB_FLAGS = 3ull << 62;
 constexpr unsigned long long LB_EPOCH_MASK = ((1ull << 30) - 1ull) << 32;
-constexpr int LB_WINDOW = 4;   // predecessor words fetched per look-back round (independent L2 reads in flight instead of a serial walk)
+constexpr int LB_WINDOW = 8;   // predecessor words fetched per look-back round (independent L2 reads in flight instead of a serial walk)
 
-struct OsShared {              // carved out of dynamic shared memory
-    unsigned int (*wc)[256];   // [WARPS][256] per-warp digit counters -> per-warp start offsets inside the sorted tile
-    unsigned int* dbase;       // [256] digit -> (first output slot of this tile's run) - (start of the digit inside the tile)
-    unsigned int* wtot;        // [8]
-};
+__device__ __forceinline__ uint32_t sort_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <typename T, int THREADS, int KPT, bool FULL, bool MATCH>
-__device__ __forceinline__ void onesweep_tile(const typename SortKey<T>::U* __restrict__ src, typename SortKey<T>::U* __restrict__ dst,
-                                              typename SortKey<T>::U* __restrict__ skeys, const OsShared& sh, size_t n, unsigned int tile,
-                                              int shift, bool raw_in, bool raw_out, const unsigned int* __restrict__ gbase,
-                                              unsigned long long* __restrict__ lookback, unsigned long long ep) {
-    using K = SortKey<T>;
-    using U = typename K::U;
-    constexpr int WARPS = THREADS / 32;
-    constexpr int TILE = THREADS * KPT;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned int lt = (1u << lane) - 1u;
-    const size_t tbase = (size_t)tile * TILE;
-    const size_t wbase = tbase + (size_t)warp * (KPT * 32);
-    const unsigned int nvalid = FULL ? (unsigned)TILE : (unsigned)(n - tbase);
-    unsigned int (*wc)[256] = sh.wc;
-    U key[KPT];
-    unsigned short rank[KPT];
-    // all loads of the thread in flight before the first use (full tiles: unpredicated, so ptxas keeps them together)
+// Ranks of a warp's KPT x 32 keys among the keys of the same digit seen so far by this warp (stable).  Equal digits inside a 32-key step
+// are grouped by ballots; the group's lowest lane bumps the warp's shared counter of that digit once (predicated ATOMS, no divergent branch)
+// and hands the old value round; the steps are issued in order by the one warp that owns the counter row.
+template <typename T, int KPT, bool FULL>
+__device__ __forceinline__ void onesweep_rank(const typename SortKey<T>::U* __restrict__ stage, unsigned int wofs, int lane, unsigned int lt,
+                                              unsigned int nvalid, int shift, uint32_t wc_row, unsigned short (&rank)[KPT]) {
+    using U = typename SortKey<T>::U;
 #pragma unroll
     for (int k = 0; k < KPT; ++k) {
-        const size_t i = wbase + (size_t)k * 32 + lane;
-        key[k] = (FULL || i < n) ? __ldcs(src + i) : U(0);
-    }
-    const unsigned int wc_row = (unsigned int)__cvta_generic_to_shared(&wc[warp][0]);
-#pragma unroll
-    for (int k = 0; k < KPT; ++k) {
-        const bool valid = FULL || (wbase + (size_t)k * 32 + lane < n);
-        if (raw_in) key[k] = K::enc(key[k]);
-        const unsigned int dg = valid ? ((unsigned)(key[k] >> shift) & 255u) : 256u;   // missing keys form their own group
-        const unsigned int grp = MATCH ? __match_any_sync(0xffffffffu, dg) : match_digit<FULL ? 8 : 9>(dg);
+        const unsigned int li = wofs + (unsigned)k * 32 + lane;
+        const bool valid = FULL || li < nvalid;
+        const U key = stage[li];
+        const unsigned int dg = valid ? ((unsigned)(key >> shift) & 255u) : 256u;   // missing keys form their own group
+        const unsigned int grp = match_digit<FULL ? 8 : 9>(dg);
         const unsigned int before = __popc(grp & lt);
         const int leader = __ffs(grp) - 1;
-        // the group's lowest lane bumps the warp's counter of this digit once and hands the old value round (predicated ATOMS, no
-        // divergent branch); steps are issued in order by the one warp that owns this counter row -> equal digits keep their order
         unsigned int old = 0;
         const unsigned int gsize = __popc(grp);
         const unsigned int doit = (valid && before == 0) ? 1u : 0u;
@@ -302,94 +280,42 @@ __device__ __forceinline__ void onesweep_tile(const typename SortKey<T>::U* __re
             "setp.ne.u32 p, %3, 0;\n\t"
             "@p atom.shared.add.u32 %0, [%1], %2;\n\t}"
             : "+r"(old)
-            : "r"(wc_row + dg * 4u), "r"(gsize), "r"(doit)
-            : "memory");
+            : "r"(wc_row + dg * 4u), "r"(gsize), "r"(doit));
         old = __shfl_sync(0xffffffffu, old, leader);
         rank[k] = (unsigned short)(old + before);
     }
-    __syncthreads();
-    unsigned int cnt = 0, tstart = 0;
-    unsigned long long* myword = nullptr;
-    if (threadIdx.x < 256) {
-        const int dd = threadIdx.x;
-        // running prefix of digit dd over the warps; the tile's count goes out at once so that successors can make progress
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            const unsigned int c = wc[w][dd];
-            wc[w][dd] = cnt;
-            cnt += c;
-        }
-        myword = lookback + (size_t)tile * 256 + dd;
-        *(volatile unsigned long long*)myword = (tile == 0 ? LB_INCLUSIVE : LB_PARTIAL) | ep | (unsigned long long)cnt;
-        // exclusive scan of the 256 digit counts -> where digit dd starts inside the sorted tile
-        unsigned int inc = cnt;
-#pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            const unsigned int t = __shfl_up_sync(0xffffffffu, inc, s);
-            if (lane >= s) inc += t;
-        }
-        if (lane == 31) sh.wtot[warp] = inc;
-        tstart = inc - cnt;
-    }
-    __syncthreads();
-    if (threadIdx.x < 256) {
-        for (int w = 0; w < warp; ++w) tstart += sh.wtot[w];
-        const int dd = threadIdx.x;
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) wc[w][dd] += tstart;
-    }
-    __syncthreads();
-    // the tile, sorted by this digit, in shared memory
+}
+
+// The tile, sorted by the digit, into the second shared-memory buffer: local slot = start of the digit's run for this warp + rank.
+template <typename T, int KPT, bool FULL>
+__device__ __forceinline__ void onesweep_reorder(const typename SortKey<T>::U* __restrict__ stage, uint32_t sorted_s, unsigned int wofs, int lane,
+                                                 unsigned int nvalid, int shift, uint32_t wc_row, const unsigned short (&rank)[KPT]) {
+    using U = typename SortKey<T>::U;
 #pragma unroll
     for (int k = 0; k < KPT; ++k) {
-        if (FULL || (wbase + (size_t)k * 32 + lane < n)) {
-            const unsigned int dg = (unsigned)(key[k] >> shift) & 255u;
-            skeys[wc[warp][dg] + rank[k]] = key[k];
-        }
-    }
-    if (threadIdx.x < 256) {
-        const int dd = threadIdx.x;
-        unsigned int excl = 0;
-        if (tile > 0) {
-            long long t = (long long)tile - 1;   // next predecessor to consume
-            bool done = false;
-            while (!done) {
-                unsigned long long v[LB_WINDOW];
-#pragma unroll
-                for (int j = 0; j < LB_WINDOW; ++j)
-                    v[j] = (t - j >= 0) ? *(const volatile unsigned long long*)(lookback + (size_t)(t - j) * 256 + dd) : LB_INCLUSIVE | ep;
-#pragma unroll
-                for (int j = 0; j < LB_WINDOW; ++j) {
-                    if (done) break;
-                    if ((v[j] & LB_FLAGS) == 0 || (v[j] & LB_EPOCH_MASK) != ep) break;   // not published yet: fetch again from here
-                    excl += (unsigned int)v[j];
-                    --t;
-                    if (v[j] & LB_INCLUSIVE) done = true;
-                }
-            }
-            *(volatile unsigned long long*)myword = LB_INCLUSIVE | ep | (unsigned long long)(excl + cnt);
-        }
-        sh.dbase[dd] = gbase[dd] + excl - tstart;
-    }
-    __syncthreads();
-    if (FULL) {
-#pragma unroll
-        for (int k = 0; k < KPT; ++k) {
-            const unsigned int i = (unsigned)k * THREADS + threadIdx.x;
-            const U kk = skeys[i];
-            const unsigned int dg = (unsigned)(kk >> shift) & 255u;
-            dst[sh.dbase[dg] + i] = raw_out ? K::dec(kk) : kk;
-        }
-    } else {
-        for (unsigned int i = threadIdx.x; i < nvalid; i += THREADS) {
-            const U kk = skeys[i];
-            const unsigned int dg = (unsigned)(kk >> shift) & 255u;
-            dst[sh.dbase[dg] + i] = raw_out ? K::dec(kk) : kk;
+        const unsigned int li = wofs + (unsigned)k * 32 + lane;
+        if (FULL || li < nvalid) {
+            const U key = stage[li];
+            const unsigned int dg = (unsigned)(key >> shift) & 255u;
+            unsigned int base;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(base) : "r"(wc_row + dg * 4u));
+            const uint32_t a = sorted_s + (base + rank[k]) * (unsigned)sizeof(U);
+            if constexpr (sizeof(U) == 8) asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(key) : "memory");
+            else asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(key) : "memory");
         }
     }
 }
 
-template <typename T, int THREADS, int KPT, int MINB, bool MATCH>
+// One digit pass over the whole chunk.  Persistent CTAs take tiles by ticket; per tile:
+//   stage   the tile's keys arrive in shared memory by ONE bulk async copy (cp.async.bulk, the TMA engine; SASS UBLKCP) issued by one
+//           thread and completing on an mbarrier -- issued for the NEXT tile as soon as the current one has been reordered, so the DRAM
+//           latency of tile t+1 hides behind the look-back and the write-out of tile t (plain loads only for a misaligned or ragged tile)
+//   rank    warp w owns a contiguous run; equal digits inside a 32-key step are grouped by ballots, a per-warp shared counter row carries
+//           the running rank (stable).  Keys are re-read from shared memory, so a thread holds 16-bit ranks, not keys, in registers.
+//   publish thread d sends the tile's count of digit d (PARTIAL) at once; decoupled look-back resolves the exclusive prefix later
+//   reorder the tile is written, sorted by digit, into a second shared-memory buffer
+//   write   consecutive threads -> consecutive addresses inside each bucket run
+template <typename T, int THREADS, int KPT, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) sort_onesweep_kernel(const typename SortKey<T>::U* __restrict__ in, typename SortKey<T>::U* __restrict__ out,
                                                                       typename SortKey<T>::U* __restrict__ tmp, size_t n, int d, SortPlan* __restrict__ plan,
                                                                       unsigned long long* __restrict__ lookback, unsigned int ntiles,
@@ -400,13 +326,14 @@ __global__ void __launch_bounds__(THREADS, MINB) sort_onesweep_kernel(const type
     constexpr int TILE = THREADS * KPT;
     static_assert(THREADS >= 256 && THREADS % 32 == 0, "thread d serves digit d");
     if (!plan->active[d]) return;
-    extern __shared__ __align__(16) unsigned char os_smem[];
-    U* skeys = reinterpret_cast<U*>(os_smem);                                                   // [TILE]
-    OsShared sh;
-    sh.wc = reinterpret_cast<unsigned int (*)[256]>(os_smem + (size_t)TILE * sizeof(U));
-    sh.dbase = &sh.wc[WARPS][0];
-    sh.wtot = sh.dbase + 256;
-    __shared__ unsigned int s_tile;
+    extern __shared__ __align__(128) unsigned char os_smem[];
+    U* stage = reinterpret_cast<U*>(os_smem);                                   // [TILE] the tile as it sits in memory
+    U* sorted = stage + TILE;                                                   // [TILE] the tile sorted by the digit
+    unsigned int (*wc)[256] = reinterpret_cast<unsigned int (*)[256]>(sorted + TILE);   // [WARPS][256]
+    unsigned int* dbase = &wc[WARPS][0];                                        // [256]
+    unsigned int* wtot = dbase + 256;                                           // [8]
+    __shared__ unsigned int s_next;
+    __shared__ __align__(8) unsigned long long s_bar;
     const int ssel = plan->src_sel[d], dsel = plan->dst_sel[d];
     const U* __restrict__ src = ssel == SEL_IN ? in : (ssel == SEL_OUT ? out : tmp);
     U* __restrict__ dst = dsel == SEL_OUT ? out : tmp;
@@ -414,16 +341,152 @@ __global__ void __launch_bounds__(THREADS, MINB) sort_onesweep_kernel(const type
     const unsigned int* gbase = plan->base[d];
     const int shift = 8 * d;
     const unsigned long long ep = (epoch << 32) & LB_EPOCH_MASK;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int lt = (1u << lane) - 1u;
+    const bool src_aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+    const uint32_t bar = sort_smem_u32(&s_bar), stage_s = sort_smem_u32(stage), sorted_s = sort_smem_u32(sorted);
+    const uint32_t wc_row = sort_smem_u32(&wc[warp][0]);
+    // a tile can come by bulk copy when its bytes are a multiple of 16 from a 16-byte aligned address
+    auto bulk_ok = [&](unsigned int t) -> bool {
+        if (!src_aligned) return false;
+        const size_t tb = (size_t)t * TILE;
+        const size_t cnt = (tb + TILE <= n) ? (size_t)TILE : n - tb;
+        return (cnt * sizeof(U)) % 16 == 0;
+    };
+    auto issue_bulk = [&](unsigned int t) {   // one thread
+        const size_t tb = (size_t)t * TILE;
+        const uint32_t bytes = (uint32_t)(((tb + TILE <= n) ? (size_t)TILE : n - tb) * sizeof(U));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(stage_s), "l"(src + tb), "r"(bytes), "r"(bar)
+                     : "memory");
+    };
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned int t0 = atomicAdd(&plan->tile_ticket[d], 1u);
+        s_next = t0;
+        if (t0 < ntiles && bulk_ok(t0)) issue_bulk(t0);
+    }
+    unsigned int phase = 0;
     for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(&plan->tile_ticket[d], 1u);
-        for (int i = threadIdx.x; i < WARPS * 256; i += THREADS) (&sh.wc[0][0])[i] = 0;
-        __syncthreads();
-        const unsigned int tile = s_tile;
+        for (int i = threadIdx.x; i < WARPS * 256; i += THREADS) (&wc[0][0])[i] = 0;
+        __syncthreads();                                        // s_next, zeroed counters, mbarrier init
+        const unsigned int tile = s_next;
         if (tile >= ntiles) return;
-        if ((size_t)(tile + 1) * TILE <= n) onesweep_tile<T, THREADS, KPT, true, MATCH>(src, dst, skeys, sh, n, tile, shift, raw_in, raw_out, gbase, lookback, ep);
-        else onesweep_tile<T, THREADS, KPT, false, MATCH>(src, dst, skeys, sh, n, tile, shift, raw_in, raw_out, gbase, lookback, ep);
-        // the next iteration's zeroing of wc / reuse of skeys must wait for every reader of this tile
+        const size_t tbase = (size_t)tile * TILE;
+        const bool full = tbase + TILE <= n;
+        const unsigned int nvalid = full ? (unsigned)TILE : (unsigned)(n - tbase);
+        if (bulk_ok(tile)) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "W_%=:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@!p bra W_%=;\n\t}"
+                ::"r"(bar), "r"(phase)
+                : "memory");
+            phase ^= 1u;
+        } else {                                                // misaligned source or ragged byte count: plain loads by everybody
+            for (unsigned int i = threadIdx.x; i < nvalid; i += THREADS) stage[i] = __ldcs(src + tbase + i);
+            __syncthreads();
+        }
+        const unsigned int wofs = (unsigned)warp * (KPT * 32);
+        if (raw_in) {   // first pass only: encode the thread's own keys in place, so that ranking and reordering read encoded keys
+#pragma unroll
+            for (int k = 0; k < KPT; ++k) {
+                const unsigned int li = wofs + (unsigned)k * 32 + lane;
+                if (full || li < nvalid) stage[li] = K::enc(stage[li]);
+            }
+        }
+        unsigned short rank[KPT];
+        if (full) onesweep_rank<T, KPT, true>(stage, wofs, lane, lt, nvalid, shift, wc_row, rank);
+        else onesweep_rank<T, KPT, false>(stage, wofs, lane, lt, nvalid, shift, wc_row, rank);
         __syncthreads();
+        unsigned int cnt = 0, tstart = 0;
+        unsigned long long* myword = nullptr;
+        if (threadIdx.x < 256) {
+            const int dd = threadIdx.x;
+            // running prefix of digit dd over the warps; the tile's count goes out at once so that successors can make progress
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const unsigned int c = wc[w][dd];
+                wc[w][dd] = cnt;
+                cnt += c;
+            }
+            myword = lookback + (size_t)tile * 256 + dd;
+            *(volatile unsigned long long*)myword = (tile == 0 ? LB_INCLUSIVE : LB_PARTIAL) | ep | (unsigned long long)cnt;
+            // exclusive scan of the 256 digit counts -> where digit dd starts inside the sorted tile
+            unsigned int inc = cnt;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, inc, s);
+                if (lane >= s) inc += t;
+            }
+            if (lane == 31) wtot[warp] = inc;
+            tstart = inc - cnt;
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            for (int w = 0; w < warp; ++w) tstart += wtot[w];
+            const int dd = threadIdx.x;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) wc[w][dd] += tstart;
+        }
+        __syncthreads();
+        if (full) onesweep_reorder<T, KPT, true>(stage, sorted_s, wofs, lane, nvalid, shift, wc_row, rank);
+        else onesweep_reorder<T, KPT, false>(stage, sorted_s, wofs, lane, nvalid, shift, wc_row, rank);
+        __syncthreads();                                        // `stage` is free again, `sorted` is complete
+        if (threadIdx.x == 0) {                                 // next tile: ticket + bulk copy, in flight during look-back and write-out
+            const unsigned int t1 = atomicAdd(&plan->tile_ticket[d], 1u);
+            s_next = t1;
+            if (t1 < ntiles && bulk_ok(t1)) issue_bulk(t1);
+        }
+        if (threadIdx.x < 256) {
+            const int dd = threadIdx.x;
+            unsigned int excl = 0;
+            if (tile > 0) {
+                long long t = (long long)tile - 1;   // next predecessor to consume
+                bool done = false;
+                while (!done) {
+                    unsigned long long v[LB_WINDOW];
+#pragma unroll
+                    for (int j = 0; j < LB_WINDOW; ++j)
+                        v[j] = (t - j >= 0) ? *(const volatile unsigned long long*)(lookback + (size_t)(t - j) * 256 + dd) : (LB_INCLUSIVE | ep);
+#pragma unroll
+                    for (int j = 0; j < LB_WINDOW; ++j) {
+                        if (done) break;
+                        if ((v[j] & LB_FLAGS) == 0 || (v[j] & LB_EPOCH_MASK) != ep) break;   // not published yet: fetch again from here
+                        excl += (unsigned int)v[j];
+                        --t;
+                        if (v[j] & LB_INCLUSIVE) done = true;
+                    }
+                }
+                *(volatile unsigned long long*)myword = LB_INCLUSIVE | ep | (unsigned long long)(excl + cnt);
+            }
+            dbase[dd] = gbase[dd] + excl - tstart;
+        }
+        __syncthreads();
+        if (full && !raw_out) {
+#pragma unroll
+            for (int k = 0; k < KPT; ++k) {
+                const unsigned int i = (unsigned)k * THREADS + threadIdx.x;
+                const U kk = sorted[i];
+                dst[dbase[(unsigned)(kk >> shift) & 255u] + i] = kk;
+            }
+        } else if (full) {   // last pass: back to the raw bit patterns
+#pragma unroll
+            for (int k = 0; k < KPT; ++k) {
+                const unsigned int i = (unsigned)k * THREADS + threadIdx.x;
+                const U kk = sorted[i];
+                dst[dbase[(unsigned)(kk >> shift) & 255u] + i] = K::dec(kk);
+            }
+        } else {
+            for (unsigned int i = threadIdx.x; i < nvalid; i += THREADS) {
+                const U kk = sorted[i];
+                dst[dbase[(unsigned)(kk >> shift) & 255u] + i] = raw_out ? K::dec(kk) : kk;
+            }
+        }
+        // the loop top zeroes wc and syncs before anybody reads s_next / writes `sorted` again
     }
 }
 
@@ -467,7 +530,7 @@ int32_t sort_scratch(dab_ctx* ctx, size_t dev_bytes) {
 constexpr size_t SORT_PLAN_BYTES = 65536;   // SortPlan + the staging areas of dab_sorted_split, ahead of the look-back words
 static_assert(sizeof(SortPlan) + 8192 <= SORT_PLAN_BYTES, "plan area");
 
-template <typename T, int THREADS, int KPT, int MINB, bool MATCH>
+template <typename T, int THREADS, int KPT, int MINB>
 int32_t sort_passes(dab_ctx* ctx, const typename SortKey<T>::U* in, typename SortKey<T>::U* out, typename SortKey<T>::U* tmp, size_t n) {
     using K = SortKey<T>;
     using U = typename K::U;
@@ -497,8 +560,8 @@ int32_t sort_passes(dab_ctx* ctx, const typename SortKey<T>::U* in, typename Sor
         sort_copy_if_kernel<U><<<cgrid, 256, 0, ctx->stream>>>(plan, in, out, n, 1);   // acts only when every key is equal
         DAB_LAUNCHED(ctx);
     }
-    auto kern = sort_onesweep_kernel<T, THREADS, KPT, MINB, MATCH>;
-    constexpr size_t smem = (size_t)TILE * sizeof(U) + (size_t)(THREADS / 32) * 1024 + 1024 + 32;
+    auto kern = sort_onesweep_kernel<T, THREADS, KPT, MINB>;
+    constexpr size_t smem = 2 * (size_t)TILE * sizeof(U) + (size_t)(THREADS / 32) * 1024 + 1024 + 32;
     int per_sm = 0;
     {   // >48 KiB of dynamic shared memory is an opt-in attribute of the (kernel, device) pair; the occupancy query needs it set
         static std::mutex mu;
@@ -552,19 +615,19 @@ int32_t sort_t(dab_ctx* ctx, const void* in_v, void* out_v, void* tmp_v, size_t 
     // tile shape: 32 KiB of keys per CTA in shared memory -> ~128-byte bucket runs per tile on random digits
     if constexpr (sizeof(U) == 8) {
         switch (ctx->opt_sort_variant) {
-            case 1: return sort_passes<T, 256, 16, 4, false>(ctx, in, out, tmp, n);
-            case 2: return sort_passes<T, 256, 16, 3, true>(ctx, in, out, tmp, n);
-            case 3: return sort_passes<T, 512, 8, 2, false>(ctx, in, out, tmp, n);
-            case 4: return sort_passes<T, 256, 12, 4, false>(ctx, in, out, tmp, n);
-            default: return sort_passes<T, 256, 16, 3, false>(ctx, in, out, tmp, n);
+            case 1: return sort_passes<T, 256, 16, 2>(ctx, in, out, tmp, n);
+            case 2: return sort_passes<T, 256, 8, 4>(ctx, in, out, tmp, n);
+            case 3: return sort_passes<T, 512, 8, 1>(ctx, in, out, tmp, n);
+            case 4: return sort_passes<T, 256, 12, 3>(ctx, in, out, tmp, n);
+            default: return sort_passes<T, 256, 16, 3>(ctx, in, out, tmp, n);
         }
     } else {
         switch (ctx->opt_sort_variant) {
-            case 1: return sort_passes<T, 256, 32, 3, false>(ctx, in, out, tmp, n);
-            case 2: return sort_passes<T, 256, 32, 2, true>(ctx, in, out, tmp, n);
-            case 3: return sort_passes<T, 512, 16, 2, false>(ctx, in, out, tmp, n);
-            case 4: return sort_passes<T, 256, 24, 3, false>(ctx, in, out, tmp, n);
-            default: return sort_passes<T, 256, 32, 2, false>(ctx, in, out, tmp, n);
+            case 1: return sort_passes<T, 256, 32, 2>(ctx, in, out, tmp, n);
+            case 2: return sort_passes<T, 256, 16, 4>(ctx, in, out, tmp, n);
+            case 3: return sort_passes<T, 512, 16, 1>(ctx, in, out, tmp, n);
+            case 4: return sort_passes<T, 256, 24, 3>(ctx, in, out, tmp, n);
+            default: return sort_passes<T, 256, 32, 3>(ctx, in, out, tmp, n);
         }
     }
 }

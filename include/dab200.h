@@ -241,6 +241,16 @@ int32_t dab_copy_box(dab_ctx* ctx, int32_t elem_bytes, void* dst, const size_t d
  * :101-117).  Float products accumulate in fp64 and round once; Int32/Int64 wrap.  dtypes: F32 F64 I32 I64. */
 int32_t dab_gemv(dab_ctx* ctx, int32_t dtype, int32_t trans, const void* A, size_t m, size_t n, const void* x, void* r);
 
+/* ==== Level-3 tile product K12 (widening row f4; the one contraction on the path: tensor-core roofline) =====================
+ * R[m x n] (ldc) = op(A) * B on column-major operands of ONE worker: transA = 0 -> A is m x k (lda); transA = 1 -> op(A) = A^T with A
+ * stored k x m (lda); B is k x n (ldb).  Replaces  localpart(A) * convert(localtype(B), Bjk)  and the transpose / adjoint forms of
+ * _matmatmul! (src/linalg.jl:218-226); the caller scales C by beta and adds alpha * R per tile exactly as the reference (:232-252).
+ * Float32 with 16-byte aligned bases and leading dimensions: TMA-fed tcgen05 (3xTF32 error-compensated, TMEM accumulators drained
+ * every "gemm_kc" k for fp32 round-to-nearest accumulation); otherwise and for Float64 / Int32 / Int64: shared-memory tiled FMA kernel
+ * (integers wrap like Julia's).  R is overwritten. */
+int32_t dab_gemm(dab_ctx* ctx, int32_t dtype, int32_t transA, size_t m, size_t n, size_t k, const void* A, size_t lda, const void* B,
+                 size_t ldb, void* C, size_t ldc);
+
 /* dst[j + i*dst_ld] = src[i + j*src_ld] for i < rows, j < cols (both column-major): the per-piece body of
  * copy(::Transpose/Adjoint{T,<:DArray{T,2}}) (src/linalg.jl:1-17: transpose!(lp, Array(D[reverse(I)...]))).
  * src may be a PEER pointer: rows are pulled coalesced over NVLink and written coalesced locally through a

@@ -19,7 +19,7 @@ from ._darray import (B200Array, DArray, SubDArray, allowscalar, dab_dtype, np_d
 from .layout import Layout, chunk_idxs, cuts_for, defaultdist, make_layout, slab_plan
 from ._mapreduce import (all, any, axpy_, count, dot, extrema, isequal, mapreduce, mapreducedim, maximum, mean, minimum, norm,  # noqa: A004
                          prod, reduce, rmul_, sum)
-from ._linalg import Adjoint, Transpose, adjoint, copy_transposed, lmul_diag, matmul, mul_, rmul_diag, transpose
+from ._linalg import Adjoint, Transpose, adjoint, copy_transposed, lmul_diag, matmat, matmul, mul_, mul_mat_, rmul_diag, transpose
 from ._sort import sort, sort_with_boundaries
 from .runtime import Runtime, init, myid, nworkers, runtime, workers
 

@@ -111,6 +111,8 @@ _SIGS = {
     "dab_mailbox_create": (_i32, [_vp, _vp]),
     "dab_mailbox_attach": (_i32, [_vp, _vp, _i32, _i32]),
     "dab_mailbox_detach": (_i32, [_vp]),
+    "dab_peer_barrier": (_i32, [_vp]),
+    "dab_accumulate_stack": (_i32, [_vp, _i32, _vp, _sz, _vp, _vp, _vp, _sz, _i32]),
     "dab_ipc_get_handle": (_i32, [_vp, _vp, _vp]),
     "dab_ipc_open": (_i32, [_vp, _vp, _pvp]),
     "dab_ipc_close": (_i32, [_vp, _vp]),

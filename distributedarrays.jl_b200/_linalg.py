@@ -8,7 +8,9 @@ Mirrors the reference's ``src/linalg.jl``:
   exchange as mapreducedim_between (NCCL send/recv to the owner of each y chunk)
 * ``lmul!(D::Diagonal, DA)`` / ``rmul!(DA, D::Diagonal)`` (:169-187)                      -> fused broadcast with extrusion
 
-Matrix-matrix ``mul!`` (:189-277) has a different (tensor-core) roofline and is not served yet: it raises UnsupportedError.
+* ``mul!(C::DMatrix, A::DMatrix, B::AbstractMatrix, a, b)`` and the Adjoint/Transpose forms, ``A*B``, ``A'*B`` (:189-311)
+                                                                                          -> K12 ``dab_gemm`` (tcgen05 3xTF32 tile
+  products for Float32, SIMT tiles for Float64 / Int32 / Int64) + the same exchange of the tile results to the owners of C
 """
 from __future__ import annotations
 
@@ -151,7 +153,7 @@ def mul_(y: DArray, A: Union[DArray, Transpose], x, alpha=1, beta=0) -> DArray:
     differ, ArgumentError when y's cuts do not match the matrix cuts along the kept dim."""
     M, trans = _unwrap(A)
     if isinstance(x, (DArray, np.ndarray)) and len(np.shape(x) if not isinstance(x, DArray) else x.dims) == 2:
-        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "matrix-matrix mul! is not served by the B200 backend yet")
+        return mul_mat_(y, A, x, alpha, beta)
     if M.ndim != 2 or y.ndim != 1:
         raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, "mul!: y must be a DVector and A a DMatrix")
     rd, cd = (1, 0) if trans else (0, 1)
@@ -248,8 +250,10 @@ def matmul(A: Union[DArray, Transpose], x) -> DArray:
     ``transpose(A)*x`` (:293-301, 303-311): on ``procs(A)[1,:]``, one chunk per grid column."""
     M, trans = _unwrap(A)
     xnd = len(x.dims) if isinstance(x, DArray) else np.ndim(x)
+    if xnd == 2:
+        return matmat(A, x)
     if xnd != 1:
-        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "matrix-matrix products are not served by the B200 backend yet")
+        raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, "A*x: x must be a vector or a matrix")
     if M.ndim != 2:
         raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, "A must be a DMatrix")
     xdt = x.dtype if isinstance(x, DArray) else np.asarray(x).dtype
@@ -262,6 +266,180 @@ def matmul(A: Union[DArray, Transpose], x) -> DArray:
     rt = M.rt
     y = darray(lambda I: B200Array.empty(rt, shape_of(I), T), (M.dims[rd],), procs=pids, dist=[M.layout.grid[rd]], dtype=T, rt=rt)
     return mul_(y, A, x)
+
+
+# ---- matrix-matrix ------------------------------------------------------------------------------------------------------------------
+
+
+def matmat_exchange_plan(L, Clayout, trans: bool, rank_of, my_rank: int):
+    """Who ships which tile result where in ``_matmatmul!``: R[i,j,k] is computed by the rank holding ``procs(A)[i,j]``
+    (``procs(A)[j,i]`` for the transposed forms) and consumed by the rank holding ``C.pids[i,k]`` (reference src/linalg.jl:208-252).
+    Pure function of the layouts; both sides of every pair list their transfers in the same (k, i, j) order.  Entries carry the tile
+    shape (rows of C chunk i, columns of C chunk k)."""
+    g0, g1 = L.grid
+    gi, gj = (g1, g0) if trans else (g0, g1)
+    c0, gk = Clayout.grid
+    plan = {"owned": [], "local": [], "sends": [], "recvs": []}
+    for k in range(gk):
+        for i in range(gi):
+            lin_c = i + k * c0
+            orank = rank_of(Clayout.pids[lin_c])
+            rows, cols = rlen(Clayout.indices[lin_c][0]), rlen(Clayout.indices[lin_c][1])
+            if orank == my_rank:
+                plan["owned"].append((i, k))
+            for j in range(gj):
+                trank = rank_of(L.pids[(j + i * g0) if trans else (i + j * g0)])
+                if orank == my_rank and trank == my_rank:
+                    plan["local"].append((i, j, k, rows, cols))
+                elif orank == my_rank:
+                    plan["recvs"].append((i, j, k, rows, cols, trank))
+                elif trank == my_rank:
+                    plan["sends"].append((i, j, k, rows, cols, orank))
+    return plan
+
+
+def _b_block(rt: Runtime, B, rlo: int, rhi: int, clo: int, chi: int, dtype: np.dtype) -> B200Array:
+    """``convert(localtype(B), B[rlo:rhi, clo:chi])`` on this rank's GPU (src/linalg.jl:214, 221-225): host matrices are sliced and
+    uploaded, DMatrices halo-fetched (peer loads when the block lives on other GPUs)."""
+    shape = (rhi - rlo + 1, chi - clo + 1)
+    if isinstance(B, DArray):
+        if B.dtype != dtype:
+            raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"mul!: eltype of B {B.dtype} vs matrix eltype {dtype}")
+        out = B200Array.empty(rt, shape, dtype, temp=True)
+        if out.size:
+            SubDArray(B, ((rlo, rhi), (clo, chi)), (False, False)).copy_to(out)
+        return out
+    h = np.asfortranarray(np.asarray(B)[rlo - 1:rhi, clo - 1:chi], dtype=dtype)
+    out = B200Array.empty(rt, shape, dtype, temp=True)
+    if out.size:
+        out.copy_from_host(h, sync=True)
+    return out
+
+
+def mul_mat_(Cd: DArray, A: Union[DArray, Transpose], B, alpha=1, beta=0) -> DArray:
+    """``mul!(C::DMatrix, A::DMatrix, B::AbstractMatrix, α=1, β=0)`` and the Adjoint / Transpose forms = ``_matmatmul!`` (reference
+    src/linalg.jl:189-261).  Same errors as the reference: DimensionMismatch for the contracted / result sizes, ArgumentError when the
+    cuts of C's first dimension differ from A's."""
+    M, trans = _unwrap(A)
+    if M.ndim != 2 or Cd.ndim != 2:
+        raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, "mul!: C and A must be DMatrices")
+    rd, cd = (1, 0) if trans else (0, 1)
+    mA, nA = M.dims[rd], M.dims[cd]
+    mB, nB = B.dims if isinstance(B, DArray) else tuple(np.shape(B))
+    if mB != nA:
+        raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"matrix A has dimensions ({mA}, {nA}), matrix B has dimensions ({mB}, {nB})")
+    if Cd.dims != (mA, nB):
+        raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"result C has dimensions {Cd.dims}, needs ({mA}, {nB})")
+    if list(Cd.layout.cuts[0]) != list(M.layout.cuts[rd]):
+        raise _lib.ArgumentError(_lib.ERR_ARG, "cuts of the first dimension of the output matrix must match cuts of dimension %d of the first input matrix" % (rd + 1))
+    dt = Cd.dtype
+    if dt not in _GEMV_DTYPES or M.dtype != dt:
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"mul!: eltypes C={dt} A={M.dtype} (served: equal Float32/Float64/Int32/Int64)")
+    rt = Cd.rt
+    L, CL = M.layout, Cd.layout
+    g0, g1 = L.grid
+    gi, gj = (g1, g0) if trans else (g0, g1)
+    c0, gk = CL.grid
+    cuts_c, cuts_k = L.cuts[cd], CL.cuts[1]
+    code, isz = dab_dtype(dt), dt.itemsize
+    remote_b = isinstance(B, DArray) and rt.world > 1
+    if remote_b:
+        if B._handles is None:
+            B.share()
+        rt.barrier()
+
+    def tile_pid(i, j):
+        return L.pids[(j + i * g0) if trans else (i + j * g0)]
+
+    # ---- R[i,j,k] = op(localpart(A)) * Bjk on the tile owners (src/linalg.jl:208-229)
+    R: Dict[Tuple[int, int, int], B200Array] = {}
+    temps: List[B200Array] = []
+    for j in range(gj):
+        for k in range(gk):
+            bjk = None
+            for i in range(gi):
+                pid = tile_pid(i, j)
+                if pid not in M.chunks:
+                    continue
+                ch = M.chunks[pid]
+                if bjk is None:
+                    bjk = _b_block(rt, B, cuts_c[j], cuts_c[j + 1] - 1, cuts_k[k], cuts_k[k + 1] - 1, dt)
+                    temps.append(bjk)
+                m_t, k_t, n_t = ch.shape[rd], ch.shape[cd], bjk.shape[1]
+                r = B200Array.empty(rt, (m_t, n_t), dt, temp=True)
+                if r.size:
+                    _lib.call("dab_gemm", rt.ctx, code, 1 if trans else 0, m_t, n_t, k_t, C.c_void_p(ch.ptr), max(1, ch.shape[0]), C.c_void_p(bjk.ptr),
+                              max(1, k_t), C.c_void_p(r.ptr), max(1, m_t))
+                R[(i, j, k)] = r
+    # ---- ship the tile results to the owner of C's chunk (i, k): one grouped exchange (the fetch(rijk) of :248-249)
+    plan = matmat_exchange_plan(L, CL, trans, rt.rank_of, rt.rank)
+    stacks: Dict[Tuple[int, int], B200Array] = {}
+    for (i, k) in plan["owned"]:
+        lin_c = i + k * c0
+        stacks[(i, k)] = B200Array.empty(rt, (int(np.prod(shape_of(CL.indices[lin_c]))) * gj,), dt, temp=True)
+    for i, j, k, rows, cols in plan["local"]:
+        if rows * cols:
+            _lib.call("dab_d2d", rt.ctx, C.c_void_p(stacks[(i, k)].ptr + j * rows * cols * isz), C.c_void_p(R[(i, j, k)].ptr), rows * cols * isz)
+    sends = [(R[(i, j, k)].ptr, rows * cols * isz, peer) for i, j, k, rows, cols, peer in plan["sends"] if rows * cols]
+    recvs = [(stacks[(i, k)].ptr + j * rows * cols * isz, rows * cols * isz, peer) for i, j, k, rows, cols, peer in plan["recvs"] if rows * cols]
+    if sends or recvs:
+        _lib.call("dab_group_start", rt.ctx)
+        for ptr, nb, peer in sends:
+            _lib.call("dab_send", rt.ctx, C.c_void_p(ptr), nb, peer)
+        for ptr, nb, peer in recvs:
+            _lib.call("dab_recv", rt.ctx, C.c_void_p(ptr), nb, peer)
+        _lib.call("dab_group_end", rt.ctx)
+    # ---- scale C (:232-240), then add!(localpart(C), R[i,j,k], α) for each j (:243-252; j order)
+    a_s, b_s = np.asarray(alpha, dtype=dt), np.asarray(beta, dtype=dt)
+    for (i, k), stack in stacks.items():
+        cch = Cd.chunks[CL.pids[i + k * c0]]
+        nel = cch.size
+        if nel == 0:
+            continue
+        if beta != 1:
+            if beta == 0:
+                z = np.zeros((), dtype=dt)
+                _lib.call("dab_fill", rt.ctx, code, C.c_void_p(cch.ptr), nel, C.c_void_p(z.ctypes.data))
+            else:
+                _lib.call("dab_binary_scalar", rt.ctx, code, _lib.MUL, C.c_void_p(cch.ptr), C.c_void_p(cch.ptr), C.c_void_p(b_s.ctypes.data), 0, nel)
+        for j in range(gj):
+            rp = stack.ptr + j * nel * isz
+            if alpha != 1:
+                _lib.call("dab_binary_scalar", rt.ctx, code, _lib.MUL, C.c_void_p(rp), C.c_void_p(rp), C.c_void_p(a_s.ctypes.data), 1, nel)
+            _lib.call("dab_binary", rt.ctx, code, _lib.ADD, C.c_void_p(cch.ptr), C.c_void_p(cch.ptr), C.c_void_p(rp), nel)
+    for t in list(R.values()) + temps + list(stacks.values()):
+        t.free()
+    if remote_b:
+        rt.sync()
+        rt.barrier()
+    return Cd
+
+
+def matmat(A: Union[DArray, Transpose], B) -> DArray:
+    """``A*B`` (reference src/linalg.jl:285-292): C on ``procs(A)[:, 1:min(size(procs(A),2), size(procs(B),2))]`` with that grid;
+    ``A'*B`` / ``transpose(A)*B`` (:302-311): on ``procs(A)[1:min(size(procs(A),1), size(procs(B),2)), :]`` with grid
+    ``(size(procs(A),2), that min)``.  The reference asks ``procs(B)`` for its grid, so B is a DMatrix there; a host matrix is accepted
+    here as a one-column grid (what ``distribute`` of a matrix no wider than tall gives on these workers)."""
+    M, trans = _unwrap(A)
+    if M.ndim != 2:
+        raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, "A must be a DMatrix")
+    bdt = B.dtype if isinstance(B, DArray) else np.asarray(B).dtype
+    T = np.result_type(M.dtype, bdt)                       # promote_op(t*s + t*s)
+    if T != M.dtype:
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"A*B: eltype {M.dtype} with a {bdt} matrix needs a converted copy of A")
+    bcols = B.dims[1] if isinstance(B, DArray) else np.shape(B)[1]
+    bg1 = B.layout.grid[1] if isinstance(B, DArray) else 1
+    g0, g1 = M.layout.grid
+    pg = np.asarray(M.layout.pids).reshape((g0, g1), order="F")
+    rt = M.rt
+    if not trans:
+        nc = min(g1, bg1)
+        pids, dims, dist = [int(p) for p in pg[:, :nc].reshape(-1, order="F")], (M.dims[0], bcols), [g0, nc]
+    else:
+        nr = min(g0, bg1)
+        pids, dims, dist = [int(p) for p in pg[:nr, :].reshape(-1, order="F")], (M.dims[1], bcols), [g1, nr]
+    Cd = darray(lambda I: B200Array.empty(rt, shape_of(I), T), dims, procs=pids, dist=dist, dtype=T, rt=rt)
+    return mul_mat_(Cd, A, B)
 
 
 # ---- Diagonal scaling ---------------------------------------------------------------------------------------------------------------

@@ -13,6 +13,7 @@
 #include <nccl.h>
 
 #include "dab_common.cuh"
+#include "dab_scalar_ops.cuh"
 
 namespace {
 
@@ -88,6 +89,49 @@ int32_t nccl_fail(dab_ctx* ctx, ncclResult_t r, const char* what) {
 #define NEED_COMM(ctx)                                                                                    \
     NEED_NCCL(ctx);                                                                                       \
     if (!(ctx)->comm) return dab_fail((ctx), DAB_ERR_NCCL, "no communicator: call dab_comm_init_rank first")
+
+
+// ---- device-side barrier across the ranks (stream-ordered; no host synchronisation, no NCCL launch) ---------------------------------------
+// One CTA: thread j stores this rank's arrival number into rank j's counter row (peer store over NVLink, system fence first so that every
+// write of the preceding kernels of this stream is visible to a peer that sees the number), then polls its own row until rank j has
+// arrived too.  Kernels queued after it on this stream therefore start only when EVERY rank's earlier kernels have completed: the fence
+// the reference gets from remotecall_wait / fetch, without leaving the GPU.  A dead peer surfaces after the wall-clock timeout as a status
+// word in pinned host memory (checked by dab_sync), not as a hung device.
+__global__ void peer_barrier_kernel(void* const* __restrict__ peers, int rank, int nranks, unsigned long long seq, unsigned long long timeout_ns,
+                                    volatile unsigned long long* __restrict__ host_status) {
+    const int j = threadIdx.x;
+    if (j >= nranks) return;
+    __threadfence_system();
+    volatile unsigned long long* theirs = reinterpret_cast<volatile unsigned long long*>((char*)peers[j] + DAB_MBOX_BARRIER_OFFSET) + rank;
+    *theirs = seq;
+    volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>((char*)peers[rank] + DAB_MBOX_BARRIER_OFFSET) + j;
+    const unsigned long long t0 = dab_globaltimer_ns();
+    unsigned int spins = 0;
+    while (*mine < seq) {
+        if ((++spins & 1023u) == 0 && dab_globaltimer_ns() - t0 > timeout_ns) {
+            host_status[0] = 1ull;
+            __threadfence_system();
+            break;
+        }
+    }
+    __threadfence_system();
+}
+
+// y = beta * y (fill 0 when beta == 0, untouched when beta == 1), then y += alpha * stack[j] for j = 0 .. count-1 IN ORDER, each step one
+// multiply and one add rounded separately: the rmul!/fill! + add!(localpart(y), R[i,j], alpha) sequence of mul! (reference src/linalg.jl:
+// 101-117, 62-76) in ONE launch instead of 1 + 2*count; bit-identical to the separate launches.
+template <typename T>
+__global__ void __launch_bounds__(256) accumulate_stack_kernel(T* __restrict__ y, size_t n, T beta, int beta_mode, T alpha, int alpha_one,
+                                                              const T* __restrict__ stack, size_t stride, int count) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        T v = beta_mode == 0 ? T(0) : (beta_mode == 1 ? y[i] : jl::mul(y[i], beta));
+        for (int j = 0; j < count; ++j) {
+            const T r = stack[(size_t)j * stride + i];
+            v = jl::add(v, alpha_one ? r : jl::mul(alpha, r));
+        }
+        y[i] = v;
+    }
+}
 
 }  // namespace
 
@@ -285,6 +329,42 @@ int32_t dab_mailbox_detach(dab_ctx* ctx) {
     ctx->mbox_ranks = 0;
     cudaGetLastError();
     return DAB_OK;
+}
+
+
+int32_t dab_peer_barrier(dab_ctx* ctx) {
+    DAB_ENTER(ctx);
+    if (ctx->mbox_ranks <= 1) return DAB_OK;   // one worker: stream order is the barrier
+    volatile unsigned long long* status = (volatile unsigned long long*)((char*)ctx->host_slot + (DAB_MAX_RANKS + 1) * 16);
+    const unsigned long long seq = ++ctx->barrier_seq;
+    peer_barrier_kernel<<<1, DAB_MAX_RANKS, 0, ctx->stream>>>(ctx->peer_mbox_dev, ctx->rank, ctx->mbox_ranks, seq,
+                                                             (unsigned long long)ctx->opt_combine_timeout_ms * 1000000ull, status);
+    DAB_LAUNCHED(ctx);
+    return DAB_OK;
+}
+
+int32_t dab_accumulate_stack(dab_ctx* ctx, int32_t dtype, void* y, size_t n, const void* beta, const void* alpha, const void* stack, size_t stride,
+                             int32_t count) {
+    DAB_ENTER(ctx);
+    if (n == 0) return DAB_OK;
+    DAB_REQUIRE(ctx, y && beta && alpha && (stack || count == 0) && count >= 0, DAB_ERR_ARG, "dab_accumulate_stack: bad argument");
+    const int grid = dab_grid_for(ctx, (n + 255) / 256, 8);
+#define ACC(T)                                                                                                                       \
+    {                                                                                                                                \
+        const T b = *(const T*)beta, a = *(const T*)alpha;                                                                           \
+        accumulate_stack_kernel<T><<<grid, 256, 0, ctx->stream>>>((T*)y, n, b, b == T(0) ? 0 : (b == T(1) ? 1 : 2), a, a == T(1), \
+                                                                   (const T*)stack, stride, count);                                  \
+        DAB_LAUNCHED(ctx);                                                                                                           \
+        return DAB_OK;                                                                                                               \
+    }
+    switch (dtype) {
+        case DAB_F32: ACC(float)
+        case DAB_F64: ACC(double)
+        case DAB_I32: ACC(int32_t)
+        case DAB_I64: ACC(long long)
+        default: return dab_fail(ctx, DAB_ERR_UNSUPPORTED, "dab_accumulate_stack: dtype %d", dtype);
+    }
+#undef ACC
 }
 
 // ---- peer memory -------------------------------------------------------------------------------------------

@@ -34,6 +34,7 @@ struct dab_ctx {
     void* peer_mbox_host[DAB_MAX_RANKS];
     int mbox_ranks;         // 0 = not attached
     unsigned long long mbox_seq;
+    unsigned long long barrier_seq;   // dab_peer_barrier: how many device-side barriers this rank has entered
     int fuse_op;            // >= 0: the next launch_reduce appends the cross-rank combine for this DAB_* op
     struct dab_alloc_cache* cache;  // size-bucketed reuse of small cudaMalloc blocks (dab_core.cu)
     void* sort_dev;         // radix-sort scratch: digit histograms + per-tile counts (dab_sort.cu)
@@ -42,7 +43,7 @@ struct dab_ctx {
     unsigned long long sort_epoch;  // one per digit pass ever launched: tags the look-back words so the scratch is never re-cleared
     int opt_sort_variant;   // dab_set_option("sort_variant"): tile shape of the onesweep kernel (tuning sweeps)
     long long opt_combine_timeout_ms;  // dab_set_option("combine_timeout_ms"): how long the fused combine waits for a peer (default 120 s)
-    long long opt_gemm_kc;  // dab_set_option("gemm_kc"): k extent summed inside tensor memory before a partial tile is drained (default 256)
+    long long opt_gemm_kc;  // dab_set_option("gemm_kc"): k extent summed inside tensor memory before a partial tile is drained (default 64)
     int opt_gemm_simt;      // dab_set_option("gemm_simt"): 1 = force the SIMT tile kernel for Float32 (A/B measurements)
     int opt_ew_tma;         // dab_set_option("ew_tma"): route aligned unary elementwise launches through the TMA-staged kernel
     char err[512];
@@ -90,7 +91,8 @@ static inline size_t dab_dtype_size(int32_t dt) {
 
 // Cross-rank combine fused into the reduce kernel's last CTA (see reduce_kernel): nranks == 0 disables it.
 #define DAB_MBOX_SLOT 32                                   /* [0,8) result  [8,16) wide carrier  [16,24) sequence flag */
-#define DAB_MBOX_BYTES (2 * DAB_MAX_RANKS * DAB_MBOX_SLOT) /* two parities */
+#define DAB_MBOX_BARRIER_OFFSET (2 * DAB_MAX_RANKS * DAB_MBOX_SLOT) /* after the two parity banks: one 8-byte arrival counter per rank (dab_peer_barrier) */
+#define DAB_MBOX_BYTES (DAB_MBOX_BARRIER_OFFSET + DAB_MAX_RANKS * 8)
 struct FusedComm {
     void* const* peers;        // device array of the nranks mailboxes
     void* host_out;            // pinned host slot: [0,8) folded result, [8,16) status (0 ok, 1 timed out)

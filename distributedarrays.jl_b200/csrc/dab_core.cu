@@ -135,6 +135,7 @@ int32_t dab_init(int32_t device, dab_ctx** out) {
     INIT_CUDA(cudaMalloc(&ctx->gather_slots, (size_t)DAB_MAX_RANKS * 16));
     INIT_CUDA(cudaHostAlloc(&ctx->host_slot, (size_t)(DAB_MAX_RANKS + 2) * 16, cudaHostAllocDefault));
     INIT_CUDA(cudaStreamSynchronize(ctx->stream));
+    memset(ctx->host_slot, 0, (size_t)(DAB_MAX_RANKS + 2) * 16);
 #undef INIT_CUDA
     *out = ctx;
     return DAB_OK;
@@ -170,6 +171,11 @@ int32_t dab_shutdown(dab_ctx* ctx) {
 int32_t dab_sync(dab_ctx* ctx) {
     DAB_ENTER(ctx);
     DAB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    volatile unsigned long long* status = (volatile unsigned long long*)((char*)ctx->host_slot + (DAB_MAX_RANKS + 1) * 16);
+    if (*status != 0) {   // set by peer_barrier_kernel (dab_comm.cu) when a peer never arrived
+        *status = 0;
+        return dab_fail(ctx, DAB_ERR_NCCL, "device-side peer barrier timed out waiting for another rank (did every rank make the same collective call?)");
+    }
     return DAB_OK;
 }
 

@@ -11,9 +11,11 @@
 //   * four converter warps split every fp32 tile into tf32 "hi" (round-to-nearest) and "lo" (the rounded remainder) in place
 //   * ONE thread issues tcgen05.mma.kind::tf32 (SASS UTCHMMA... ) with the accumulators in TENSOR MEMORY: per 8-deep k-step the three
 //     products a_lo*b_hi + a_hi*b_lo + a_hi*b_hi ("3xTF32": the dropped a_lo*b_lo term is 2^-22 relative), M = N = 128
-//   * two-level accumulation: a TMEM accumulator only sums KC consecutive k (default 256); four drain warps pull each finished partial
-//     tile out of TMEM (tcgen05.ld, SASS LDTM) and add it to fp32 registers with round-to-nearest while the tensor core already works
-//     on the other accumulator -- the tensor core's internal adder truncates, which over a long k would bias the sum
+//   * two-level accumulation, because the tensor core TRUNCATES its fp32 accumulator on every tcgen05.mma (measured: ~2^-25 relative
+//     bias per accumulating instruction, linear in their number -- 3e-6 after k = 256 on same-sign data): a TMEM accumulator only sums
+//     KC consecutive k (default 64 = 8 instructions), the two correction products go to a SEPARATE accumulator (their truncation is
+//     2^-11 smaller), and eight drain warps pull each finished pair of partial tiles out of TMEM (tcgen05.ld, SASS LDTM) and add them to
+//     fp32 registers with round-to-nearest while the tensor core already works on the other accumulator set (all 512 TMEM columns)
 //   * epilogue: the drain warps hold one output row per thread (TMEM lane == row), so consecutive lanes store consecutive rows of a
 //     column-major C: coalesced 128-byte stores
 // Everything else (Float64, Int32, Int64; Float32 operands whose base / leading dimension are not 16-byte aligned, which TMA cannot
@@ -113,10 +115,11 @@ int32_t launch_simt(dab_ctx* ctx, int transA, size_t m, size_t n, size_t k, cons
 constexpr int TG_M = 128, TG_N = 128, TG_K = 32, TG_STAGES = 3;
 constexpr int TG_TILE_BYTES = TG_M * TG_K * 4;                   // 16 KiB: one operand tile (128 x 32 fp32)
 constexpr int TG_STAGE_BYTES = 4 * TG_TILE_BYTES;                // A_hi, A_lo, B_hi, B_lo
-constexpr int TG_THREADS = 320;                                  // warp 0 TMA, warp 1 MMA, warps 2-5 convert, warps 6-9 drain/epilogue
+constexpr int TG_THREADS = 448;                                  // warp 0 TMA, warp 1 MMA, warps 2-5 convert, warps 6-13 drain/epilogue
+constexpr int TG_DRAIN_THREADS = 256;                            // two warps per TMEM lane quarter, 64 accumulator columns each
 constexpr int TG_BAR_OFFSET = TG_STAGES * TG_STAGE_BYTES;
 constexpr int TG_SMEM_BYTES = TG_BAR_OFFSET + 256 + 1024;        // + barriers + slack for the 1024-byte alignment of the swizzle atoms
-constexpr int TG_TMEM_COLS = 256;                                // two 128-column fp32 accumulators
+constexpr int TG_TMEM_COLS = 512;                                // two sets of {main, correction} 128-column fp32 accumulators
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -166,6 +169,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {   // 32 lanes x 16 consecutive fp32 columns (SASS LDTM.x16)
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
 __device__ __forceinline__ float4 split_tf32(float4& v) {   // v <- hi (tf32, round to nearest), returns lo = tf32(v - hi)
     float4 lo;
     uint32_t h;
@@ -204,7 +215,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32x3_kernel(const __grid
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar0 + 8 * (9 + a), 1);
-            mbar_init(bar0 + 8 * (11 + a), 128);
+            mbar_init(bar0 + 8 * (11 + a), TG_DRAIN_THREADS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -255,7 +266,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32x3_kernel(const __grid
                 mbar_wait(bar0 + 8 * (3 + s), ph);                                          // converted tiles are in place
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = sbase + s * TG_STAGE_BYTES, a_lo = a_hi + TG_TILE_BYTES, b_hi = a_hi + 2 * TG_TILE_BYTES, b_lo = a_hi + 3 * TG_TILE_BYTES;
-                const uint32_t d = tmem_base + acc * TG_N;
+                const uint32_t d = tmem_base + acc * (2 * TG_N), ds = d + TG_N;            // main (hi*hi) and correction accumulators of this set
 #pragma unroll
                 for (int j = 0; j < TG_K / 8; ++j) {
                     // A untransposed = "MN-major" (m contiguous).  For 32-bit operands the tensor core only takes MN-major tiles in the 128-byte
@@ -267,9 +278,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32x3_kernel(const __grid
                     const uint32_t albo = TA ? 16u : 4096u, asbo = TA ? 1024u : 512u, alay = TA ? 2u : 1u;
                     const uint64_t dah = umma_desc(a_hi + aoff, albo, asbo, alay), dal = umma_desc(a_lo + aoff, albo, asbo, alay);
                     const uint64_t dbh = umma_desc(b_hi + j * 32u, 16u, 1024u), dbl = umma_desc(b_lo + j * 32u, 16u, 1024u);
-                    umma_tf32(d, dal, dbh, idesc, (chunk_start && j == 0) ? 0u : 1u);       // small terms first
-                    umma_tf32(d, dah, dbl, idesc, 1u);
-                    umma_tf32(d, dah, dbh, idesc, 1u);
+                    const uint32_t first = (chunk_start && j == 0) ? 0u : 1u;
+                    umma_tf32(ds, dal, dbh, idesc, first);                                  // the two correction products (2^-11 of the main one) ...
+                    umma_tf32(ds, dah, dbl, idesc, 1u);                                     // ... sum in their own accumulator
+                    umma_tf32(d, dah, dbh, idesc, first);
                 }
                 umma_commit(bar0 + 8 * (6 + s));                                            // frees the smem stage when these MMAs have read it
                 if ((kb + 1) % kc_blocks == 0 || kb + 1 == nkb) umma_commit(bar0 + 8 * (9 + acc));   // partial tile complete
@@ -299,33 +311,29 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32x3_kernel(const __grid
             mbar_arrive(bar0 + 8 * (3 + s));
         }
     } else {
-        // ===== drain + epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; lane == output row =====
+        // ===== drain + epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; lane == output row; two warps share a lane quarter and take
+        // 64 of the 128 accumulator columns each (keeps the running fp32 sums in registers) =====
         const uint32_t quarter = (uint32_t)(warp & 3);
+        const uint32_t half = (uint32_t)(warp - 6) >> 2;
         const uint32_t row = m0 + quarter * 32 + lane;
-        float acc[TG_N];
+        constexpr int NC = TG_N / 2;
+        float acc[NC];
         const uint32_t nchunks = (nkb + kc_blocks - 1) / kc_blocks;
         for (uint32_t ch = 0; ch < nchunks; ++ch) {
             const uint32_t a = ch & 1u, use = ch >> 1;
             mbar_wait(bar0 + 8 * (9 + a), use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int c4 = 0; c4 < TG_N / 32; ++c4) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + a * TG_N + c4 * 32 + ((quarter * 32u) << 16);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                      "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                      "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                      "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
+            for (int c4 = 0; c4 < NC / 16; ++c4) {
+                uint32_t v[16], w[16];
+                const uint32_t taddr = tmem_base + a * (2 * TG_N) + half * NC + c4 * 16 + ((quarter * 32u) << 16);
+                tmem_ld16(taddr, v);                  // main partial (hi*hi)
+                tmem_ld16(taddr + TG_N, w);           // correction partial (lo*hi + hi*lo)
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float p = __uint_as_float(v[i]);
-                    acc[c4 * 32 + i] = ch == 0 ? p : __fadd_rn(acc[c4 * 32 + i], p);
+                for (int i = 0; i < 16; ++i) {
+                    const float p = __fadd_rn(__uint_as_float(v[i]), __uint_as_float(w[i]));
+                    acc[c4 * 16 + i] = ch == 0 ? p : __fadd_rn(acc[c4 * 16 + i], p);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -334,8 +342,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32x3_kernel(const __grid
         if (row < m) {
             float* crow = C + row;
 #pragma unroll
-            for (int j = 0; j < TG_N; ++j)
-                if (n0 + j < n) crow[(size_t)(n0 + j) * ldc] = nkb ? acc[j] : 0.0f;
+            for (int j = 0; j < NC; ++j) {
+                const uint32_t col = n0 + half * NC + j;
+                if (col < n) crow[(size_t)col * ldc] = nkb ? acc[j] : 0.0f;
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -389,7 +399,7 @@ int32_t launch_tf32x3(dab_ctx* ctx, int transA, size_t m, size_t n, size_t k, co
     if (st != DAB_OK) return st;
     const size_t gx = (m + TG_M - 1) / TG_M, gy = (n + TG_N - 1) / TG_N;
     if (gx > 0x7fffffffull || gy > 65535ull) return dab_fail(ctx, DAB_ERR_UNSUPPORTED, "dab_gemm: tile grid %zu x %zu too large", gx, gy);
-    long long kc = ctx->opt_gemm_kc > 0 ? ctx->opt_gemm_kc : 256;
+    long long kc = ctx->opt_gemm_kc > 0 ? ctx->opt_gemm_kc : 64;
     uint32_t kc_blocks = (uint32_t)((kc + TG_K - 1) / TG_K);
     if (kc_blocks < 1) kc_blocks = 1;
     {

@@ -304,6 +304,17 @@ int32_t dab_mailbox_create(dab_ctx* ctx, void* handle64);
 int32_t dab_mailbox_attach(dab_ctx* ctx, const void* handles, int32_t rank, int32_t nranks);
 int32_t dab_mailbox_detach(dab_ctx* ctx);
 
+/* Device-side barrier across the ranks, ordered on the ctx stream (needs the mailboxes above; a no-op for one rank): kernels queued
+ * after it start only when every rank's kernels queued before ITS call have completed.  The fence around one-sided peer reads / writes
+ * (the remotecall_wait of the reference) without a host synchronisation or an NCCL launch; a peer that never arrives surfaces as
+ * DAB_ERR_NCCL at the next dab_sync after "combine_timeout_ms". */
+int32_t dab_peer_barrier(dab_ctx* ctx);
+/* y = beta*y (fill!(0) when *beta == 0, untouched when 1), then y += alpha * stack[j*stride .. +n) for j = 0..count-1 in order, every
+ * multiply and add rounded separately: rmul!/fill! + add!(localpart(y), R[i,j], alpha) of mul! (src/linalg.jl:101-117, 62-76; also the
+ * between-phase of a sum over slabs) in one launch.  alpha, beta: host scalars of dtype (F32 F64 I32 I64). */
+int32_t dab_accumulate_stack(dab_ctx* ctx, int32_t dtype, void* y, size_t n, const void* beta, const void* alpha, const void* stack,
+                             size_t stride, int32_t count);
+
 /* ==== peer memory (one process per GPU): CUDA IPC handles, shipped by the host runtime ==== */
 int32_t dab_ipc_get_handle(dab_ctx* ctx, const void* dptr, void* handle64);
 int32_t dab_ipc_open(dab_ctx* ctx, const void* handle64, void** dptr);

@@ -767,6 +767,68 @@ def darray_matvec(A: ODArray, x: np.ndarray, trans: bool = False) -> ODArray:
     return darray_mul_vec(y, A, np.asarray(x), 1, 0, trans)
 
 
+def _tile_matmat(A: np.ndarray, B: np.ndarray, trans: bool) -> np.ndarray:
+    """``localpart(A)*Bjk`` / ``transpose(localpart(A))*Bjk`` (src/linalg.jl:218-226): BLAS gemm for floats (order unspecified ->
+    tolerance contract; restated in fp64, rounded once), the generic wrap-around loop for integers."""
+    M = A.T if trans else A
+    if A.dtype.kind == "f":
+        return np.asfortranarray((M.astype(np.float64) @ B.astype(np.float64)).astype(A.dtype))
+    with np.errstate(over="ignore"):
+        return np.asfortranarray(M @ B.astype(A.dtype))
+
+
+def darray_mul_mat(C: ODArray, A: ODArray, B: np.ndarray, alpha=1, beta=0, trans: bool = False) -> ODArray:
+    """``_matmatmul!(C::DMatrix, A::DMatrix, B::AbstractMatrix, α, β, tA)`` src/linalg.jl:189-257: tile products R[i,j,k] on
+    procs(A)[i,j] (``[j,i]`` for tA in 'T','C'), C scaled by β, then ``add!(localpart(C), R[i,j,k], α)`` on C.pids[i,k] (j order here;
+    the reference issues those adds as @async tasks)."""
+    B = np.asarray(B)
+    rd, cd = (1, 0) if trans else (0, 1)
+    mA, nA = A.dims[rd], A.dims[cd]
+    if B.shape[0] != nA:
+        raise ValueError("DimensionMismatch: matrix A has dimensions (%d, %d), matrix B has dimensions %s" % (mA, nA, B.shape))
+    if C.dims != (mA, B.shape[1]):
+        raise ValueError("DimensionMismatch: result C has dimensions %s, needs (%d, %d)" % (C.dims, mA, B.shape[1]))
+    if list(C.cuts[0]) != list(A.cuts[rd]):
+        raise ValueError("ArgumentError: cuts of the first dimension of the output matrix must match cuts of the input matrix")
+    gi, gj, gk = A.grid[rd], A.grid[cd], C.grid[1]
+    dt = C.chunks[0].dtype
+    out = [None] * len(C.chunks)
+    for k in range(gk):
+        clo, chi = C.cuts[1][k], C.cuts[1][k + 1] - 1
+        for i in range(gi):
+            lin_c = i + k * C.grid[0]
+            ci = C.chunks[lin_c].copy()
+            if beta != 1:
+                ci = (ci * dt.type(beta)).astype(dt) if beta != 0 else np.zeros_like(ci)
+            for j in range(gj):
+                lin = (j + i * A.grid[0]) if trans else (i + j * A.grid[0])
+                lo, hi = A.cuts[cd][j], A.cuts[cd][j + 1] - 1
+                r = _tile_matmat(A.chunks[lin], B[lo - 1:hi, clo - 1:chi], trans)
+                ci = _add_scaled(ci, r.astype(dt), alpha)
+            out[lin_c] = np.asfortranarray(ci)
+    return ODArray(C.dims, C.grid, C.pids, C.indices, C.cuts, out)
+
+
+def darray_matmat(A: ODArray, B: ODArray, trans: bool = False) -> ODArray:
+    """``A*B`` src/linalg.jl:285-292 and ``A'*B`` / ``transpose(A)*B`` :302-311 for DMatrix B: C over
+    ``procs(A)[:, 1:min(size(procs(A),2), size(procs(B),2))]`` with grid ``(size(procs(A),1), that min)`` -- for the transposed forms
+    ``procs(A)[1:min(size(procs(A),1), size(procs(B),2)), :]`` with grid ``(size(procs(A),2), that min)`` -- then ``mul!(C, A, B)``."""
+    g0, g1 = A.grid
+    pg = np.asarray(A.pids).reshape((g0, g1), order="F")
+    Bfull = to_array(B)
+    if not trans:
+        nc = min(g1, B.grid[1])
+        pids = list(pg[:, :nc].reshape(-1, order="F"))
+        Cl = make_layout((A.dims[0], B.dims[1]), pids, [g0, nc])
+    else:
+        nr = min(g0, B.grid[1])
+        pids = list(pg[:nr, :].reshape(-1, order="F"))
+        Cl = make_layout((A.dims[1], B.dims[1]), pids, [g1, nr])
+    dt = np.result_type(A.chunks[0].dtype, B.chunks[0].dtype)
+    Cl.chunks = [np.zeros(tuple(rlen(r) for r in ix), dtype=dt, order="F") for ix in Cl.indices]
+    return darray_mul_mat(Cl, A, Bfull, 1, 0, trans)
+
+
 def darray_transpose(D: ODArray) -> ODArray:
     """``copy(::Transpose{T,<:DArray{T,2}})`` / Adjoint for real T, src/linalg.jl:1-17:
     ``DArray(reverse(size(D)), procs(D)) do I; transpose!(lp, Array(D[reverse(I)...]))``."""

@@ -175,6 +175,54 @@ def _worker_level2_sort(rank, world, port, wpr, q):
                         yi = yi + 3 * p
                     assert np.array_equal(yi, want.chunks[i]), (grid, trans, i)
                 dist.barrier()
+        # ---- mul!(C, A, B, 3, 2) and its transposed form: tile results R[i,j,k] travel to the owners of C's chunks (i, k)
+        from darray_b200._linalg import matmat_exchange_plan
+        for grid in [(P, 1), (1, P)] + ([(2, 2)] if P == 4 else []):
+            for trans in (False, True):
+                A = rng.integers(-9, 9, (23, 17)).astype(np.int64)
+                rd, cd = (1, 0) if trans else (0, 1)
+                Bm = rng.integers(-9, 9, (A.shape[cd], 11)).astype(np.int64)
+                pids = list(range(1, P + 1))
+                L = dab.make_layout(A.shape, pids, list(grid))
+                oA = orc.distribute(A, procs=pids, dist=list(grid))
+                oB = orc.distribute(Bm, procs=pids, dist=[1, P])
+                oC = orc.darray_matmat(oA, oB, trans)                                          # layout of A*B as the reference builds it
+                C0 = rng.integers(-9, 9, oC.dims).astype(np.int64)
+                oC0 = orc.distribute(C0, procs=oC.pids, dist=list(oC.grid))
+                want = orc.darray_mul_mat(oC0, oA, Bm, 3, 2, trans)
+                CL = dab.make_layout(oC.dims, oC.pids, list(oC.grid))
+                assert CL.indices == oC.indices
+                g0 = grid[0]
+                gi, gj = (grid[1], grid[0]) if trans else grid
+                gk = oC.grid[1]
+                plan = matmat_exchange_plan(L, CL, trans, rank_of, rank)
+                tile = {}
+                for i in range(gi):
+                    for j in range(gj):
+                        lin = (j + i * g0) if trans else (i + j * g0)
+                        if rank_of(L.pids[lin]) == rank:
+                            lo, hi = L.cuts[cd][j], L.cuts[cd][j + 1] - 1
+                            for k in range(gk):
+                                clo, chi = CL.cuts[1][k], CL.cuts[1][k + 1] - 1
+                                tile[(i, j, k)] = orc._tile_matmat(oA.chunks[lin], Bm[lo - 1:hi, clo - 1:chi], trans)
+                stacks = {ik: [None] * gj for ik in plan["owned"]}
+                for i, j, k, rows, cols in plan["local"]:
+                    stacks[(i, k)][j] = tile[(i, j, k)]
+                reqs = [dist.isend(torch.from_numpy(np.ascontiguousarray(tile[(i, j, k)].reshape(-1, order="F"))), peer)
+                        for i, j, k, rows, cols, peer in plan["sends"]]
+                for i, j, k, rows, cols, peer in plan["recvs"]:
+                    buf = torch.empty(rows * cols, dtype=torch.int64)
+                    dist.recv(buf, peer)
+                    stacks[(i, k)][j] = buf.numpy().reshape((rows, cols), order="F")
+                for r in reqs:
+                    r.wait()
+                for (i, k), parts in stacks.items():
+                    lin_c = i + k * CL.grid[0]
+                    ci = 2 * oC0.chunks[lin_c]
+                    for p in parts:
+                        ci = ci + 3 * p
+                    assert np.array_equal(ci, want.chunks[lin_c]), (grid, trans, i, k)
+                dist.barrier()
         # ---- sort(d; sample=true)
         for n in (P, 1000, 30011):
             a = rng.integers(-10 ** 6, 10 ** 6, n).astype(np.int64)

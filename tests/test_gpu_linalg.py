@@ -137,8 +137,85 @@ def test_matvec_errors_and_reference_dot_test(dab, rt8):
     if list(y_bad.layout.cuts[0]) != list(DA.layout.cuts[0]):
         with pytest.raises(dab.ArgumentError):
             dab.mul_(y_bad, DA, b)
-    with pytest.raises(dab.UnsupportedError):
-        DA @ np.zeros((20, 3))                                                # matrix-matrix: not served yet, never a silent fallback
+    with pytest.raises(dab.DimensionMismatch):
+        DA @ np.zeros((21, 3))                                                # matrix-matrix: contracted sizes differ
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int64, np.int32])
+@pytest.mark.parametrize("grid", [None, (8, 1), (1, 8), (2, 4), (4, 2)])
+def test_matmatmul(dab, rt8, dtype, grid):
+    """``A*B``, ``A'*B``, ``transpose(A)*B`` and ``mul!(C, A, B, alpha, beta)`` (reference src/linalg.jl:189-311; reference tests
+    test/darray.jl:915-931, 996-1012): layout of the result (owners, grid, cuts) equals the oracle's, integer results exactly, float
+    results within the forward-error bound of the tile products (K12: tcgen05 3xTF32 for aligned Float32 tiles, SIMT otherwise)."""
+    rng = np.random.default_rng(47)
+    m, kdim, n = 96, 130, 72                               # 130 / 8 -> 17,17,16,... column blocks: unaligned leading dimensions too
+    mk = (lambda *s: rng.integers(-9, 9, s).astype(dtype)) if np.dtype(dtype).kind != "f" else (lambda *s: rng.standard_normal(s).astype(dtype))
+    A, At, B = mk(m, kdim), mk(kdim, m), mk(kdim, n)
+    tol = 4e-6 if dtype == np.float32 else 1e-13
+    for trans in (False, True):
+        H = At if trans else A
+        DA = dab.distribute(H, dist=grid)
+        oA = orc.distribute(H, nworkers=8) if grid is None else orc.distribute(H, procs=list(range(1, 9)), dist=list(grid))
+        for bgrid in (None, (1, 8), (8, 1)):
+            DB = dab.distribute(B, dist=bgrid)
+            oB = orc.distribute(B, nworkers=8) if bgrid is None else orc.distribute(B, procs=list(range(1, 9)), dist=list(bgrid))
+            W = dab.transpose(DA) if trans else DA
+            Cd = W @ DB
+            oC = orc.darray_matmat(oA, oB, trans)
+            assert Cd.layout.grid == tuple(oC.grid) and list(Cd.layout.pids) == oC.pids and list(Cd.layout.indices) == oC.indices
+            got, want = dab.to_array(Cd), orc.to_array(oC)
+            M = H.T if trans else H
+            if np.dtype(dtype).kind == "f":
+                bound = np.abs(M.astype(np.float64)) @ np.abs(B.astype(np.float64))
+                assert np.all(np.abs(got.astype(np.float64) - M.astype(np.float64) @ B.astype(np.float64)) <= tol * bound)
+                assert np.all(np.abs(got.astype(np.float64) - want) <= 2 * tol * bound)
+            else:
+                assert np.array_equal(got, want)
+        # mul!(C, A, B, alpha, beta) on an existing C with the layout of A*B; B as a host matrix
+        C0 = mk(M.shape[0], n)
+        Cd = dab.distribute(C0, procs=oC.pids, dist=list(oC.grid))
+        oC0 = orc.distribute(C0, procs=oC.pids, dist=list(oC.grid))
+        dab.mul_(Cd, dab.adjoint(DA) if trans else DA, B, 3, 2)
+        wantC = orc.to_array(orc.darray_mul_mat(oC0, oA, B, 3, 2, trans))
+        if np.dtype(dtype).kind == "f":
+            assert np.all(np.abs(dab.to_array(Cd) - wantC) <= 2 * tol * (3 * bound + 2 * np.abs(C0)))
+        else:
+            assert np.array_equal(dab.to_array(Cd), wantC)
+
+
+def test_matmatmul_reference_tests_and_errors(dab, rt8):
+    rng = np.random.default_rng(53)
+    A, B = rng.standard_normal((30, 30)), rng.standard_normal((30, 20))       # test/darray.jl:996-1012
+    DA, DB = dab.distribute(A), dab.distribute(B)
+    for W, want in ((DA, A @ B), (dab.transpose(DA), A.T @ B), (dab.adjoint(DA), A.T @ B)):
+        assert np.allclose(dab.to_array(W @ DB), want, rtol=1e-12, atol=1e-12)
+    A2 = rng.standard_normal((20, 20))                                        # test/darray.jl:915-931
+    B2 = rng.standard_normal((20, 20))
+    D2, E2 = dab.distribute(A2), dab.distribute(B2)
+    assert np.abs(dab.to_array(D2 @ E2) - A2 @ B2).max() < np.sqrt(np.finfo(np.float64).eps)
+    assert np.abs(dab.to_array(D2.T @ E2) - A2.T @ B2).max() < np.sqrt(np.finfo(np.float64).eps)
+    Cd = dab.dzeros((30, 20), procs=list(DA.layout.pids)[:DA.layout.grid[0]], dist=[DA.layout.grid[0], 1])
+    with pytest.raises(dab.DimensionMismatch):
+        dab.mul_(Cd, DA, np.zeros((31, 20)))
+    with pytest.raises(dab.DimensionMismatch):
+        dab.mul_(Cd, DA, np.zeros((30, 21)))
+    bad = dab.dzeros((30, 20), procs=[1, 2, 3], dist=[3, 1])
+    if list(bad.layout.cuts[0]) != list(DA.layout.cuts[0]):
+        with pytest.raises(dab.ArgumentError):
+            dab.mul_(bad, DA, B)
+
+
+def test_matmatmul_float32_tensor_core_tiles(dab, rt2):
+    """Chunks big and aligned enough for the tcgen05 path (2 workers -> 512 x 256 column blocks): 1e-6 relative on positive data."""
+    rng = np.random.default_rng(59)
+    A, B = rng.random((512, 512)).astype(np.float32), rng.random((512, 384)).astype(np.float32)
+    DA, DB = dab.distribute(A), dab.distribute(B)
+    want = A.astype(np.float64) @ B.astype(np.float64)
+    got = dab.to_array(DA @ DB)
+    assert got.dtype == np.float32 and float(np.abs(got - want).max() / np.abs(want).min()) <= 1e-6
+    gt = dab.to_array(DA.T @ DB)
+    wt = A.T.astype(np.float64) @ B.astype(np.float64)
+    assert float(np.abs(gt - wt).max() / np.abs(wt).min()) <= 1e-6
 
 
 @pytest.mark.parametrize("shape", [(100, 200), (200, 100), (7, 3), (1, 9), (64, 64), (257, 1031), (3, 1)])

@@ -119,6 +119,21 @@ def main():
             assert np.array_equal(dab.to_array(y2), got)
             dab.mul_(yv, W, xv, 2, 1)                           # y = 2*A*x + y
             assert np.all(np.abs(dab.to_array(yv) - 3 * want) <= 3e-6 * want)
+        # matrix-matrix: A*B, A'*B with B a DMatrix (blocks halo-fetched), mul!(C, A, B, 2, 1)
+        Bx = orc.rand_u01(31, 0, 157 * 64).reshape((157, 64), order="F")
+        Bt = orc.rand_u01(32, 0, 203 * 64).reshape((203, 64), order="F")
+        for trans, Bh in ((False, Bx), (True, Bt)):
+            W = dM.T if trans else dM
+            dBm = dab.distribute(Bh)
+            Cm = W @ dBm
+            oBm = orc.distribute(Bh, nworkers=P)
+            oCm = orc.darray_matmat(oM, oBm, trans)
+            assert list(Cm.layout.pids) == oCm.pids and list(Cm.layout.indices) == oCm.indices and Cm.layout.grid == tuple(oCm.grid)
+            wantm = (Mx.T if trans else Mx).astype(np.float64) @ Bh.astype(np.float64)
+            gotm = dab.to_array(Cm)
+            assert np.all(np.abs(gotm - wantm) <= 2e-6 * wantm), float(np.abs(gotm / wantm - 1).max())
+            dab.mul_(Cm, W, Bh, 2, 1)
+            assert np.all(np.abs(dab.to_array(Cm) - 3 * wantm) <= 6e-6 * wantm)
         Tm = dM.T.copy()
         oT = orc.darray_transpose(oM)
         assert list(Tm.layout.indices) == oT.indices and np.array_equal(dab.to_array(Tm), Mx.T)

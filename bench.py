@@ -425,7 +425,8 @@ def main():
             ms_d = max_over_ranks(ms_d)
             extras["sum_dims1"] = {"GBs": 4.0 * dimsA[0] * dimsA[1] * reps / (ms_d * 1e-3) / 1e9, "dims": list(dimsA), "grid": list(g),
                                    "ms": ms_d / reps, "bytes_per_elem": 4,
-                                   "what": "sum(A, dims=1): per-chunk column reduction + partial-slab exchange to the fibre owners (NCCL send/recv)"}
+                                   "what": "sum(A, dims=1): per-chunk column reduction + partial slabs PUT into the fibre owners' exchange arena over NVLink "
+                                           "+ device-side barrier + ordered accumulate (no NCCL launch, no host sync)"}
             if not args.no_parity:
                 R = dab.sum(A, dims=1)
                 parity["checks"]["sum_dims1"] = parity_sum_dims1(dab, rt, A, R, SEED + 1)
@@ -454,8 +455,8 @@ def main():
                 ms_m, _ = timed(lambda: (W @ v).close(), reps)
                 ms_m = max_over_ranks(ms_m)
                 extras[key] = {"GBs": 4.0 * dimsA[0] * dimsA[1] * reps / (ms_m * 1e-3) / 1e9, "ms": ms_m / reps, "bytes_per_elem": 4,
-                               "what": "mul!(y, A, x) on the sum_dims1 matrix: dab_gemv per chunk (fp64 carriers) + NCCL send/recv of the tile "
-                                       "results to the owners of y + ordered add!"}
+                               "what": "mul!(y, A, x) on the sum_dims1 matrix: x blocks halo-fetched (peer loads), dab_gemv per chunk (fp64 carriers), tile "
+                                       "results PUT into the y owners' exchange arena over NVLink, device-side barriers, one fused beta-scale + ordered add!"}
             xv.close()
             xt.close()
             A.close()

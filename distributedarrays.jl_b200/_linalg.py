@@ -170,17 +170,45 @@ def mul_(y: DArray, A: Union[DArray, Transpose], x, alpha=1, beta=0) -> DArray:
     g0, g1 = L.grid
     gi, gj = (g1, g0) if trans else (g0, g1)             # y chunks, tiles per y chunk
     cuts_c = L.cuts[cd]
-    if isinstance(x, DArray) and rt.world > 1:
+    isz, code = dt.itemsize, dab_dtype(dt)
+    ypids = y.layout.pids
+    remote_x = isinstance(x, DArray) and rt.world > 1
+    if remote_x:
         if x._handles is None:
-            x.share()
-        rt.barrier()
+            x.share()                                      # once per DVector: the CUDA-IPC handles of its chunks
+        rt.device_barrier()                                # x's producers (on their own streams) are done before anybody reads it
 
     def tile_pid(i, j):                                    # procs(A)[i,j]  /  procs(A)[j,i]
         return L.pids[(j + i * g0) if trans else (i + j * g0)]
 
-    # ---- R[i,j] = localpart(A) * xj on the tile owners (src/linalg.jl:90-98)
-    R: Dict[Tuple[int, int], B200Array] = {}
+    # ---- where the tile results are combined: per consumer rank, the stacks of its y chunks back to back (gj slots of plen each);
+    # every rank derives the same table, so a producer knows the slot of its tile inside the CONSUMER's arena bank
+    def stack_table(rank):
+        off, tab = 0, {}
+        for i in range(gi):
+            if rt.rank_of(ypids[i]) == rank:
+                tab[i] = off
+                off += (rlen(y.layout.indices[i][0]) * gj * isz + 255) & ~255
+        return tab, off
+
+    tables = {r: stack_table(r) for r in {rt.rank_of(p) for p in ypids}}
+    need = max(t[1] for t in tables.values())
+    use_arena = need <= rt.arena()["bank_bytes"] if rt.world > 1 else False
+    if use_arena:
+        bank = rt.arena_next_bank()
+        peers = rt.arena()["peers"]
+        my_base = peers[rt.rank] + bank
+        my_tab = tables.get(rt.rank, ({}, 0))[0]
+    else:                                                  # one rank (or stacks too large for the arena): private stacks + NCCL send/recv
+        my_tab, my_bytes = stack_table(rt.rank)
+        my_stack = B200Array.empty(rt, (max(my_bytes, 16),), np.uint8, temp=True)
+        my_base = my_stack.ptr
+
+    # ---- R[i,j] = localpart(A) * xj on the tile owners (src/linalg.jl:90-98); a tile whose consumer is this rank is written straight
+    # into its slot of the stack
+    temps: List[B200Array] = []
     xblocks: Dict[int, B200Array] = {}
+    puts, sends = [], []
     for j in range(gj):
         for i in range(gi):
             pid = tile_pid(i, j)
@@ -189,59 +217,50 @@ def mul_(y: DArray, A: Union[DArray, Transpose], x, alpha=1, beta=0) -> DArray:
             ch = M.chunks[pid]
             if j not in xblocks:
                 xblocks[j] = _x_block(rt, x, cuts_c[j], cuts_c[j + 1] - 1, dt)
-            nout = ch.shape[rd]
-            r = B200Array.empty(rt, (nout,), dt, temp=True)
-            _lib.call("dab_gemv", rt.ctx, dab_dtype(dt), 1 if trans else 0, C.c_void_p(ch.ptr), ch.shape[0], ch.shape[1],
-                      C.c_void_p(xblocks[j].ptr), C.c_void_p(r.ptr))
-            R[(i, j)] = r
-    # ---- ship the tile results to the owner of y's chunk i (the fetch(rij) of :113-115), all pairs in one grouped exchange
-    ypids = y.layout.pids
-    plan = matvec_exchange_plan(L, y.layout, trans, rt.rank_of, rt.rank)
-    stacks: Dict[int, B200Array] = {}
-    for i in plan["owned"]:
-        stacks[i] = B200Array.empty(rt, (rlen(y.layout.indices[i][0]) * gj,), dt, temp=True)
-    isz = dt.itemsize
-    local = plan["local"]
-    sends = [(R[(i, j)].ptr, plen * isz, peer) for i, j, plen, peer in plan["sends"]]
-    recvs = [(stacks[i].ptr + j * plen * isz, plen * isz, peer) for i, j, plen, peer in plan["recvs"]]
-    for i, j, plen in local:
-        if plen:
-            _lib.call("dab_d2d", rt.ctx, C.c_void_p(stacks[i].ptr + j * plen * dt.itemsize), C.c_void_p(R[(i, j)].ptr), plen * dt.itemsize)
-    sends = [s for s in sends if s[1]]
-    recvs = [r for r in recvs if r[1]]
-    if sends or recvs:
-        _lib.call("dab_group_start", rt.ctx)
-        for ptr, nb, peer in sends:
-            _lib.call("dab_send", rt.ctx, C.c_void_p(ptr), nb, peer)
-        for ptr, nb, peer in recvs:
-            _lib.call("dab_recv", rt.ctx, C.c_void_p(ptr), nb, peer)
-        _lib.call("dab_group_end", rt.ctx)
-    # ---- scale y (:101-111), then add!(localpart(y), R[i,j], α) for each j (:114-117; j order)
-    a_s = np.asarray(alpha, dtype=dt)
-    b_s = np.asarray(beta, dtype=dt)
-    for i, stack in stacks.items():
-        ych = y.chunks[ypids[i]]
-        plen = ych.size
-        if plen == 0:
-            continue
-        code = dab_dtype(dt)
-        if beta != 1:
-            if beta == 0:
-                z = np.zeros((), dtype=dt)
-                _lib.call("dab_fill", rt.ctx, code, C.c_void_p(ych.ptr), plen, C.c_void_p(z.ctypes.data))
+            plen = ch.shape[rd]
+            orank = rt.rank_of(ypids[i])
+            if orank == rt.rank:
+                rptr = my_base + my_tab[i] + j * plen * isz
             else:
-                _lib.call("dab_binary_scalar", rt.ctx, code, _lib.MUL, C.c_void_p(ych.ptr), C.c_void_p(ych.ptr),
-                          C.c_void_p(b_s.ctypes.data), 0, plen)
-        for j in range(gj):
-            rp = stack.ptr + j * plen * dt.itemsize
-            if alpha != 1:
-                _lib.call("dab_binary_scalar", rt.ctx, code, _lib.MUL, C.c_void_p(rp), C.c_void_p(rp), C.c_void_p(a_s.ctypes.data), 1, plen)
-            _lib.call("dab_binary", rt.ctx, code, _lib.ADD, C.c_void_p(ych.ptr), C.c_void_p(ych.ptr), C.c_void_p(rp), plen)
-    for t in list(R.values()) + list(xblocks.values()) + list(stacks.values()):
+                r = B200Array.empty(rt, (plen,), dt, temp=True)
+                temps.append(r)
+                rptr = r.ptr
+                if use_arena:
+                    puts.append((peers[orank] + bank + tables[orank][0][i] + j * plen * isz, rptr, plen * isz))
+                else:
+                    sends.append((rptr, plen * isz, orank))
+            _lib.call("dab_gemv", rt.ctx, code, 1 if trans else 0, C.c_void_p(ch.ptr), ch.shape[0], ch.shape[1], C.c_void_p(xblocks[j].ptr),
+                      C.c_void_p(rptr))
+    # ---- ship the tile results to the owner of y's chunk i (the fetch(rij) of :113-115)
+    if use_arena:
+        for dst, src, nb in puts:                          # one-sided puts over NVLink into the consumer's arena bank
+            if nb:
+                _lib.call("dab_d2d", rt.ctx, C.c_void_p(dst), C.c_void_p(src), nb)
+        rt.device_barrier()                                # every producer's puts have landed; also: every reader of x is done with it
+    elif rt.world > 1:
+        plan = matvec_exchange_plan(L, y.layout, trans, rt.rank_of, rt.rank)   # same (i, j) order on both sides of every pair
+        sends = [(ptr, nb, peer) for ptr, nb, peer in sends if nb]
+        recvs = [(my_base + my_tab[i] + j * plen * isz, plen * isz, peer) for i, j, plen, peer in plan["recvs"] if plen]
+        if sends or recvs:
+            _lib.call("dab_group_start", rt.ctx)
+            for ptr, nb, peer in sends:
+                _lib.call("dab_send", rt.ctx, C.c_void_p(ptr), nb, peer)
+            for ptr, nb, peer in recvs:
+                _lib.call("dab_recv", rt.ctx, C.c_void_p(ptr), nb, peer)
+            _lib.call("dab_group_end", rt.ctx)
+    # ---- scale y (:101-111), then add!(localpart(y), R[i,j], α) for each j (:114-117; j order) -- one fused launch per y chunk
+    a_s, b_s = np.asarray(alpha, dtype=dt), np.asarray(beta, dtype=dt)
+    for i, off in my_tab.items():
+        ych = y.chunks[ypids[i]]
+        if ych.size:
+            _lib.call("dab_accumulate_stack", rt.ctx, code, C.c_void_p(ych.ptr), ych.size, C.c_void_p(b_s.ctypes.data), C.c_void_p(a_s.ctypes.data),
+                      C.c_void_p(my_base + off), ych.size, gj)
+    for t in temps + list(xblocks.values()):
         t.free()
-    if isinstance(x, DArray) and rt.world > 1:
-        rt.sync()
-        rt.barrier()
+    if not use_arena:
+        my_stack.free()
+        if remote_x:
+            rt.device_barrier()                            # owners may not overwrite x before every reader's fetch has run
     return y
 
 

@@ -431,29 +431,55 @@ def mapreducedim(f: Optional[Callable], op, d: DArray, dims, init=None) -> DArra
         partial: Dict[int, B200Array] = {}
         for pid, ch in src.chunks.items():
             partial[pid] = reduce_chunk_dims(rt, ch, reg_in, opc, mapc, rdt)
-        # ---- phase 2: mapreducedim_between! (src/mapreduce.jl:71-81)
+        # ---- phase 2: mapreducedim_between! (src/mapreduce.jl:71-81): the partial slabs of a fibre are gathered on the owner of the R
+        # chunk, in grid order.  Multi-rank: one-sided puts over NVLink into the owner's exchange arena + a device-side barrier (no NCCL
+        # launch, no host sync); slabs too large for the arena, or DAB_FUSED_COMBINE=0, take the grouped ncclSend/ncclRecv path.
         Rchunks: Dict[int, B200Array] = {}
-        stacks: Dict[int, Tuple[B200Array, int, int]] = {}
+        isz = rdt.itemsize
+
+        def stack_table(rank):
+            off, tab = 0, {}
+            for rl, members in enumerate(fibres):
+                if rt.rank_of(Rpids[rl]) == rank:
+                    plen = int(np.prod(shape_of(Rindices[rl])))
+                    tab[rl] = (off, plen, len(members))
+                    off += (plen * len(members) * isz + 255) & ~255
+            return tab, off
+
+        tables = {r: stack_table(r) for r in {rt.rank_of(p) for p in Rpids}}
+        use_arena = rt.world > 1 and max(t[1] for t in tables.values()) <= rt.arena()["bank_bytes"]
+        my_tab, my_bytes = tables.get(rt.rank, ({}, 0))
+        priv = None
+        if use_arena:
+            bank = rt.arena_next_bank()
+            peers = rt.arena()["peers"]
+            my_base = peers[rt.rank] + bank
+        else:
+            priv = B200Array.empty(rt, (max(my_bytes, 16),), np.uint8, temp=True)
+            my_base = priv.ptr
         xp = exchange_plan(L, Rlayout, fibres, rt.rank_of, rt.rank)
-        for rl in xp["owned"]:
-            plen = int(np.prod(shape_of(Rindices[rl])))
-            stacks[rl] = (B200Array.empty(rt, (plen * len(fibres[rl]),), rdt, temp=True), plen, len(fibres[rl]))
         for rl, slot, mp in xp["local"]:
-            stack, plen, _ = stacks[rl]
-            _lib.call("dab_d2d", rt.ctx, C.c_void_p(stack.ptr + slot * plen * rdt.itemsize), C.c_void_p(partial[mp].ptr), plen * rdt.itemsize)
-        sends = [(partial[mp].ptr, partial[mp].size * rdt.itemsize, peer) for mp, peer, _ in xp["sends"]]
-        recvs = []
-        for rl, slot, _, peer in xp["recvs"]:
-            stack, plen, _ = stacks[rl]
-            recvs.append((stack.ptr + slot * plen * rdt.itemsize, plen * rdt.itemsize, peer))
-        if sends or recvs:
-            _lib.call("dab_group_start", rt.ctx)
-            for ptr, nb, peer in sends:
-                _lib.call("dab_send", rt.ctx, C.c_void_p(ptr), nb, peer)
-            for ptr, nb, peer in recvs:
-                _lib.call("dab_recv", rt.ctx, C.c_void_p(ptr), nb, peer)
-            _lib.call("dab_group_end", rt.ctx)
-        for rl, (stack, plen, nm) in stacks.items():
+            off, plen, _ = my_tab[rl]
+            if plen:
+                _lib.call("dab_d2d", rt.ctx, C.c_void_p(my_base + off + slot * plen * isz), C.c_void_p(partial[mp].ptr), plen * isz)
+        if use_arena:
+            for mp, peer, rl in xp["sends"]:
+                off, plen, _ = tables[peer][0][rl]
+                slot = fibres[rl].index(L.pids.index(mp))
+                if plen:
+                    _lib.call("dab_d2d", rt.ctx, C.c_void_p(peers[peer] + bank + off + slot * plen * isz), C.c_void_p(partial[mp].ptr), plen * isz)
+            rt.device_barrier()
+        else:
+            sends = [(partial[mp].ptr, partial[mp].size * isz, peer) for mp, peer, _ in xp["sends"]]
+            recvs = [(my_base + my_tab[rl][0] + slot * my_tab[rl][1] * isz, my_tab[rl][1] * isz, peer) for rl, slot, _, peer in xp["recvs"]]
+            if sends or recvs:
+                _lib.call("dab_group_start", rt.ctx)
+                for ptr, nb, peer in sends:
+                    _lib.call("dab_send", rt.ctx, C.c_void_p(ptr), nb, peer)
+                for ptr, nb, peer in recvs:
+                    _lib.call("dab_recv", rt.ctx, C.c_void_p(ptr), nb, peer)
+                _lib.call("dab_group_end", rt.ctx)
+        for rl, (off, plen, nm) in my_tab.items():
             owner = Rpids[rl]
             Rch = B200Array.empty(rt, shape_of(Rindices[rl]), rdt)
             acc = 0
@@ -463,10 +489,10 @@ def mapreducedim(f: Optional[Callable], op, d: DArray, dims, init=None) -> DArra
                           C.c_void_p(v.ctypes.data))
                 acc = 1
             # Base.mapreducedim!(identity, op, localpart(R), Bfull): accumulate the nm partial slabs, in grid order, onto R
-            _lib.call("dab_reducedim", rt.ctx, dab_dtype(rdt), opc, _lib.MAP_ID, C.c_void_p(stack.ptr), plen, nm, 1, C.c_void_p(Rch.ptr), acc)
+            _lib.call("dab_reducedim", rt.ctx, dab_dtype(rdt), opc, _lib.MAP_ID, C.c_void_p(my_base + off), plen, nm, 1, C.c_void_p(Rch.ptr), acc)
             Rchunks[owner] = Rch
-        for stack, _, _ in stacks.values():  # temporaries are freed in stream order
-            stack.free()
+        if priv is not None:
+            priv.free()
         for p in partial.values():
             p.free()
         return DArray(Rlayout, rdt, Rchunks, rt)

@@ -351,8 +351,8 @@ int32_t dab_accumulate_stack(dab_ctx* ctx, int32_t dtype, void* y, size_t n, con
     const int grid = dab_grid_for(ctx, (n + 255) / 256, 8);
 #define ACC(T)                                                                                                                       \
     {                                                                                                                                \
-        const T b = *(const T*)beta, a = *(const T*)alpha;                                                                           \
-        accumulate_stack_kernel<T><<<grid, 256, 0, ctx->stream>>>((T*)y, n, b, b == T(0) ? 0 : (b == T(1) ? 1 : 2), a, a == T(1), \
+        const T b = *(const T*)beta, a = *(const T*)alpha, zero = 0, one = 1;                                                        \
+        accumulate_stack_kernel<T><<<grid, 256, 0, ctx->stream>>>((T*)y, n, b, b == zero ? 0 : (b == one ? 1 : 2), a, a == one,     \
                                                                    (const T*)stack, stride, count);                                  \
         DAB_LAUNCHED(ctx);                                                                                                           \
         return DAB_OK;                                                                                                               \

@@ -142,6 +142,46 @@ int32_t copy_rows(dab_ctx* ctx, char* t, const char* s, size_t row_bytes, const 
     }
 }
 
+
+// ---- strided / vector-indexed views: gather ------------------------------------------------------------------------------------------
+// The piece of  Array(d[I...])  that lives in one chunk when some index is a StepRange or a Vector{Int} (reference src/darray.jl:661,
+// 798-820 with indexin_mask / restrict_indices :706-781).  Per dimension k the element offset of coordinate t is either affine
+// (t * stride[k]) or read from an index table (table[k][t]); source and destination each have their own.  Up to 8 dimensions.
+constexpr int GB_MAXD = 8;
+struct GatherGeom {
+    unsigned long long extent[GB_MAXD];
+    long long dst_stride[GB_MAXD], src_stride[GB_MAXD];          // elements; src may be negative (reversed StepRange)
+    const long long* dst_index[GB_MAXD];                          // device tables of element offsets, or nullptr
+    const long long* src_index[GB_MAXD];
+    int ndim;
+};
+
+template <typename U>
+__global__ void __launch_bounds__(256) gather_box_kernel(U* __restrict__ dst, const U* __restrict__ src, GatherGeom g, unsigned long long total) {
+    for (unsigned long long id = (unsigned long long)blockIdx.x * 256 + threadIdx.x; id < total; id += (unsigned long long)gridDim.x * 256) {
+        unsigned long long r = id;
+        long long doff = 0, soff = 0;
+#pragma unroll
+        for (int k = 0; k < GB_MAXD; ++k) {
+            if (k < g.ndim) {
+                const unsigned long long t = r % g.extent[k];
+                r /= g.extent[k];
+                doff += g.dst_index[k] ? g.dst_index[k][t] : (long long)t * g.dst_stride[k];
+                soff += g.src_index[k] ? g.src_index[k][t] : (long long)t * g.src_stride[k];
+            }
+        }
+        dst[doff] = src[soff];
+    }
+}
+
+template <typename U>
+int32_t launch_gather(dab_ctx* ctx, void* dst, const void* src, const GatherGeom& g, unsigned long long total) {
+    const int grid = dab_grid_for(ctx, (size_t)((total + 255) / 256), 16);
+    gather_box_kernel<U><<<grid, 256, 0, ctx->stream>>>((U*)dst, (const U*)src, g, total);
+    DAB_LAUNCHED(ctx);
+    return DAB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -207,6 +247,34 @@ int32_t dab_copy_box(dab_ctx* ctx, int32_t elem_bytes, void* dst, const size_t d
         return DAB_OK;
     }
     return copy_rows(ctx, t, s, row_bytes, e, spp, dpp);
+}
+
+int32_t dab_gather_box(dab_ctx* ctx, int32_t elem_bytes, int32_t ndim, void* dst, const long long* dst_strides, const void* const* dst_index,
+                       const void* src, const long long* src_strides, const void* const* src_index, const size_t* extent) {
+    DAB_ENTER(ctx);
+    DAB_REQUIRE(ctx, dst && src && extent && dst_strides && src_strides, DAB_ERR_ARG, "dab_gather_box: null pointer");
+    DAB_REQUIRE(ctx, ndim >= 1 && ndim <= GB_MAXD, DAB_ERR_UNSUPPORTED, "dab_gather_box: %d dimensions (served: 1..%d)", ndim, GB_MAXD);
+    GatherGeom g;
+    memset(&g, 0, sizeof(g));
+    g.ndim = ndim;
+    unsigned long long total = 1;
+    for (int k = 0; k < ndim; ++k) {
+        if (extent[k] == 0) return DAB_OK;
+        g.extent[k] = extent[k];
+        g.dst_stride[k] = dst_strides[k];
+        g.src_stride[k] = src_strides[k];
+        g.dst_index[k] = dst_index ? (const long long*)dst_index[k] : nullptr;
+        g.src_index[k] = src_index ? (const long long*)src_index[k] : nullptr;
+        total *= extent[k];
+    }
+    switch (elem_bytes) {
+        case 1: return launch_gather<uint8_t>(ctx, dst, src, g, total);
+        case 2: return launch_gather<uint16_t>(ctx, dst, src, g, total);
+        case 4: return launch_gather<uint32_t>(ctx, dst, src, g, total);
+        case 8: return launch_gather<unsigned long long>(ctx, dst, src, g, total);
+        case 16: return launch_gather<int4>(ctx, dst, src, g, total);
+        default: return dab_fail(ctx, DAB_ERR_ARG, "dab_gather_box: elem_bytes %d", elem_bytes);
+    }
 }
 
 }  // extern "C"

@@ -41,6 +41,7 @@ class Runtime:
         self._ipc_cache = {}
         self.last_kernel = None  # which entry point served the last local broadcast launch (diagnostics)
         self.fused_combine = False
+        self._arena = None
         if use_dist is None:
             use_dist = self.world > 1
         if use_dist and self.world > 1:
@@ -78,6 +79,40 @@ class Runtime:
         self.sync()
         if self.dist is not None:
             self.dist.barrier()
+
+    def device_barrier(self):
+        """Stream-ordered barrier across the ranks (``dab_peer_barrier``): later launches on this rank's stream start only after every
+        rank's earlier launches have completed -- the fence around one-sided peer reads / puts, without a host synchronisation.  Falls
+        back to the host barrier when the peer mailboxes are not attached (``DAB_FUSED_COMBINE=0``)."""
+        if self.world == 1:
+            return
+        if self.fused_combine:
+            _lib.call("dab_peer_barrier", self.ctx)
+        else:
+            self.barrier()
+
+    def arena(self, bank_bytes: int = 8 << 20):
+        """The exchange arena: two banks of device memory per rank, mapped by every other rank over CUDA IPC (collective on first use).
+        Small cross-worker payloads (tile results of ``mul!``, partial slabs of ``mapreducedim_between!``) are PUT straight into the
+        consumer's bank with device-to-device copies over NVLink and ordered by ``device_barrier`` -- no NCCL launch, no host sync.
+        Banks alternate per exchange, so a producer can fill the next bank while the consumer still reads the previous one."""
+        if self._arena is None:
+            ptr = self.alloc(2 * bank_bytes + 256)
+            base = (ptr + 255) & ~255
+            if self.world > 1:
+                handles = self.allgather_object((self.ipc_handle(ptr), base - ptr))
+                peers = [base if r == self.rank else self.ipc_open(h) + off for r, (h, off) in enumerate(handles)]
+            else:
+                peers = [base]
+            self._arena = {"alloc": ptr, "peers": peers, "bank_bytes": bank_bytes, "turn": 0}
+        return self._arena
+
+    def arena_next_bank(self) -> int:
+        """Byte offset of the bank the next exchange uses (every rank calls this once per exchange, in the same order)."""
+        a = self.arena()
+        off = (a["turn"] & 1) * a["bank_bytes"]
+        a["turn"] += 1
+        return off
 
     def allgather_object(self, obj) -> list:
         if self.dist is None:
@@ -184,6 +219,12 @@ class Runtime:
                 except _lib.DabError:
                     pass
             self._ipc_cache.clear()
+            if self._arena is not None:
+                try:
+                    _lib.call("dab_free", self.ctx, C.c_void_p(self._arena["alloc"]))
+                except _lib.DabError:
+                    pass
+                self._arena = None
             _lib.lib().dab_shutdown(self.ctx)
             self.ctx = None
         if self.dist is not None:

@@ -233,6 +233,14 @@ int32_t dab_reducedim(dab_ctx* ctx, int32_t dtype, int32_t op, int32_t map, cons
 int32_t dab_copy_box(dab_ctx* ctx, int32_t elem_bytes, void* dst, const size_t dst_shape[4], const size_t dst_off[4],
                      const void* src, const size_t src_shape[4], const size_t src_off[4], const size_t extent[4]);
 
+/* Strided and vector-indexed views: the piece of Array(d[I...]) held by one chunk when some index is a StepRange or a Vector{Int}
+ * (src/darray.jl:661, 798-820; indexin_mask / restrict_indices :706-781).  ndim <= 8.  Coordinate t of dimension k contributes
+ * t * dst_strides[k] (resp. src_strides[k], may be negative) ELEMENTS to the destination (source) offset, or, when dst_index[k]
+ * (src_index[k]) is non-NULL, the value table[k][t] of a device array of int64 element offsets.  dst / src point at the element of
+ * coordinate 0; src may be a peer mapping.  dst_index / src_index may be NULL (all affine). */
+int32_t dab_gather_box(dab_ctx* ctx, int32_t elem_bytes, int32_t ndim, void* dst, const long long* dst_strides, const void* const* dst_index,
+                       const void* src, const long long* src_strides, const void* const* src_index, const size_t* extent);
+
 /* ==== Level-2 linear algebra K9 (widening row f4; HBM-bound) ==============================
  * r = op(A) * x on ONE column-major chunk A (m x n, leading dimension m): trans = 0 -> r[m] = A x[n];
  * trans = 1 -> r[n] = A' x[m].  Replaces  localpart(A)*convert(localtype(x), xj)  (src/linalg.jl:95-97)

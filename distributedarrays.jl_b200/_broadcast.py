@@ -517,8 +517,30 @@ def _finish_remote_reads(rt, had_remote: bool):
         rt.barrier()
 
 
+def _materialise_views(args):
+    """SubDArray arguments (``a .= 3 .+ abs2.(view(d, ...))``) enter a broadcast as ``DArray(view)`` (reference src/darray.jl:603-609):
+    a halo read into a fresh DArray with the default layout, released when the broadcast has been launched."""
+    from ._darray import SubDArray
+    out, temps = [], []
+    for a in args:
+        if isinstance(a, SubDArray):
+            a = a.to_darray()
+            temps.append(a)
+        out.append(a)
+    return out, temps
+
+
 def broadcast_into(dest: DArray, f: Callable, *args) -> DArray:
     """``dest .= f.(args...)``: ``Base.copyto!(dest::DArray, bc::Broadcasted{Nothing})`` (reference src/broadcast.jl:65-85)."""
+    args, _views = _materialise_views(args)
+    try:
+        return _broadcast_into(dest, f, *args)
+    finally:
+        for v in _views:
+            v.close()
+
+
+def _broadcast_into(dest: DArray, f: Callable, *args) -> DArray:
     shapes = [a.dims if isinstance(a, DArray) else (a.shape if isinstance(a, np.ndarray) else ()) for a in args]
     # materialize!(dest, bc) instantiates the Broadcasted with axes(dest): every argument must be broadcastable TO dest's axes
     # (each of its dims is 1 or equals dest's; missing trailing dims count as 1), else DimensionMismatch (src/broadcast.jl:66)
@@ -544,6 +566,15 @@ def broadcast_into(dest: DArray, f: Callable, *args) -> DArray:
 def broadcast(f: Callable, *args, rt=None) -> DArray:
     """``f.(args...)`` allocating: ``Base.copy(bc::Broadcasted{<:DArrayStyle})`` (reference src/broadcast.jl:91-98).
     The result gets the DEFAULT layout for its size, not the arguments' (src/darray.jl:174)."""
+    args, _views = _materialise_views(args)
+    try:
+        return _broadcast(f, *args, rt=rt)
+    finally:
+        for v in _views:
+            v.close()
+
+
+def _broadcast(f: Callable, *args, rt=None) -> DArray:
     rt = rt or next((a.rt for a in args if isinstance(a, DArray)), None) or runtime()
     shapes = [a.dims if isinstance(a, DArray) else (a.shape if isinstance(a, np.ndarray) else ()) for a in args]
     dims = _bc_shape(shapes)

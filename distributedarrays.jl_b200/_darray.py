@@ -259,7 +259,7 @@ class DArray:
                 raise RuntimeError("ErrorException: scalar indexing disabled")  # src/darray.jl:640
             J = tuple((int(k) % s + 1, int(k) % s + 1) if -s <= int(k) < s else _oob(k, s) for k, s in zip(key, self.dims))
             return SubDArray(self, J, tuple(True for _ in key)).to_numpy()[()]
-        J, drop = [], []
+        J, drop, idx = [], [], []
         for k, s in zip(key, self.dims):
             if isinstance(k, (int, np.integer)):
                 kk = int(k)
@@ -268,15 +268,28 @@ class DArray:
                 kk %= s
                 J.append((kk + 1, kk + 1))
                 drop.append(True)
+                idx.append(None)
             elif isinstance(k, slice):
                 lo, hi, st = k.indices(s)
-                if st != 1:
-                    raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "strided (step != 1) views are not served by the B200 backend")
-                J.append((lo + 1, max(lo, hi)))
+                if st == 1:
+                    J.append((lo + 1, max(lo, hi)))
+                    idx.append(None)
+                else:                                      # StepRange (src/darray.jl:661): 1-based global indices lo+1 : st : ...
+                    v = np.arange(lo, hi, st, dtype=np.int64) + 1
+                    J.append((int(v.min()), int(v.max())) if v.size else (1, 0))
+                    idx.append(v)
+                drop.append(False)
+            elif isinstance(k, (list, np.ndarray)) and np.asarray(k).ndim == 1 and (np.asarray(k).size == 0 or np.asarray(k).dtype.kind in "iu"):
+                v = np.asarray(k, dtype=np.int64)          # Vector{Int} (0-based here, like every Python index)
+                if v.size and (v.min() < -s or v.max() >= s):
+                    _oob(int(v.max() if v.max() >= s else v.min()), s)
+                v = np.where(v < 0, v + s, v) + 1
+                J.append((int(v.min()), int(v.max())) if v.size else (1, 0))
+                idx.append(v)
                 drop.append(False)
             else:
                 raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"index type {type(k).__name__} is not served by the B200 backend")
-        return SubDArray(self, tuple(J), tuple(drop))
+        return SubDArray(self, tuple(J), tuple(drop), tuple(idx) if builtins_any(i is not None for i in idx) else None)
 
     def __array__(self, dtype=None, copy=None):
         a = to_array(self)
@@ -317,25 +330,68 @@ class DArray:
         return Transpose(self)
 
 
+builtins_any = any
+
+
 def _oob(k, s):
     raise IndexError(f"BoundsError: index {k} out of range for dimension of size {s}")
 
 
 class SubDArray:
-    """``view(d, I...)`` with unit ranges (reference src/darray.jl:65, 661).  ``J`` are 1-based inclusive ranges."""
+    """``view(d, I...)`` (reference src/darray.jl:65, 661).  Every index is an Int (dropped dim), a unit range, a StepRange or a
+    Vector{Int}.  ``J`` are the 1-based inclusive bounding ranges; ``idx[k]`` is ``None`` for a unit range (then ``J[k]`` IS the
+    index) or the int64 vector of 1-based global indices of a strided / vector-indexed dim."""
 
-    def __init__(self, parent: DArray, J: Tuple[Range, ...], drop: Tuple[bool, ...]):
+    def __init__(self, parent: DArray, J: Tuple[Range, ...], drop: Tuple[bool, ...], idx: Optional[Tuple] = None):
         self.parent, self.J, self.drop = parent, J, drop
+        self.idx = idx if idx is not None else tuple(None for _ in J)
+
+    @property
+    def unit(self) -> bool:
+        return all(i is None for i in self.idx)
+
+    @property
+    def full_shape(self):
+        return tuple(rlen(j) if ix is None else int(ix.size) for j, ix in zip(self.J, self.idx))
 
     @property
     def shape(self):
-        return tuple(rlen(j) for j, d in zip(self.J, self.drop) if not d)
+        return tuple(n for n, d in zip(self.full_shape, self.drop) if not d)
+
+    dims = shape
+
+    @property
+    def dtype(self):
+        return self.parent.dtype
+
+    def index_vectors(self):
+        """1-based global indices per dim (unit ranges expanded)."""
+        return [np.arange(j[0], j[1] + 1, dtype=np.int64) if ix is None else ix for j, ix in zip(self.J, self.idx)]
+
+    def restrict(self, R: Sequence[Range]) -> "SubDArray":
+        """``view(s, R...)`` in the coordinates of the (undropped) view: ``Base.reindex(SD.indices, I)`` of the reference
+        (src/darray.jl:606).  ``R`` holds one 1-based inclusive range per KEPT dim."""
+        J, idx, it = [], [], iter(R)
+        for j, ix, dr in zip(self.J, self.idx, self.drop):
+            if dr:
+                J.append(j)
+                idx.append(None)
+                continue
+            lo, hi = next(it)
+            if ix is None:
+                J.append((j[0] + lo - 1, j[0] + hi - 1))
+                idx.append(None)
+            else:
+                v = ix[lo - 1:hi]
+                J.append((int(v.min()), int(v.max())) if v.size else (1, 0))
+                idx.append(v)
+        return SubDArray(self.parent, tuple(J), self.drop, tuple(idx))
 
     def to_device(self, rt: Optional[Runtime] = None) -> B200Array:
         """Dense device copy of the view on the calling rank's GPU: the halo read (src/darray.jl:584-602, 798-820)."""
         d = self.parent
         rt = rt or d.rt
-        out = B200Array.empty(rt, tuple(rlen(j) for j in self.J), d.dtype)
+        out = B200Array.empty(rt, self.full_shape, d.dtype)
         return self.copy_to(out)
 
     def copy_to(self, out: B200Array) -> B200Array:
@@ -343,9 +399,13 @@ class SubDArray:
         peer-load copy kernel per intersecting chunk, asynchronous on the ctx stream."""
         d = self.parent
         rt = out.rt
-        full_shape = tuple(rlen(j) for j in self.J)
+        full_shape = self.full_shape
         if out.size != int(np.prod(full_shape)) or out.dtype != d.dtype:
             raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"destination {out.shape}/{out.dtype} vs view {full_shape}/{d.dtype}")
+        if out.size == 0:
+            return out
+        if not self.unit or d.ndim > 4:
+            return self._gather_to(out)
         for piece in slab_plan(d.layout, self.J):
             pid = d.layout.pids[piece.chunk]
             src_ptr = d.peer_ptr(pid)
@@ -353,6 +413,78 @@ class SubDArray:
             _lib.call("dab_copy_box", rt.ctx, d.dtype.itemsize, C.c_void_p(out.ptr), _lib.sz4(full_shape),
                       _lib.sz4([r[0] - 1 for r in piece.dst] + [0] * (4 - len(piece.dst))), C.c_void_p(src_ptr), _lib.sz4(src_shape),
                       _lib.sz4([r[0] - 1 for r in piece.src] + [0] * (4 - len(piece.src))), _lib.sz4([rlen(r) for r in piece.src]))
+        return out
+
+    def _gather_to(self, out: B200Array) -> B200Array:
+        """StepRange / Vector{Int} indices (and views of arrays with more than 4 dims): per chunk, the positions of the view that fall
+        into the chunk (``indexin_mask``, src/darray.jl:706-710) and their local source indices; affine runs are passed as strides,
+        anything else as small device index tables (``dab_gather_box``)."""
+        d = self.parent
+        rt = out.rt
+        N = d.ndim
+        if N > 8:
+            raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "views of arrays with more than 8 dimensions are not served")
+        iv = self.index_vectors()
+        dstr = np.cumprod([1] + [len(v) for v in iv[:-1]]).astype(np.int64)
+        isz = d.dtype.itemsize
+        tables: List[B200Array] = []
+        for c, Kc in enumerate(d.layout.indices):
+            sel = [np.nonzero((v >= k[0]) & (v <= k[1]))[0] for v, k in zip(iv, Kc)]
+            if builtins_any(s.size == 0 for s in sel):
+                continue
+            sshape = shape_of(Kc)
+            sstr = np.cumprod([1] + list(sshape[:-1])).astype(np.int64)
+            dbase = sbase = 0
+            ds, ss, di, si, ext = [], [], [], [], []
+            for k in range(N):
+                doff = sel[k].astype(np.int64) * dstr[k]
+                soff = (iv[k][sel[k]] - Kc[k][0]) * sstr[k]
+                dbase += int(doff[0])
+                sbase += int(soff[0])
+                doff, soff = doff - doff[0], soff - soff[0]
+                ext.append(len(doff))
+                for off, strides, tabs in ((doff, ds, di), (soff, ss, si)):
+                    step = int(off[1]) if len(off) > 1 else 0
+                    if len(off) <= 1 or np.array_equal(off, step * np.arange(len(off), dtype=np.int64)):
+                        strides.append(step)
+                        tabs.append(None)
+                    else:
+                        t = B200Array.from_numpy(rt, np.ascontiguousarray(off, dtype=np.int64))
+                        tables.append(t)
+                        strides.append(0)
+                        tabs.append(t.ptr)
+            pid = d.layout.pids[c]
+            LL, VP = C.c_longlong * N, C.c_void_p * N
+            _lib.call("dab_gather_box", rt.ctx, isz, N, C.c_void_p(out.ptr + dbase * isz), LL(*ds), VP(*di), C.c_void_p(d.peer_ptr(pid) + sbase * isz),
+                      LL(*ss), VP(*si), (C.c_size_t * N)(*ext))
+        for t in tables:
+            t.free()                                           # stream-ordered
+        return out
+
+    def to_darray(self) -> DArray:
+        """``DArray(SD::SubDArray)`` (reference src/darray.jl:603-609): a new DArray of ``size(SD)`` on ``procs(D)`` with the default
+        distribution; every chunk is ``Array(D[reindex(SD.indices, I)...])`` -- here a halo read straight into the new localpart."""
+        d = self.parent
+        rt = d.rt
+        shape = self.shape
+        remote = rt.world > 1
+        if remote:
+            if d._handles is None:
+                d.share()
+            rt.device_barrier()
+
+        def init(I):
+            ch = B200Array.empty(rt, shape_of(I), d.dtype)
+            if ch.size:
+                sub = self.restrict(I)
+                sub.copy_to(B200Array(rt, ch.ptr, sub.full_shape, d.dtype, own=False))
+            return ch
+
+        if len(shape) == 0:
+            raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "DArray of a zero-dimensional view")
+        out = darray(init, shape, procs=list(d.layout.pids), dtype=d.dtype, rt=rt)
+        if remote:
+            rt.device_barrier()
         return out
 
     def to_numpy(self) -> np.ndarray:
@@ -365,6 +497,31 @@ class SubDArray:
     def __array__(self, dtype=None, copy=None):
         a = self.to_numpy()
         return a.astype(dtype) if dtype is not None else a
+
+    def __getitem__(self, key):
+        """``view(s, I...)`` of a view composes into a view of the parent (Base.reindex)."""
+        if not isinstance(key, tuple):
+            key = (key,)
+        kept = [k for k, dr in enumerate(self.drop) if not dr]
+        if len(key) != len(kept):
+            raise IndexError(f"expected {len(kept)} indices")
+        iv = self.index_vectors()
+        full = list(self.parent.dims)
+        pkey = [None] * len(full)
+        for k, dr in enumerate(self.drop):
+            if dr:
+                pkey[k] = self.J[k][0] - 1
+        for k, sub in zip(kept, key):
+            v = iv[k] - 1                                     # 0-based global indices of this dim of the view
+            if isinstance(sub, (int, np.integer)):
+                pkey[k] = int(v[sub])
+            else:
+                w = v[sub]
+                if isinstance(sub, slice) and w.size and np.array_equal(w, np.arange(w[0], w[0] + w.size)):
+                    pkey[k] = slice(int(w[0]), int(w[0]) + int(w.size))
+                else:
+                    pkey[k] = np.asarray(w, dtype=np.int64)
+        return self.parent[tuple(pkey)]
 
 
 # ---- constructors --------------------------------------------------------------------------------------------------------

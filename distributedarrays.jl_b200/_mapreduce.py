@@ -227,7 +227,16 @@ def reduce(op, d: DArray, dims=None, init=None):
 
 def mapreduce(f: Optional[Callable], op, d: DArray, *ds, dims=None, init=None, _partials: bool = False):
     """``mapreduce(f, op, d::DArray, ds...[; dims, init])`` (reference src/mapreduce.jl:29-35 and :42-94).  With extra arguments
-    (same-size DArrays / arrays / scalars) ``f`` takes one value per argument: ``mapreduce(*, +, x, y)`` is ``dot(x, y)``."""
+    (same-size DArrays / arrays / scalars) ``f`` takes one value per argument: ``mapreduce(*, +, x, y)`` is ``dot(x, y)``.
+    A ``SubDArray`` is reduced through ``DArray(d)`` exactly as the reference does (src/mapreduce.jl:36)."""
+    from ._darray import SubDArray
+    if isinstance(d, SubDArray):
+        tmp = d.to_darray()
+        try:
+            return mapreduce(f, op, tmp, *ds, dims=dims, init=init, _partials=_partials)
+        finally:
+            if dims is None:
+                tmp.close()
     if dims is None:
         if init is not None:
             raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "mapreduce(f, op, d; init) without dims falls back to scalar iteration in the reference; not served")
@@ -254,6 +263,13 @@ def minimum(d: DArray, f: Optional[Callable] = None, dims=None):
 
 
 def _pred_reduce(opc: int, d: DArray, f: Optional[Callable]):
+    from ._darray import SubDArray
+    if isinstance(d, SubDArray):
+        tmp = d.to_darray()
+        try:
+            return _pred_reduce(opc, tmp, f)
+        finally:
+            tmp.close()
     if f is None:
         if d.dtype != np.dtype(np.bool_):
             raise TypeError("TypeError: non-boolean used in boolean context")
@@ -282,6 +298,13 @@ def count(d: DArray, f: Optional[Callable] = None) -> int:
 def extrema(d: DArray):
     """``extrema(d)`` (reference src/mapreduce.jl:124-131): per-chunk (min, max) in ONE pass over the chunk, then the fold
     ``(t, s) -> (min(t[1], s[1]), max(t[2], s[2]))`` over the workers in procs order."""
+    from ._darray import SubDArray
+    if isinstance(d, SubDArray):
+        tmp = d.to_darray()
+        try:
+            return extrema(tmp)
+        finally:
+            tmp.close()
     if d.dtype == np.dtype(np.bool_):
         return (_mapreduce_all(None, _lib.MIN, d), _mapreduce_all(None, _lib.MAX, d))
     _check_nonempty(d, _lib.MAX)
@@ -545,6 +568,18 @@ def rmul_(x: DArray, a) -> DArray:
 def isequal(d: DArray, other) -> bool:
     """``d == a`` (reference src/darray.jl:403-414): sizes equal and every localpart equal to the matching slice -- one fused
     ``all(x .== y)`` pass per chunk."""
+    from ._darray import SubDArray
+    if isinstance(d, SubDArray) or isinstance(other, SubDArray):
+        a = d.to_darray() if isinstance(d, SubDArray) else d
+        b = other.to_darray() if isinstance(other, SubDArray) else other
+        if not isinstance(a, DArray):
+            a, b = b, a
+        try:
+            return isequal(a, b)
+        finally:
+            for t, o in ((a, d), (b, other)):
+                if isinstance(o, SubDArray):
+                    t.close()
     shape = other.dims if isinstance(other, DArray) else tuple(np.shape(other))
     if tuple(shape) != tuple(d.dims):
         return False

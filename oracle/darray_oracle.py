@@ -297,6 +297,46 @@ def getindex_array(d: ODArray, J: Sequence[Range]) -> np.ndarray:
     return out
 
 
+def getindex_general(d: ODArray, I: Sequence) -> np.ndarray:
+    """``Array(d[I...])`` for any mix of Int, UnitRange ``(lo, hi)``, StepRange / Vector{Int} (1-D int arrays of 1-based indices):
+    ``setindex!(a::Array, s::SubDArray, I...)`` src/darray.jl:798-820, chunk by chunk --
+    ``K_mask = map(indexin_mask, J, K_c)`` (:807, which positions of J fall into the chunk), ``idxs = restrict_indices(Inew, K_mask)``
+    (:808, where they land in ``a``), ``localidxs = K .- (first(K_c) - 1)`` (:813) and ``a[idxs...] = localpart(d)[localidxs...]`` (:814).
+    Scalar indices drop their dimension (view semantics)."""
+    J, drop = [], []
+    for ix in I:
+        if isinstance(ix, (int, np.integer)):
+            J.append(np.array([int(ix)], dtype=np.int64))
+            drop.append(True)
+        elif isinstance(ix, tuple):
+            J.append(np.arange(ix[0], ix[1] + 1, dtype=np.int64))
+            drop.append(False)
+        else:
+            J.append(np.asarray(ix, dtype=np.int64))
+            drop.append(False)
+    for j, n in zip(J, d.dims):
+        if j.size and (j.min() < 1 or j.max() > n):
+            raise IndexError("BoundsError")
+    a = np.empty([len(j) for j in J], dtype=d.chunks[0].dtype, order="F")
+    for c, Kc in enumerate(d.indices):
+        masks = [(j >= k[0]) & (j <= k[1]) for j, k in zip(J, Kc)]                # indexin_mask(J, K_c)
+        if any(not m.any() for m in masks):
+            continue
+        idxs = [np.nonzero(m)[0] for m in masks]                                    # restrict_indices: positions inside a
+        local = [j[m] - k[0] for j, m, k in zip(J, masks, Kc)]                      # 0-based local indices in the chunk
+        a[np.ix_(*idxs)] = d.chunks[c][np.ix_(*local)]
+    return a[tuple(0 if dr else slice(None) for dr in drop)]
+
+
+def darray_from_view(d: ODArray, I: Sequence) -> ODArray:
+    """``DArray(SD::SubDArray)`` src/darray.jl:603-609: ``DArray(size(SD), procs(D)) do I; convert(Array, D[reindex(SD.indices, I)...])``
+    -- default distribution of the view's size over procs(D); chunk values = the matching block of the gathered view."""
+    full = getindex_general(d, I)
+    out = make_layout(full.shape, d.pids)
+    out.chunks = [np.asfortranarray(full[tuple(slice(lo - 1, hi) for lo, hi in ix)]) for ix in out.indices]
+    return out
+
+
 # --------------------------------------------------------------------------
 # Scalar semantics of Julia Base used on the path (Appendix A of SURVEY.md)
 # --------------------------------------------------------------------------

@@ -283,3 +283,25 @@ def test_c1_fixture_map_and_sum():
     assert s.dtype == np.float32 and s == np.float32(parts[0] + parts[1])
     exact = 2 * orc.rand_u01_ksum(1234, 0, 1 << 20) * 2.0 ** -24 + (1 << 20)
     assert abs(float(s) - exact) <= 1e-6 * exact
+
+
+def test_oracle_general_views_match_numpy_and_reference_slices():
+    """getindex_general (StepRange / Vector{Int} / Int indices, src/darray.jl:661, 798-820) against NumPy fancy indexing on the gathered
+    array -- the comparison every reference view test makes (test/darray.jl:185-218, 740-757) -- including the reference's own slices."""
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((200, 200))
+    d = orc.distribute(A, procs=[1, 2], dist=[1, 2])
+    assert np.array_equal(orc.getindex_general(d, [(1, 150), (1, 150)]), A[:150, :150])          # D[1:150, 1:150]
+    assert np.array_equal(orc.getindex_general(d, [4, (23, 176)]), A[3, 22:176])                  # D[4, 23:176]
+    assert np.array_equal(orc.getindex_general(d, [(23, 176), 197]), A[22:176, 196])              # D[23:176, 197]
+    B = rng.standard_normal((37, 29, 5))
+    e = orc.distribute(B, nworkers=8)
+    for I, np_ix in [([np.arange(1, 38, 3), (2, 20), 2], np.ix_(np.arange(0, 37, 3), np.arange(1, 20), [1])),
+                     ([np.array([5, 1, 30, 17]), np.arange(29, 0, -2), (1, 5)], np.ix_([4, 0, 29, 16], np.arange(28, -1, -2), np.arange(5))),
+                     ([(1, 37), np.array([], dtype=np.int64), (1, 5)], np.ix_(np.arange(37), [], np.arange(5)))]:
+        got = orc.getindex_general(e, I)
+        want = B[np_ix]
+        want = want.reshape([n for n, ix in zip(want.shape, I) if not isinstance(ix, (int, np.integer))])
+        assert got.shape == want.shape and np.array_equal(got, want)
+    v = orc.darray_from_view(d, [(1, 5), (5, 8)])                                                 # test/darray.jl:759-771
+    assert v.dims == (5, 4) and np.array_equal(orc.to_array(v), A[:5, 4:8])

@@ -169,6 +169,16 @@ def _d2h_window(dab, rt, chunk, off, n):
     return out
 
 
+def _sum_of(dab, rt, arr, n):
+    """sum of a raw device array through the C ABI (dab_reduce_host)."""
+    import ctypes as C
+
+    import numpy as np
+    out = np.zeros(2, dtype=np.uint64)
+    dab._lib.call("dab_reduce_host", rt.ctx, dab._lib.F32, dab._lib.SUM, dab._lib.MAP_ID, None, C.c_void_p(arr.ptr), n, C.c_void_p(out.ctypes.data))
+    return out.view(np.float32)[0]
+
+
 def parity_hot_path(dab, rt, x, y, n_per, world):
     """Checks of the timed step's outputs against exact ground truth (every rank takes part; rank 0 reports).
 
@@ -393,9 +403,25 @@ def main():
             e2e_step()
         ms_e, _ = timed(e2e_step, e2e_steps)
         ms_e = max_over_ranks(ms_e)
+        # the bound of this leg: the step moves 4 B/element over PCIe and is credited 12 B/element, so e2e <= 3 x the H2D rate; measured
+        # beside it: the pinned H2D rate alone and the pipelined pageable path (dab_h2d staging) on 1 GiB
+        lp = dab.localpart(x)
+        ms_c, _ = timed(lambda: lp.copy_from_host(hx, sync=False), 2, warm=1)
+        ms_c = max_over_ranks(ms_c)
+        pg = np.empty(1 << 28, dtype=np.float32)
+        pg[:] = 0.5
+        lpv = dab.B200Array(rt, lp.ptr, (1 << 28,), np.float32, own=False)
+        ms_p, _ = timed(lambda: lpv.copy_from_host(pg, sync=False), 2, warm=1)
+        ms_p = max_over_ranks(ms_p)
+        del pg
+        h2d = 4.0 * n_per * 2 / (ms_c * 1e-3) / 1e9
         e2e = {"value": 12.0 * N * e2e_steps / (ms_e * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 4 * N,
                "d2h_bytes_per_step": 16 * world, "ms_per_step": ms_e / e2e_steps,
-               "path": "copyto!(x::DArray, host Array) [pinned H2D] -> y .= a.*x .+ b -> sum(y) -> host scalar"}
+               "path": "copyto!(x::DArray, host Array) [pinned H2D] -> y .= a.*x .+ b -> sum(y) -> host scalar",
+               "h2d_pinned_GBs_per_gpu": h2d, "h2d_pageable_pipelined_GBs_per_gpu": 4.0 * (1 << 28) * 2 / (ms_p * 1e-3) / 1e9,
+               "bound": f"PCIe-bound: 4 of the 12 credited bytes/element cross the host link, so e2e <= 3 x H2D = {3 * h2d * world:.0f} GB/s at "
+                        f"{world} GPU(s); the device part of the step is {ms / args.steps:.2f} ms of the {ms_e / e2e_steps:.1f} ms. A CPU worker pool "
+                        "streams the same step from host DRAM (no link to cross), which is why one GPU cannot win this leg however fast its kernels are"}
     except Exception as ex:  # never lose the main line because of the e2e leg
         e2e = {"value": None, "unit": "GB/s", "error": repr(ex)[:200]}
 
@@ -459,7 +485,83 @@ def main():
                                        "results PUT into the y owners' exchange arena over NVLink, device-side barriers, one fused beta-scale + ordered add!"}
             xv.close()
             xt.close()
+            # Level-3 widening (K12): C = A*B through the public API (tile products on the tcgen05 3xTF32 kernel, B blocks halo-fetched,
+            # tile results shipped to the owners of C, ordered add!); useful flops = 2*m*n*k, the tensor core executes 3x that in TF32
+            try:
+                nB = 2048
+                Bm = dab.drand((dimsA[1], nB), dtype=np.float32, seed=SEED + 2)
+                ms_g, _ = timed(lambda: (A @ Bm).close(), 3)
+                ms_g = max_over_ranks(ms_g)
+                fl = 2.0 * dimsA[0] * dimsA[1] * nB * 3
+                tf = fl / (ms_g * 1e-3) / 1e12
+                pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops") if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+                extras["matmat_A_B"] = {"useful_TFLOPs": tf, "tf32_mma_TFLOPs": 3 * tf, "ms": ms_g / 3, "dims": [dimsA[0], dimsA[1], nB],
+                                        "frac_of_tf32_peak": (3 * tf / (world * pk / 2)) if pk else None,
+                                        "what": "A*B (mul!(C, A, B)): dab_gemm tiles = TMA + tcgen05.mma kind::tf32 with TMEM accumulators, 3xTF32 "
+                                                "error-compensated; tf32 peak taken as measured bf16 peak / 2"}
+                if not args.no_parity:
+                    Cm = A @ Bm
+                    from oracle import core as ocore
+                    lc = dab.localpart(Cm)
+                    worst, rows = 0.0, 64
+                    if lc.size:
+                        Ic = Cm.layout.localindices(rt.myid())
+                        r0 = Ic[0][0] - 1
+                        arow = np.empty((rows, dimsA[1]))
+                        for kk in range(dimsA[1]):                             # A[r0:r0+64, :] regenerated from the counter-based generator
+                            arow[:, kk] = ocore.rand_u01_f32(SEED + 1, kk * dimsA[0] + r0, rows)
+                        for jc in (Ic[1][0] - 1, Ic[1][1] - 1):                # first and last column of this rank's chunk of C
+                            want = arow @ ocore.rand_u01_f32(SEED + 2, jc * dimsA[1], dimsA[1]).astype(np.float64)
+                            got = _d2h_window(dab, rt, lc, (jc - (Ic[1][0] - 1)) * lc.shape[0], rows)
+                            worst = max(worst, float(np.abs(got - want).max() / np.abs(want).min()))
+                    allw = max(rt.allgather_object(worst))
+                    parity["checks"]["matmat_A_B"] = {"ok": allw <= 2e-6, "worst_rel_err": allw, "tol": 2e-6, "entries_per_rank": 2 * rows,
+                                                      "vs": "fp64 product of the regenerated inputs"}
+                    Cm.close()
+                Bm.close()
+            except Exception as ex:
+                extras["matmat_A_B"] = {"error": repr(ex)[:300]}
             A.close()
+            # sort widening (K11 onesweep): one chunk through the C ABI, and sort(d::DVector) end to end (samplesort incl. the exchange)
+            try:
+                import ctypes as C
+                from darray_b200 import _lib
+                ns = 1 << 28
+                keys = dab.drand((ns * world,), dtype=np.float32, seed=SEED + 3)
+                kin = dab.localpart(keys)
+                kout, ktmp = dab.B200Array.empty(rt, (ns,), np.float32), dab.B200Array.empty(rt, (ns,), np.float32)
+                ms_s, _ = timed(lambda: _lib.call("dab_sort", rt.ctx, _lib.F32, C.c_void_p(kin.ptr), C.c_void_p(kout.ptr), C.c_void_p(ktmp.ptr), ns), 5)
+                ms_s = max_over_ranks(ms_s) / 5
+                if not args.no_parity:
+                    head = _d2h_window(dab, rt, kout, 0, 1 << 20)
+                    srt_ok = bool(np.all(head[:-1] <= head[1:])) and abs(float(dab.sum(keys)) - float(_sum_of(dab, rt, kout, ns))) <= 1e-6 * float(dab.sum(keys))
+                    parity["checks"]["sort_chunk"] = {"ok": bool(all(rt.allgather_object(srt_ok))), "what": "first 2^20 keys ascending; sum preserved (1e-6)"}
+                kout.free()
+                ktmp.free()
+                # rand(Float32) keys occupy 3 of the 4 digit positions fully (sign/exponent byte varies little but is not constant)
+                extras["sort_chunk_f32_2p28"] = {"ms": ms_s, "Gkeys_s_per_gpu": ns / ms_s / 1e6, "algorithmic_GBs_per_gpu": 4.0 * ns * (1 + 2 * 4) / ms_s / 1e6,
+                                                 "frac_of_hbm_peak": 4.0 * ns * (1 + 2 * 4) / ms_s / 1e6 / peak,
+                                                 "what": "dab_sort (onesweep LSD radix sort, 8-bit digits) of one 2^28 Float32 chunk per GPU; algorithmic "
+                                                         "bytes = 4 B x (1 histogram read + 2 per digit pass x 4 passes)"}
+                keys.close()
+                dv = dab.drand(((1 << 26) * world,), dtype=np.float32, seed=SEED + 4)
+                ms_d, _ = timed(lambda: dab.sort(dv).close(), 3)
+                ms_d = max_over_ranks(ms_d) / 3
+                extras["sort_dvector_2p26_per_gpu"] = {"ms": ms_d, "Gkeys_s": (1 << 26) * world / ms_d / 1e6,
+                                                       "what": "sort(d::DVector; sample=true) end to end: chunk sorts, sampling, split, exchange of the pieces, result DArray"}
+                if not args.no_parity:
+                    sd = dab.sort(dv)
+                    tot = float(dab.sum(sd))
+                    okd = abs(tot - float(dab.sum(dv))) <= 1e-6 * tot and len(sd) == len(dv)
+                    lp = dab.localpart(sd)
+                    if lp.size > 1:
+                        w = _d2h_window(dab, rt, lp, 0, min(lp.size, 1 << 20))
+                        okd = okd and bool(np.all(w[:-1] <= w[1:]))
+                    parity["checks"]["sort_dvector"] = {"ok": bool(all(rt.allgather_object(bool(okd)))), "what": "length and sum preserved; local head ascending"}
+                    sd.close()
+                dv.close()
+            except Exception as ex:
+                extras["sort"] = {"error": repr(ex)[:300]}
         except Exception as ex:
             extras["error"] = repr(ex)[:300]
 

@@ -200,10 +200,14 @@ def sort_with_boundaries(d: DArray, sample=True, by=None, alg=None, **kwargs):
 
     # ---- ship piece i to worker i
     totals = [sum(sizes[p][j] for p in pids) for j in range(nparts)]
+    # a worker that receives ONE non-empty piece already holds its sorted result: the piece lands straight in the result chunk and the
+    # second sort (``sort!(lp_sorting)``, src/sort.jl:61) has nothing to do; several pieces are concatenated and sorted again
     recv: Dict[int, B200Array] = {}
+    single_run: Dict[int, bool] = {}
     for j, pid in enumerate(pids):
         if rt.is_local(pid) and totals[j]:
-            recv[j] = B200Array.empty(rt, (totals[j],), dt, temp=True)
+            single_run[j] = sum(1 for p in pids if sizes[p][j]) == 1
+            recv[j] = B200Array.empty(rt, (totals[j],), dt, temp=not single_run[j])
     plan = sort_exchange_plan(pids, sizes, rt.rank_of, rt.rank)
     for j, p, off, n in plan["local"]:
         _lib.call("dab_d2d", rt.ctx, C.c_void_p(recv[j].ptr + off * isz), C.c_void_p(srt[p].ptr + (ends[p][j] - n) * isz), n * isz)
@@ -225,6 +229,9 @@ def sort_with_boundaries(d: DArray, sample=True, by=None, alg=None, **kwargs):
         raise _lib.ArgumentError(_lib.ERR_EMPTY, "sort: empty DVector")
     chunks: Dict[int, B200Array] = {}
     for j, buf in recv.items():
+        if single_run[j]:
+            chunks[pids[j]] = buf
+            continue
         out = B200Array.empty(rt, (totals[j],), dt)
         _sort_chunk(rt, buf.ptr, totals[j], dt, out)
         buf.free()

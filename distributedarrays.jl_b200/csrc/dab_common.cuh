@@ -39,6 +39,8 @@ struct dab_ctx {
     struct dab_alloc_cache* cache;  // size-bucketed reuse of small cudaMalloc blocks (dab_core.cu)
     void* sort_dev;         // radix-sort scratch: digit histograms + per-tile counts (dab_sort.cu)
     size_t sort_dev_bytes;
+    void* stage[2];         // pinned staging buffers of the pipelined pageable H2D path (dab_h2d)
+    cudaEvent_t stage_ev[2];
     void* sort_host;        // pinned: split-point staging of dab_sorted_split
     unsigned long long sort_epoch;  // one per digit pass ever launched: tags the look-back words so the scratch is never re-cleared
     int opt_sort_variant;   // dab_set_option("sort_variant"): tile shape of the onesweep kernel (tuning sweeps)

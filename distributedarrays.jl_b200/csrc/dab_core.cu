@@ -4,6 +4,7 @@
 #include <map>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <unordered_map>
 
 #include "dab_common.cuh"
@@ -156,6 +157,11 @@ int32_t dab_shutdown(dab_ctx* ctx) {
     if (ctx->dim_scratch) cudaFree(ctx->dim_scratch);
     if (ctx->sort_dev) cudaFree(ctx->sort_dev);
     if (ctx->sort_host) cudaFreeHost(ctx->sort_host);
+    for (int b = 0; b < 2; ++b)
+        if (ctx->stage[b]) {
+            cudaFreeHost(ctx->stage[b]);
+            cudaEventDestroy(ctx->stage_ev[b]);
+        }
     if (ctx->cache) {
         for (auto& kv : ctx->cache->free_blocks) cudaFree(kv.second);
         delete ctx->cache;
@@ -329,9 +335,51 @@ int32_t dab_host_free(dab_ctx* ctx, void* hptr) {
     if (hptr) DAB_CUDA(ctx, cudaFreeHost(hptr));
     return DAB_OK;
 }
+// distribute(A) / copyto!(d, A) from ORDINARY (pageable) host memory: cudaMemcpyAsync would fall back to the driver's small internal
+// bounce buffer and block the calling thread at a fraction of the PCIe rate.  Large pageable sources are therefore pipelined through two
+// pinned staging buffers: a few host threads copy block k+1 into one buffer while the copy engine sends block k from the other.  The call
+// returns when the last block has been STAGED -- the caller's array may be reused at once, the device side stays asynchronous on the ctx
+// stream.  Pinned sources (dab_host_alloc / cudaHostRegister) go straight to cudaMemcpyAsync.
+static int32_t h2d_staged(dab_ctx* ctx, char* dptr, const char* hptr, size_t nbytes) {
+    constexpr size_t BLOCK = 32ull << 20;
+    constexpr int NT = 8;
+    if (!ctx->stage[0]) {
+        for (int b = 0; b < 2; ++b) {
+            DAB_CUDA(ctx, cudaHostAlloc(&ctx->stage[b], BLOCK, cudaHostAllocDefault));
+            DAB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[b], cudaEventDisableTiming));
+        }
+    }
+    int b = 0;
+    for (size_t off = 0; off < nbytes; off += BLOCK, b ^= 1) {
+        const size_t n = nbytes - off < BLOCK ? nbytes - off : BLOCK;
+        DAB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[b]));          // the copy engine has drained this buffer (no-op the first time)
+        char* st = (char*)ctx->stage[b];
+        const char* src = hptr + off;
+        const size_t per = ((n + NT - 1) / NT + 63) & ~(size_t)63;
+        std::thread th[NT];
+        int nth = 0;
+        for (int t = 1; t < NT && (size_t)t * per < n; ++t, ++nth) {
+            const size_t lo = (size_t)t * per, len = lo + per <= n ? per : n - lo;
+            th[nth] = std::thread([=] { memcpy(st + lo, src + lo, len); });
+        }
+        memcpy(st, src, per < n ? per : n);
+        for (int t = 0; t < nth; ++t) th[t].join();
+        DAB_CUDA(ctx, cudaMemcpyAsync(dptr + off, st, n, cudaMemcpyHostToDevice, ctx->stream));
+        DAB_CUDA(ctx, cudaEventRecord(ctx->stage_ev[b], ctx->stream));
+    }
+    return DAB_OK;
+}
+
 int32_t dab_h2d(dab_ctx* ctx, void* dptr, const void* hptr, size_t nbytes) {
     DAB_ENTER(ctx);
-    if (nbytes) DAB_CUDA(ctx, cudaMemcpyAsync(dptr, hptr, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (!nbytes) return DAB_OK;
+    if (nbytes >= (16ull << 20)) {
+        cudaPointerAttributes at;
+        const cudaError_t e = cudaPointerGetAttributes(&at, hptr);
+        if (e != cudaSuccess) cudaGetLastError();
+        if (e != cudaSuccess || at.type == cudaMemoryTypeUnregistered) return h2d_staged(ctx, (char*)dptr, (const char*)hptr, nbytes);
+    }
+    DAB_CUDA(ctx, cudaMemcpyAsync(dptr, hptr, nbytes, cudaMemcpyHostToDevice, ctx->stream));
     return DAB_OK;
 }
 int32_t dab_d2h(dab_ctx* ctx, void* hptr, const void* dptr, size_t nbytes) {

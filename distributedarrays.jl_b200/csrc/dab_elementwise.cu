@@ -211,10 +211,11 @@ int32_t launch_ew1(dab_ctx* ctx, T* y, const T* x, size_t n, F f) {
         const size_t tile_elems = TMA_TILE_BYTES / sizeof(T);
         const size_t ntiles = n / tile_elems;
         const size_t smem = (size_t)TMA_STAGES * TMA_TILE_BYTES + 8 * TMA_STAGES;
-        static bool attr_set = false;
-        if (!attr_set) {
+        // the >48 KiB dynamic shared memory opt-in is a property of the (function, DEVICE) pair: remember it per device, not per process
+        static unsigned long long attr_set_mask = 0;   // bit d: done on device d (devices >= 64 simply set it every time)
+        if (ctx->device >= 64 || !(attr_set_mask & (1ull << ctx->device))) {
             DAB_CUDA(ctx, cudaFuncSetAttribute(ew1_tma_kernel<T, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
+            if (ctx->device < 64) attr_set_mask |= 1ull << ctx->device;
         }
         int grid = ctx->sm_count < (int)ntiles ? ctx->sm_count : (int)ntiles;
         ew1_tma_kernel<T, F><<<grid, EW_THREADS, smem, ctx->stream>>>(y, x, ntiles, f);

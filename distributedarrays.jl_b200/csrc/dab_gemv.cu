@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_t_kernel(const T* __restrict_
         if (col0 < n) {
             const int nc = (n - col0 < (size_t)COLS) ? (int)(n - col0) : COLS;
             // UI sweep steps per batch: the unit-wise (unaligned) variant needs the extra loads in flight
-            constexpr int UI = (VEC == 1) ? 4 : 1;
+            constexpr int UI = (VEC == 1) ? 32 / (int)sizeof(T) : 1;
             size_t i = ilo + (size_t)li * VEC;
             if (nc == COLS) {
                 const T* p0 = A + col0 * m;
@@ -233,7 +233,9 @@ int ceil_log2(size_t v) {
 template <typename T, int VEC>
 int32_t launch_n(dab_ctx* ctx, const T* A, size_t m, size_t n, const T* x, T* y) {
     using Acc = typename GvAcc<T>::type;
-    constexpr int U = 4;
+    // loads in flight per thread: 4 x 16 B when the columns are 16-byte aligned; the unit-wise variant (leading dimension not a multiple
+    // of 16 bytes, e.g. the 37/36-row splits defaultdist produces) needs 16 x 4 B to keep the same bytes in flight
+    constexpr int U = (VEC == 1) ? 64 / (int)sizeof(T) : 4;
     const size_t rvecs = (m + VEC - 1) / VEC;
     int lrt = ceil_log2(rvecs);
     if (lrt > 8) lrt = 8;

@@ -136,8 +136,9 @@ int32_t dab_alloc_async(dab_ctx* ctx, size_t nbytes, void** dptr);
 int32_t dab_free_async(dab_ctx* ctx, void* dptr);
 int32_t dab_host_alloc(dab_ctx* ctx, size_t nbytes, void** hptr); /* pinned staging */
 int32_t dab_host_free(dab_ctx* ctx, void* hptr);
-/* distribute(A) / Array(d) per chunk (src/darray.jl:544-555, 574-582): async on the ctx stream
- * (truly async only for pinned host memory). */
+/* distribute(A) / Array(d) per chunk (src/darray.jl:544-555, 574-582): async on the ctx stream.  dab_h2d from PINNED memory is one
+ * cudaMemcpyAsync; from large pageable memory it is pipelined through two pinned staging buffers (host threads fill one while the copy
+ * engine drains the other) and returns once the source has been consumed, so the caller's array may be reused immediately. */
 int32_t dab_h2d(dab_ctx* ctx, void* dptr, const void* hptr, size_t nbytes);
 int32_t dab_d2h(dab_ctx* ctx, void* hptr, const void* dptr, size_t nbytes);
 int32_t dab_d2d(dab_ctx* ctx, void* dst, const void* src, size_t nbytes);

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Single-GPU rates of K11 (dab_sort: LSD radix sort of one chunk) and of sort(d::DVector) end to end.  Keys/s with CUDA events;
-GB/s = elem * (1 + 3 * passes) * n / time, the kernel's algorithmic traffic (histogram read + per pass count read, scatter read + write)."""
+GB/s = elem * (1 + 2 * passes) * n / time, the onesweep kernel's algorithmic traffic (histogram read + per pass one read and one write)."""
 import ctypes as C
 import os
 import sys
@@ -43,7 +43,7 @@ for name, T, n, gen, passes in (
     es = np.dtype(T).itemsize
     got = out.to_numpy()
     ok = bool(np.all(got[:-1] <= got[1:])) and got[0] == a.min() and got[-1] == a.max()
-    print(f"dab_sort {name:18s} n=2^{int(np.log2(n))} {ms:8.3f} ms {n / ms / 1e6:7.2f} Gkeys/s  ~{es * (1 + 3 * passes) * n / ms / 1e6:7.0f} GB/s "
+    print(f"dab_sort {name:18s} n=2^{int(np.log2(n))} {ms:8.3f} ms {n / ms / 1e6:7.2f} Gkeys/s  ~{es * (1 + 2 * passes) * n / ms / 1e6:7.0f} GB/s "
           f"(<= {passes} passes)  sorted={ok}", flush=True)
     t0 = time.perf_counter()
     np.sort(a[: 1 << 24])

@@ -46,6 +46,7 @@ struct dab_ctx {
     int opt_sort_variant;   // dab_set_option("sort_variant"): tile shape of the onesweep kernel (tuning sweeps)
     long long opt_combine_timeout_ms;  // dab_set_option("combine_timeout_ms"): how long the fused combine waits for a peer (default 120 s)
     long long opt_gemm_kc;  // dab_set_option("gemm_kc"): k extent summed inside tensor memory before a partial tile is drained (default 64)
+    int opt_gemm_rawhi;     // dab_set_option("gemm_rawhi"): 1 = raw fp32 tile as the tf32 "hi" operand (hardware truncation), 0 = RN split
     int opt_gemm_simt;      // dab_set_option("gemm_simt"): 1 = force the SIMT tile kernel for Float32 (A/B measurements)
     int opt_ew_tma;         // dab_set_option("ew_tma"): route aligned unary elementwise launches through the TMA-staged kernel
     char err[512];

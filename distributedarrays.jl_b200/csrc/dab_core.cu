@@ -19,8 +19,10 @@ struct dab_alloc_cache {
     std::unordered_map<void*, size_t> live;   // block -> rounded size (cacheable blocks only)
     std::multimap<size_t, void*> free_blocks;
     size_t cached_bytes = 0;
-    static constexpr size_t kMaxBlock = 64ull << 20;   // larger blocks (localparts) are freed for real
-    static constexpr size_t kMaxCached = 2ull << 30;
+    // localpart-sized blocks are recycled too (an `x = A * x` loop allocates and frees the same sizes over and over, and a cudaMalloc /
+    // cudaFree pair of a 256 MiB block costs ~5 ms and synchronises the device); when the device runs out of memory the cache is flushed
+    static constexpr size_t kMaxBlock = 16ull << 30;
+    static constexpr size_t kMaxCached = 32ull << 30;
 };
 
 int dab_resident_ctas(const void* kernel, int threads) {
@@ -103,6 +105,7 @@ int32_t dab_init(int32_t device, dab_ctx** out) {
     ctx->nranks = 1;
     ctx->fuse_op = -1;
     ctx->opt_combine_timeout_ms = 120000;
+    ctx->opt_gemm_rawhi = 1;
     ctx->cache = new (std::nothrow) dab_alloc_cache();
 #define INIT_CUDA(call)                                                     \
     do {                                                                    \
@@ -191,7 +194,7 @@ int32_t dab_device_info(dab_ctx* ctx, int32_t* device, int32_t* sm_count, size_t
     DAB_CUDA(ctx, cudaMemGetInfo(&f, &t));
     if (device) *device = ctx->device;
     if (sm_count) *sm_count = ctx->sm_count;
-    if (free_bytes) *free_bytes = f;
+    if (free_bytes) *free_bytes = f + (ctx->cache ? ctx->cache->cached_bytes : 0);   // recycled blocks are given back on demand
     if (total_bytes) *total_bytes = t;
     return DAB_OK;
 }
@@ -213,6 +216,10 @@ int32_t dab_set_option(dab_ctx* ctx, const char* key, int64_t value) {
     }
     if (strcmp(key, "gemm_kc") == 0) {
         ctx->opt_gemm_kc = value;
+        return DAB_OK;
+    }
+    if (strcmp(key, "gemm_rawhi") == 0) {
+        ctx->opt_gemm_rawhi = value != 0;
         return DAB_OK;
     }
     if (strcmp(key, "gemm_simt") == 0) {
@@ -279,12 +286,32 @@ int32_t dab_alloc(dab_ctx* ctx, size_t nbytes, void** dptr) {
             c->free_blocks.erase(it);
             c->cached_bytes -= rounded;
         } else {
-            DAB_CUDA(ctx, cudaMalloc(dptr, rounded));
+            cudaError_t e = cudaMalloc(dptr, rounded);
+            if (e == cudaErrorMemoryAllocation) {   // give the cached blocks back and try again
+                cudaGetLastError();
+                DAB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                for (auto& kv : c->free_blocks) cudaFree(kv.second);
+                c->free_blocks.clear();
+                c->cached_bytes = 0;
+                e = cudaMalloc(dptr, rounded);
+            }
+            DAB_CUDA(ctx, e);
         }
         c->live[*dptr] = rounded;
         return DAB_OK;
     }
-    DAB_CUDA(ctx, cudaMalloc(dptr, nbytes));
+    {
+        cudaError_t e = cudaMalloc(dptr, nbytes);
+        if (e == cudaErrorMemoryAllocation && c) {
+            cudaGetLastError();
+            DAB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (auto& kv : c->free_blocks) cudaFree(kv.second);
+            c->free_blocks.clear();
+            c->cached_bytes = 0;
+            e = cudaMalloc(dptr, nbytes);
+        }
+        DAB_CUDA(ctx, e);
+    }
     return DAB_OK;
 }
 int32_t dab_free(dab_ctx* ctx, void* dptr) {

@@ -195,7 +195,26 @@ __device__ __forceinline__ float4 split_tf32(float4& v) {   // v <- hi (tf32, ro
     return lo;
 }
 
-template <bool TA>
+// RAWHI: the tensor core reads an fp32 word as tf32 by IGNORING its low 13 mantissa bits (verified on B200: results identical to an explicit
+// truncation), so the raw tile can serve as the "hi" operand as it is; the converters then only write "lo" = tf32_rn(v - trunc_tf32(v)) and
+// the shared-memory traffic of the conversion drops from 3 to 2 tile passes per operand (the kernel is shared-memory-bandwidth bound:
+// tensor-core operand reads + conversion = ~190 KiB per 32-deep k-block against 128 B/clk).  RAWHI = false keeps the round-to-nearest
+// split (hi rewritten in place).
+__device__ __forceinline__ float4 lo_of_trunc(const float4& v) {   // tf32_rn(v - trunc_tf32(v)), the remainder of the hardware's truncation
+    float4 lo;
+#define DAB_LO1(c)                                                                  \
+    {                                                                               \
+        const float r = v.c - __uint_as_float(__float_as_uint(v.c) & 0xffffe000u);  \
+        uint32_t l;                                                                 \
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));                        \
+        lo.c = __uint_as_float(l);                                                  \
+    }
+    DAB_LO1(x) DAB_LO1(y) DAB_LO1(z) DAB_LO1(w)
+#undef DAB_LO1
+    return lo;
+}
+
+template <bool TA, bool RAWHI>
 __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                                     float* __restrict__ C, size_t ldc, uint32_t m, uint32_t n, uint32_t k, uint32_t kc_blocks) {
     extern __shared__ unsigned char tg_raw[];
@@ -301,11 +320,16 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32x3_kernel(const __grid
             for (int q = 0; q < TG_TILE_BYTES / 16 / 128; ++q) {
                 const int i = c + q * 128;
                 float4 va = a_hi[i], vb = b_hi[i];
-                const float4 la = split_tf32(va), lb = split_tf32(vb);
-                a_hi[i] = va;
-                a_lo[i] = la;
-                b_hi[i] = vb;
-                b_lo[i] = lb;
+                if (RAWHI) {
+                    a_lo[i] = lo_of_trunc(va);
+                    b_lo[i] = lo_of_trunc(vb);
+                } else {
+                    const float4 la = split_tf32(va), lb = split_tf32(vb);
+                    a_hi[i] = va;
+                    a_lo[i] = la;
+                    b_hi[i] = vb;
+                    b_lo[i] = lb;
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                   // generic-proxy stores -> visible to the tensor core's async proxy
             mbar_arrive(bar0 + 8 * (3 + s));
@@ -402,20 +426,26 @@ int32_t launch_tf32x3(dab_ctx* ctx, int transA, size_t m, size_t n, size_t k, co
     long long kc = ctx->opt_gemm_kc > 0 ? ctx->opt_gemm_kc : 64;
     uint32_t kc_blocks = (uint32_t)((kc + TG_K - 1) / TG_K);
     if (kc_blocks < 1) kc_blocks = 1;
-    {
+    const bool raw = ctx->opt_gemm_rawhi != 0;
+    auto launch = [&](auto kern) -> int32_t {
         static std::mutex mu;
-        static std::map<std::pair<int, int>, bool> done;   // (device, transA): the >48 KiB opt-in is per (function, device)
-        std::lock_guard<std::mutex> lk(mu);
-        auto key = std::make_pair(ctx->device, transA ? 1 : 0);
-        if (!done.count(key)) {
-            if (transA) DAB_CUDA(ctx, cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES));
-            else DAB_CUDA(ctx, cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES));
-            done[key] = true;
+        static std::map<std::pair<const void*, int>, bool> done;   // the >48 KiB opt-in is per (function, device)
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto key = std::make_pair((const void*)kern, ctx->device);
+            if (!done.count(key)) {
+                DAB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES));
+                done[key] = true;
+            }
         }
-    }
-    dim3 grid((unsigned)gx, (unsigned)gy);
-    if (transA) gemm_tf32x3_kernel<true><<<grid, TG_THREADS, TG_SMEM_BYTES, ctx->stream>>>(mapA, mapB, C, ldc, (uint32_t)m, (uint32_t)n, (uint32_t)k, kc_blocks);
-    else gemm_tf32x3_kernel<false><<<grid, TG_THREADS, TG_SMEM_BYTES, ctx->stream>>>(mapA, mapB, C, ldc, (uint32_t)m, (uint32_t)n, (uint32_t)k, kc_blocks);
+        dim3 grid((unsigned)gx, (unsigned)gy);
+        kern<<<grid, TG_THREADS, TG_SMEM_BYTES, ctx->stream>>>(mapA, mapB, C, ldc, (uint32_t)m, (uint32_t)n, (uint32_t)k, kc_blocks);
+        return DAB_OK;
+    };
+    int32_t rc;
+    if (transA) rc = raw ? launch(gemm_tf32x3_kernel<true, true>) : launch(gemm_tf32x3_kernel<true, false>);
+    else rc = raw ? launch(gemm_tf32x3_kernel<false, true>) : launch(gemm_tf32x3_kernel<false, false>);
+    if (rc != DAB_OK) return rc;
     DAB_LAUNCHED(ctx);
     return DAB_OK;
 }

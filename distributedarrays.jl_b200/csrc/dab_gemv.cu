@@ -58,61 +58,88 @@ __device__ __forceinline__ GvVec<T, VEC> gv_load_cached(const T* p) {
 }
 
 // ---- r = A x ----------------------------------------------------------------------------------------------------------------
-// grid (row tiles, column splits); lrt = log2(RT)
-template <typename T, int VEC, int U>
+// grid (row tiles, column splits); lrt = log2(RT).  A thread owns R groups of VEC consecutive rows, RT*VEC rows apart, so a CTA covers
+// R*RT*VEC CONSECUTIVE rows of every column it touches: 4 KiB of contiguous DRAM per column in both variants -- R = 1 with 16-byte loads
+// when the columns are 16-byte aligned, R = 4 unit-wise loads otherwise (leading dimension not a multiple of 16 bytes, e.g. the 37/36-row
+// splits defaultdist produces; one row group per thread would read 1 KiB bursts scattered over many DRAM pages).
+template <typename T, int VEC, int U, int R>
 __global__ void __launch_bounds__(GV_THREADS) gemv_n_kernel(const T* __restrict__ A, size_t m, size_t n, const T* __restrict__ x, int lrt,
                                                             size_t cols_per_split, typename GvAcc<T>::type* __restrict__ part,
                                                             T* __restrict__ y) {
     using Acc = typename GvAcc<T>::type;
-    __shared__ Acc sh[GV_THREADS * VEC];
+    __shared__ Acc sh[GV_THREADS * VEC * R];
     const int RT = 1 << lrt, CL = GV_THREADS >> lrt;
     const int ri = threadIdx.x & (RT - 1), cl = threadIdx.x >> lrt;
-    const size_t row0 = ((size_t)blockIdx.x * RT + ri) * VEC;
+    const size_t rstep = (size_t)RT * VEC;                              // rows between a thread's groups
+    const size_t row0 = (size_t)blockIdx.x * R * rstep + (size_t)ri * VEC;
     const size_t jlo = (size_t)blockIdx.y * cols_per_split;
     const size_t jhi = (jlo + cols_per_split < n) ? jlo + cols_per_split : n;
-    Acc acc[VEC];
+    Acc acc[R][VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = Acc(0);
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[r][v] = Acc(0);
     if (row0 < m) {
         const T* col = A + row0;
+        // all R groups of this thread inside the matrix: the common case; the last row tile takes the guarded path
+        const bool full = row0 + (size_t)(R - 1) * rstep + VEC <= m;
         size_t j = jlo + cl;
         const size_t step = (size_t)CL;
-        for (; j + (U - 1) * step < jhi; j += U * step) {
-            GvVec<T, VEC> a[U];
-            T xv[U];
+        if (full) {
+            for (; j + (U - 1) * step < jhi; j += U * step) {
+                GvVec<T, VEC> a[U][R];
+                T xv[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                a[u] = gv_load_stream<T, VEC>(col + (j + u * step) * m);
-                xv[u] = __ldg(x + j + u * step);
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) a[u][r] = gv_load_stream<T, VEC>(col + (j + u * step) * m + r * rstep);
+                    xv[u] = __ldg(x + j + u * step);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) gv_mac(acc[r][v], (Acc)a[u][r].v[v], (Acc)xv[u]);
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) gv_mac(acc[v], (Acc)a[u].v[v], (Acc)xv[u]);
         }
         for (; j < jhi; j += step) {
-            GvVec<T, VEC> a = gv_load_stream<T, VEC>(col + j * m);
             const Acc xj = (Acc)__ldg(x + j);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) gv_mac(acc[v], (Acc)a.v[v], xj);
+            for (int r = 0; r < R; ++r)
+                if (row0 + (size_t)r * rstep < m) {
+                    GvVec<T, VEC> a = gv_load_stream<T, VEC>(col + j * m + r * rstep);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) gv_mac(acc[r][v], (Acc)a.v[v], xj);
+                }
         }
     }
     if (CL > 1) {  // fold the column lanes in lane order
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) sh[threadIdx.x * VEC + v] = acc[v];
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) sh[(threadIdx.x * R + r) * VEC + v] = acc[r][v];
         __syncthreads();
         if (cl == 0)
             for (int c = 1; c < CL; ++c)
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) acc[v] += sh[((c << lrt) + ri) * VEC + v];
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) acc[r][v] += sh[((((c << lrt) + ri)) * R + r) * VEC + v];
     }
-    if (cl == 0 && row0 < m) {
-        if (part) {
+    if (cl == 0) {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) part[(size_t)blockIdx.y * m + row0 + v] = acc[v];
-        } else {
+        for (int r = 0; r < R; ++r) {
+            const size_t row = row0 + (size_t)r * rstep;
+            if (row < m) {
+                if (part) {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) y[row0 + v] = (T)acc[v];
+                    for (int v = 0; v < VEC; ++v) part[(size_t)blockIdx.y * m + row + v] = acc[r][v];
+                } else {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) y[row + v] = (T)acc[r][v];
+                }
+            }
         }
     }
 }
@@ -230,19 +257,16 @@ int ceil_log2(size_t v) {
     return l;
 }
 
-template <typename T, int VEC>
-int32_t launch_n(dab_ctx* ctx, const T* A, size_t m, size_t n, const T* x, T* y) {
+template <typename T, int VEC, int U, int R>
+int32_t launch_n_cfg(dab_ctx* ctx, const T* A, size_t m, size_t n, const T* x, T* y) {
     using Acc = typename GvAcc<T>::type;
-    // loads in flight per thread: 4 x 16 B when the columns are 16-byte aligned; the unit-wise variant (leading dimension not a multiple
-    // of 16 bytes, e.g. the 37/36-row splits defaultdist produces) needs 16 x 4 B to keep the same bytes in flight
-    constexpr int U = (VEC == 1) ? 64 / (int)sizeof(T) : 4;
-    const size_t rvecs = (m + VEC - 1) / VEC;
+    const size_t rvecs = (m + (size_t)VEC * R - 1) / ((size_t)VEC * R);   // row groups-of-R
     int lrt = ceil_log2(rvecs);
     if (lrt > 8) lrt = 8;
     const int RT = 1 << lrt, CL = GV_THREADS >> lrt;
     const size_t gx = (rvecs + RT - 1) / RT;
     // one full wave of resident CTAs (no partial second wave), but every CTA keeps >= 16 column steps per lane
-    const size_t slots = (size_t)ctx->sm_count * (size_t)dab_resident_ctas((const void*)gemv_n_kernel<T, VEC, U>, GV_THREADS);
+    const size_t slots = (size_t)ctx->sm_count * (size_t)dab_resident_ctas((const void*)gemv_n_kernel<T, VEC, U, R>, GV_THREADS);
     const size_t want = slots / gx > 0 ? slots / gx : 1;
     size_t max_split = n / ((size_t)CL * U * 4);
     if (max_split < 1) max_split = 1;
@@ -258,13 +282,21 @@ int32_t launch_n(dab_ctx* ctx, const T* A, size_t m, size_t n, const T* x, T* y)
     }
     DAB_REQUIRE(ctx, gx <= 0x7fffffffull, DAB_ERR_ARG, "dab_gemv: too many row tiles");
     dim3 grid((unsigned)gx, (unsigned)nsplit);
-    gemv_n_kernel<T, VEC, U><<<grid, GV_THREADS, 0, ctx->stream>>>(A, m, n, x, lrt, cps, part, y);
+    gemv_n_kernel<T, VEC, U, R><<<grid, GV_THREADS, 0, ctx->stream>>>(A, m, n, x, lrt, cps, part, y);
     DAB_LAUNCHED(ctx);
     if (part) {
         gemv_finish_kernel<T><<<(unsigned)((m + GV_THREADS - 1) / GV_THREADS), GV_THREADS, 0, ctx->stream>>>(part, m, (int)nsplit, y);
         DAB_LAUNCHED(ctx);
     }
     return DAB_OK;
+}
+
+// loads in flight per thread: U = 4 columns x R = 1 row group.  Measured on B200 for the unit-wise variant (leading dimension not a multiple
+// of 16 bytes): (U, R) = (4, 1) gives a steady 4.1-4.2 TB/s; more loads in flight -- (8, 1), (16, 1), (4, 2), (2, 4), (4, 4) -- range
+// from 2.2 to 5.6 TB/s depending on the column stride, so the steady shape is kept (profiles/r2_gemv_unaligned_sweep.txt).
+template <typename T, int VEC>
+int32_t launch_n(dab_ctx* ctx, const T* A, size_t m, size_t n, const T* x, T* y) {
+    return launch_n_cfg<T, VEC, 4, 1>(ctx, A, m, n, x, y);
 }
 
 template <typename T, int VEC>

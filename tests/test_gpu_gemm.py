@@ -105,3 +105,28 @@ def test_gemm_other_types(dab, rt1, dtype, transA):
             with np.errstate(over="ignore"):
                 want = (A.T if transA else A) @ B                       # NumPy integer matmul wraps too
             assert R.dtype == np.dtype(dtype) and np.array_equal(R, want)
+
+
+@pytest.mark.parametrize("transA", [False, True])
+def test_gemm_f32_raw_hi_operand(dab, rt1, transA):
+    """``gemm_rawhi`` = 1: the raw fp32 tile is the tf32 "hi" operand (the tensor core ignores the low 13 mantissa bits) and only the
+    remainder tile is written by the converters.  Same accuracy contract as the round-to-nearest split."""
+    rng = np.random.default_rng(77)
+    m, n, k = 384, 256, 4096
+    A = rng.random((k, m) if transA else (m, k)).astype(F32)
+    B = rng.random((k, n)).astype(F32)
+    rt1.set_option("gemm_rawhi", 1)
+    try:
+        R = gemm(dab, rt1, A, B, transA)
+    finally:
+        rt1.set_option("gemm_rawhi", 0)
+    want = (A.T if transA else A).astype(np.float64) @ B.astype(np.float64)
+    assert float(np.abs(R - want).max() / np.abs(want).min()) <= 1e-6
+    An = rng.standard_normal(A.shape).astype(F32)
+    Bn = rng.standard_normal(B.shape).astype(F32)
+    rt1.set_option("gemm_rawhi", 1)
+    try:
+        R = gemm(dab, rt1, An, Bn, transA)
+    finally:
+        rt1.set_option("gemm_rawhi", 0)
+    check_float(R, An, Bn, transA, 2e-6)

@@ -21,10 +21,11 @@ def main():
         B = dab.drand((k, n), dtype=np.float32, seed=2)
         Cc = dab.B200Array.empty(rt, (m, n), np.float32)
         a, b = dab.localpart(A), dab.localpart(B)
-        for simt in (0, 1):
-            if simt and m * n * k > 2 ** 37:
+        for simt in (0, 2, 1):
+            if simt == 1 and m * n * k > 2 ** 37:
                 continue
-            rt.set_option("gemm_simt", simt)
+            rt.set_option("gemm_simt", 1 if simt == 1 else 0)
+            rt.set_option("gemm_rawhi", 1 if simt == 2 else 0)
             call = lambda: _lib.call("dab_gemm", rt.ctx, _lib.F32, 0, m, n, k, C.c_void_p(a.ptr), m, C.c_void_p(b.ptr), k, C.c_void_p(Cc.ptr), m)
             for _ in range(2):
                 call()
@@ -49,10 +50,11 @@ def main():
                 _lib.call("dab_d2h", rt.ctx, C.c_void_p(host.ctypes.data), C.c_void_p(Cc.ptr + 4 * j * m), 4 * rows)
                 rt.sync()
                 worst = max(worst, float(np.abs(host - want[:, j]).max() / np.abs(want[:, j]).min()))
-            print(json.dumps({"kernel": "simt" if simt else "tcgen05_3xtf32", "m": m, "n": n, "k": k, "ms": round(ms, 4), "useful_TFLOPs": round(tf, 1),
-                              "tf32_mma_TFLOPs": round(3 * tf, 1) if not simt else None, "frac_of_bf16_peak_div2_div3": round(tf / (peak / 2 / 3), 3) if not simt else None,
+            print(json.dumps({"kernel": {0: "tcgen05_3xtf32", 1: "simt", 2: "tcgen05_3xtf32_rawhi"}[simt], "m": m, "n": n, "k": k, "ms": round(ms, 4), "useful_TFLOPs": round(tf, 1),
+                              "tf32_mma_TFLOPs": round(3 * tf, 1) if simt != 1 else None, "frac_of_bf16_peak_div2_div3": round(tf / (peak / 2 / 3), 3) if simt != 1 else None,
                               "max_rel_err_vs_fp64": worst}), flush=True)
         rt.set_option("gemm_simt", 0)
+        rt.set_option("gemm_rawhi", 0)
         Cc.free()
         A.close()
         B.close()

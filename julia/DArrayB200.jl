@@ -270,7 +270,43 @@ function Base.sort(a::B200Array{T,1}; kw...) where {T}
     out
 end
 
+# localpart(A) * Bjk, transpose(localpart(A)) * Bjk inside _matmatmul!  (src/linalg.jl:218-226): K12, tcgen05 3xTF32 for Float32
+function gemm(transA::Bool, A::B200Array{T,2}, B::B200Array{T,2}) where {T}
+    m, k = transA ? reverse(size(A)) : size(A)
+    size(B, 1) == k || throw(DimensionMismatch("matrix A has dimensions ($m, $k), matrix B has dimensions $(size(B))"))
+    R = B200Array{T,2}(undef, (m, size(B, 2)))
+    check(ccall((:dab_gemm, libdab), Int32,
+                (Ptr{Cvoid}, Int32, Int32, Csize_t, Csize_t, Csize_t, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}, Csize_t),
+                ctx(), dab_dtype(T), transA, m, size(B, 2), k, A.ptr, size(A, 1), B.ptr, size(B, 1), R.ptr, m), ctx())
+    R
+end
+Base.:*(A::B200Array{T,2}, B::B200Array{T,2}) where {T} = gemm(false, A, B)
+Base.:*(A::Adjoint{T,<:B200Array{T,2}}, B::B200Array{T,2}) where {T<:Real} = gemm(true, parent(A), B)
+Base.:*(A::Transpose{T,<:B200Array{T,2}}, B::B200Array{T,2}) where {T} = gemm(true, parent(A), B)
+
+# add!(localpart(y), R[i,j], alpha) for all j after the beta scaling (src/linalg.jl:62-76, 101-117, 232-252): one fused launch over the
+# stack of tile results that the producers PUT into this worker's exchange arena; dab_peer_barrier orders the puts (device side)
+function accumulate_stack!(y::B200Array{T}, beta, alpha, stack::Ptr{Cvoid}, count::Integer) where {T}
+    check(ccall((:dab_accumulate_stack, libdab), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Csize_t, Ref{T}, Ref{T}, Ptr{Cvoid}, Csize_t, Int32),
+                ctx(), dab_dtype(T), y.ptr, length(y), T(beta), T(alpha), stack, length(y), count), ctx())
+    y
+end
+peer_barrier() = check(ccall((:dab_peer_barrier, libdab), Int32, (Ptr{Cvoid},), ctx()), ctx())
+
+# localpart(d)[idxs...] with StepRange / Vector{Int} indices (src/darray.jl:661, 798-820): strided / table-driven gather
+function Base.getindex(a::B200Array{T,N}, I::Vararg{Union{AbstractRange{Int},Vector{Int}},N}) where {T,N}
+    out = B200Array{T,N}(undef, map(length, I))
+    sstr = cumprod((1, size(a)[1:end-1]...)); dstr = cumprod((1, size(out)[1:end-1]...))
+    tabs = [B200Array(Int64.((collect(I[k]) .- first(I[k])) .* sstr[k])) for k in 1:N]       # source offsets as tables (affine ones could pass strides)
+    src = a.ptr + (sum((first(I[k]) - 1) * sstr[k] for k in 1:N)) * sizeof(T)
+    check(ccall((:dab_gather_box, libdab), Int32,
+                (Ptr{Cvoid}, Int32, Int32, Ptr{Cvoid}, Ptr{Clonglong}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Ptr{Clonglong}, Ptr{Ptr{Cvoid}}, Ptr{Csize_t}),
+                ctx(), sizeof(T), N, out.ptr, Clonglong[dstr...], C_NULL, src, zeros(Clonglong, N), Ptr{Cvoid}[t.ptr for t in tabs],
+                Csize_t[length.(I)...]), ctx())
+    out
+end
+
 # user code is then unchanged:
 #   d = DArray(I -> B200Array(rand(Float32, map(length, I))), (8 * 2^30,))
-#   d .= 1.5f0 .* d .+ 0.25f0 ;  map!(Affine(2f0, 1f0), d, d) ;  sum(d) ;  maximum(d) ;  sum(d2, dims = 1)
+#   d .= 1.5f0 .* d .+ 0.25f0 ;  map!(Affine(2f0, 1f0), d, d) ;  sum(d) ;  maximum(d) ;  sum(d2, dims = 1) ;  A * B ;  A' * x ;  sort(v)
 end # module

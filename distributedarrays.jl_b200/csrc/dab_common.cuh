@@ -43,7 +43,6 @@ struct dab_ctx {
     cudaEvent_t stage_ev[2];
     void* sort_host;        // pinned: split-point staging of dab_sorted_split
     unsigned long long sort_epoch;  // one per digit pass ever launched: tags the look-back words so the scratch is never re-cleared
-    int opt_sort_variant;   // dab_set_option("sort_variant"): tile shape of the onesweep kernel (tuning sweeps)
     long long opt_combine_timeout_ms;  // dab_set_option("combine_timeout_ms"): how long the fused combine waits for a peer (default 120 s)
     long long opt_gemm_kc;  // dab_set_option("gemm_kc"): k extent summed inside tensor memory before a partial tile is drained (default 64)
     int opt_gemm_rawhi;     // dab_set_option("gemm_rawhi"): 1 = raw fp32 tile as the tf32 "hi" operand (hardware truncation), 0 = RN split

@@ -226,10 +226,6 @@ int32_t dab_set_option(dab_ctx* ctx, const char* key, int64_t value) {
         ctx->opt_gemm_simt = value != 0;
         return DAB_OK;
     }
-    if (strcmp(key, "sort_variant") == 0) {
-        ctx->opt_sort_variant = (int)value;
-        return DAB_OK;
-    }
     if (strcmp(key, "combine_timeout_ms") == 0) {
         if (value < 1) return dab_fail(ctx, DAB_ERR_ARG, "combine_timeout_ms must be >= 1");
         ctx->opt_combine_timeout_ms = value;

@@ -613,23 +613,10 @@ int32_t sort_t(dab_ctx* ctx, const void* in_v, void* out_v, void* tmp_v, size_t 
     DAB_REQUIRE(ctx, tmp != nullptr && tmp != out && tmp != in, DAB_ERR_ARG, "dab_sort: tmp must be a distinct buffer of n elements");
     DAB_REQUIRE(ctx, n < 0xFFFFF000ull, DAB_ERR_UNSUPPORTED, "dab_sort: chunks of 2^32 or more elements are not served");
     // tile shape: 32 KiB of keys per CTA in shared memory -> ~128-byte bucket runs per tile on random digits
-    if constexpr (sizeof(U) == 8) {
-        switch (ctx->opt_sort_variant) {
-            case 1: return sort_passes<T, 256, 16, 2>(ctx, in, out, tmp, n);
-            case 2: return sort_passes<T, 256, 8, 4>(ctx, in, out, tmp, n);
-            case 3: return sort_passes<T, 512, 8, 1>(ctx, in, out, tmp, n);
-            case 4: return sort_passes<T, 256, 12, 3>(ctx, in, out, tmp, n);
-            default: return sort_passes<T, 256, 16, 3>(ctx, in, out, tmp, n);
-        }
-    } else {
-        switch (ctx->opt_sort_variant) {
-            case 1: return sort_passes<T, 256, 32, 2>(ctx, in, out, tmp, n);
-            case 2: return sort_passes<T, 256, 16, 4>(ctx, in, out, tmp, n);
-            case 3: return sort_passes<T, 512, 16, 1>(ctx, in, out, tmp, n);
-            case 4: return sort_passes<T, 256, 24, 3>(ctx, in, out, tmp, n);
-            default: return sort_passes<T, 256, 32, 3>(ctx, in, out, tmp, n);
-        }
-    }
+    // tile shape (measured on B200, profiles/r2_sort_vs_cub.txt: larger tiles and 3 resident CTAs per SM win over smaller tiles at 4 CTAs
+    // and over 128-register CTAs at 2): 256 threads x 16 keys (64-bit) / x 32 keys (32-bit) = 32 KiB of keys per tile, twice in shared memory
+    if constexpr (sizeof(U) == 8) return sort_passes<T, 256, 16, 3>(ctx, in, out, tmp, n);
+    else return sort_passes<T, 256, 32, 3>(ctx, in, out, tmp, n);
 }
 
 // ---- split points in a sorted chunk ----------------------------------------------------------------------------------------------------

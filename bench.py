@@ -534,7 +534,8 @@ def main():
                 ms_s = max_over_ranks(ms_s) / 5
                 if not args.no_parity:
                     head = _d2h_window(dab, rt, kout, 0, 1 << 20)
-                    srt_ok = bool(np.all(head[:-1] <= head[1:])) and abs(float(dab.sum(keys)) - float(_sum_of(dab, rt, kout, ns))) <= 1e-6 * float(dab.sum(keys))
+                    s_in, s_out = float(_sum_of(dab, rt, kin, ns)), float(_sum_of(dab, rt, kout, ns))   # this rank's chunk before / after
+                    srt_ok = bool(np.all(head[:-1] <= head[1:])) and abs(s_in - s_out) <= 1e-6 * s_in
                     parity["checks"]["sort_chunk"] = {"ok": bool(all(rt.allgather_object(srt_ok))), "what": "first 2^20 keys ascending; sum preserved (1e-6)"}
                 kout.free()
                 ktmp.free()

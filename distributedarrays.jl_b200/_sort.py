@@ -162,23 +162,29 @@ def sort_with_boundaries(d: DArray, sample=True, by=None, alg=None, **kwargs):
     if presample is not None:
         boundaries = boundaries_from_samples(presample, nparts, dt)
     else:
-        mine = {}
-        for pid, s in srt.items():
-            llp = s.size
+        # every worker's samples sorted[1:step:llp] (src/sort.jl:9-14) gathered on every rank: strided device gather into one staging
+        # row per local worker, then ONE small all-gather through the exchange arena (no pickled host collective)
+        wpr = rt.workers_per_rank
+        SLOT = 1024                                             # <= 1023 samples per worker
+        stage = B200Array.empty(rt, (wpr * SLOT,), dt, temp=True)
+        counts = {}
+        for k, pid in enumerate(pids):
+            ((lo, hi),) = d.layout.indices[k]
+            llp = max(0, hi - lo + 1)
             ss = SAMPLE_SIZE_ON_WORKER if llp > SAMPLE_SIZE_ON_WORKER else llp
             if ss == 0:
                 raise ZeroDivisionError("DivideError: integer division error")        # div(llp, 0), src/sort.jl:9
-            step = llp // ss
-            cnt = len(range(0, llp, step))
-            g = B200Array.empty(rt, (cnt,), dt, temp=True)
+            counts[pid] = len(range(0, llp, llp // ss))
+        for pid, s in srt.items():
+            llp = s.size
+            step = llp // (SAMPLE_SIZE_ON_WORKER if llp > SAMPLE_SIZE_ON_WORKER else llp)
+            cnt = counts[pid]
             # sorted[1:step:llp]: row 0 of the (step x cnt) column-major view of the sorted chunk
-            _lib.call("dab_copy_box", rt.ctx, isz, C.c_void_p(g.ptr), _lib.sz4((1, cnt)), _lib.sz4((0, 0, 0, 0)), C.c_void_p(s.ptr),
-                      _lib.sz4((step, cnt)), _lib.sz4((0, 0, 0, 0)), _lib.sz4((1, cnt)))
-            mine[pid] = g.to_numpy()
-            g.free()
-        everyone = {}
-        for part in (rt.allgather_object(mine) if rt.world > 1 else [mine]):
-            everyone.update(part)
+            _lib.call("dab_copy_box", rt.ctx, isz, C.c_void_p(stage.ptr + ((pid - 1) % wpr) * SLOT * isz), _lib.sz4((1, cnt)), _lib.sz4((0, 0, 0, 0)),
+                      C.c_void_p(s.ptr), _lib.sz4((step, cnt)), _lib.sz4((0, 0, 0, 0)), _lib.sz4((1, cnt)))
+        rows = rt.allgather_small(dev_ptr=stage.ptr, nbytes=wpr * SLOT * isz, dtype=dt)
+        stage.free()
+        everyone = {pid: rows[rt.rank_of(pid)][((pid - 1) % wpr) * SLOT:((pid - 1) % wpr) * SLOT + counts[pid]] for pid in pids}
         boundaries = boundaries_from_samples(np.concatenate([everyone[p] for p in pids]), nparts, dt)
 
     # ---- split every sorted chunk at the boundaries (src/sort.jl:26-40): sizes[src pid][destination index]
@@ -194,9 +200,16 @@ def sort_with_boundaries(d: DArray, sample=True, by=None, alg=None, **kwargs):
             e.append(prev)
         ends[pid] = e
         sizes_mine[pid] = [e[0]] + [e[i] - e[i - 1] for i in range(1, nparts)]
+    # the size matrix (source worker x destination) on every rank: one small all-gather through the exchange arena
+    wpr = rt.workers_per_rank
+    mine_arr = np.zeros((wpr, nparts), dtype=np.int64)
+    for pid, row in sizes_mine.items():
+        mine_arr[(pid - 1) % wpr] = row
+    allrows = rt.allgather_small(mine_arr.reshape(-1))
     sizes: Dict[int, List[int]] = {}
-    for part in (rt.allgather_object(sizes_mine) if rt.world > 1 else [sizes_mine]):
-        sizes.update(part)
+    for pid in pids:
+        r, w = rt.rank_of(pid), (pid - 1) % wpr
+        sizes[pid] = [int(v) for v in allrows[r].reshape(wpr, nparts)[w]]
 
     # ---- ship piece i to worker i
     totals = [sum(sizes[p][j] for p in pids) for j in range(nparts)]

@@ -114,6 +114,48 @@ class Runtime:
         a["turn"] += 1
         return off
 
+    def allgather_small(self, arr: Optional[np.ndarray] = None, dev_ptr: int = 0, nbytes: int = 0, dtype=np.uint8) -> List[np.ndarray]:
+        """All-gather of one small fixed-size payload per rank WITHOUT a host collective: every rank PUTs its payload (a host array,
+        or ``nbytes`` at ``dev_ptr`` on the device) into slot ``rank`` of every peer's exchange-arena bank, a device-side barrier makes
+        the puts visible, one D2H copy brings the whole bank to the host.  ~50 us instead of the milliseconds of a pickled
+        ``all_gather_object``.  Payloads must have the same size on every rank; falls back to the object gather when they do not fit."""
+        if arr is not None:
+            arr = np.ascontiguousarray(arr)
+            nbytes, dtype = arr.nbytes, arr.dtype
+        if self.world == 1:
+            if arr is not None:
+                return [arr.copy()]
+            out = np.empty(nbytes, dtype=np.uint8)
+            _lib.call("dab_d2h", self.ctx, C.c_void_p(out.ctypes.data), C.c_void_p(dev_ptr), nbytes)
+            self.sync()
+            return [out.view(dtype)]
+        slot = (nbytes + 255) & ~255
+        if not self.fused_combine or slot * self.world > self.arena()["bank_bytes"]:
+            if arr is None:
+                arr = np.empty(nbytes, dtype=np.uint8)
+                _lib.call("dab_d2h", self.ctx, C.c_void_p(arr.ctypes.data), C.c_void_p(dev_ptr), nbytes)
+                self.sync()
+                arr = arr.view(dtype)
+            return self.allgather_object(arr)
+        bank = self.arena_next_bank()
+        peers = self.arena()["peers"]
+        tmp = 0
+        if arr is not None:
+            tmp = self.alloc_temp(max(nbytes, 16))
+            _lib.call("dab_h2d", self.ctx, C.c_void_p(tmp), C.c_void_p(arr.ctypes.data), nbytes)
+            self.sync()                                    # arr may be a temporary of the caller
+            dev_ptr = tmp
+        for r in range(self.world):
+            if nbytes:
+                _lib.call("dab_d2d", self.ctx, C.c_void_p(peers[r] + bank + self.rank * slot), C.c_void_p(dev_ptr), nbytes)
+        self.device_barrier()
+        host = np.empty(slot * self.world, dtype=np.uint8)
+        _lib.call("dab_d2h", self.ctx, C.c_void_p(host.ctypes.data), C.c_void_p(peers[self.rank] + bank), slot * self.world)
+        self.sync()
+        if tmp:
+            self.free_temp(tmp)
+        return [host[r * slot:r * slot + nbytes].view(dtype) for r in range(self.world)]
+
     def allgather_object(self, obj) -> list:
         if self.dist is None:
             return [obj]

@@ -105,7 +105,6 @@ int32_t dab_init(int32_t device, dab_ctx** out) {
     ctx->nranks = 1;
     ctx->fuse_op = -1;
     ctx->opt_combine_timeout_ms = 120000;
-    ctx->opt_gemm_rawhi = 1;
     ctx->cache = new (std::nothrow) dab_alloc_cache();
 #define INIT_CUDA(call)                                                     \
     do {                                                                    \

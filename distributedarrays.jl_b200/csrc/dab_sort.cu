@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(256) sort_copy_if_kernel(const SortPlan* __res
 //      bucket run (full 32-byte sectors instead of one sector request per key)
 constexpr unsigned long long LB_PARTIAL = 1ull << 62, LB_INCLUSIVE = 2ull << 62, LB_FLAGS = 3ull << 62;
 constexpr unsigned long long LB_EPOCH_MASK = ((1ull << 30) - 1ull) << 32;
-constexpr int LB_WINDOW = 16;   // predecessor words fetched per look-back round (independent L2 reads in flight instead of a serial walk)
+constexpr int LB_WINDOW = 8;   // predecessor words fetched per look-back round (independent L2 reads in flight instead of a serial walk)
 
 __device__ __forceinline__ uint32_t sort_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -15,8 +15,13 @@ from darray_b200 import _lib  # noqa: E402
 
 def main():
     rt = dab.init(use_dist=False)
+    if os.environ.get("GEMM_KC"):
+        rt.set_option("gemm_kc", int(os.environ["GEMM_KC"]))
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1590.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
-    for (m, n, k) in [(4096, 4096, 4096), (8192, 8192, 8192), (16384, 8192, 4096), (8192, 128, 8192)]:
+    shapes = [(4096, 4096, 4096), (8192, 8192, 8192), (16384, 8192, 4096), (8192, 128, 8192)]
+    if os.environ.get("GEMM_KC"):
+        shapes = [(8192, 8192, 8192)]
+    for (m, n, k) in shapes:
         A = dab.drand((m, k), dtype=np.float32, seed=1)
         B = dab.drand((k, n), dtype=np.float32, seed=2)
         Cc = dab.B200Array.empty(rt, (m, n), np.float32)

@@ -201,6 +201,20 @@ __device__ __forceinline__ float4 split_tf32(float4& v) {   // v <- hi (tf32, ro
 // shared-memory-bandwidth bound: tensor-core operand reads + conversion = ~190 KiB per 32-deep k-block against 128 B/clk).  Measured at
 // 8192^3: +2-5 % speed, but the always-positive remainder of a truncation makes the dropped a_lo*b_lo term a bias: max error 1.02e-6 instead of
 // 0.93e-6 at k = 8192 on same-sign data.  The default keeps the round-to-nearest split (hi rewritten in place), which stays inside 1e-6.
+__device__ __forceinline__ float4 lo_of_trunc(const float4& v) {   // tf32_rn(v - trunc_tf32(v)), the remainder of the hardware's truncation
+    float4 lo;
+#define DAB_LO1(c)                                                                  \
+    {                                                                               \
+        const float r = v.c - __uint_as_float(__float_as_uint(v.c) & 0xffffe000u);  \
+        uint32_t l;                                                                 \
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));                        \
+        lo.c = __uint_as_float(l);                                                  \
+    }
+    DAB_LO1(x) DAB_LO1(y) DAB_LO1(z) DAB_LO1(w)
+#undef DAB_LO1
+    return lo;
+}
+
 template <bool TA, bool RAWHI>
 __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                                     float* __restrict__ C, size_t ldc, uint32_t m, uint32_t n, uint32_t k, uint32_t kc_blocks) {

@@ -208,7 +208,7 @@ def mul_(y: DArray, A: Union[DArray, Transpose], x, alpha=1, beta=0) -> DArray:
     # into its slot of the stack
     temps: List[B200Array] = []
     xblocks: Dict[int, B200Array] = {}
-    puts, sends = [], []
+    puts, sends = [], {}
     for j in range(gj):
         for i in range(gi):
             pid = tile_pid(i, j)
@@ -228,7 +228,7 @@ def mul_(y: DArray, A: Union[DArray, Transpose], x, alpha=1, beta=0) -> DArray:
                 if use_arena:
                     puts.append((peers[orank] + bank + tables[orank][0][i] + j * plen * isz, rptr, plen * isz))
                 else:
-                    sends.append((rptr, plen * isz, orank))
+                    sends[(i, j)] = rptr
             _lib.call("dab_gemv", rt.ctx, code, 1 if trans else 0, C.c_void_p(ch.ptr), ch.shape[0], ch.shape[1], C.c_void_p(xblocks[j].ptr),
                       C.c_void_p(rptr))
     # ---- ship the tile results to the owner of y's chunk i (the fetch(rij) of :113-115)
@@ -239,7 +239,7 @@ def mul_(y: DArray, A: Union[DArray, Transpose], x, alpha=1, beta=0) -> DArray:
         rt.device_barrier()                                # every producer's puts have landed; also: every reader of x is done with it
     elif rt.world > 1:
         plan = matvec_exchange_plan(L, y.layout, trans, rt.rank_of, rt.rank)   # same (i, j) order on both sides of every pair
-        sends = [(ptr, nb, peer) for ptr, nb, peer in sends if nb]
+        sends = [(sends[(i, j)], plen * isz, peer) for i, j, plen, peer in plan["sends"] if plen]
         recvs = [(my_base + my_tab[i] + j * plen * isz, plen * isz, peer) for i, j, plen, peer in plan["recvs"] if plen]
         if sends or recvs:
             _lib.call("dab_group_start", rt.ctx)

@@ -97,6 +97,7 @@ class Runtime:
         consumer's bank with device-to-device copies over NVLink and ordered by ``device_barrier`` -- no NCCL launch, no host sync.
         Banks alternate per exchange, so a producer can fill the next bank while the consumer still reads the previous one."""
         if self._arena is None:
+            bank_bytes = int(os.environ.get("DAB_ARENA_KB", bank_bytes >> 10)) << 10   # DAB_ARENA_KB=1 forces the NCCL fallbacks (tests)
             ptr = self.alloc(2 * bank_bytes + 256)
             base = (ptr + 255) & ~255
             if self.world > 1:

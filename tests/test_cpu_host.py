@@ -266,3 +266,28 @@ def test_bench_reference_arm_contract():
         assert k in j, k
     assert j["impl"] == "reference" and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["value"] > 0
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["value"] == j["value"]
+
+
+def test_bench_parity_fold_check_detects_a_swapped_order():
+    """bench.py's `fold` check compares sum(y) with the Float32 LEFT fold of the chunk results in procs(d) order (reference
+    src/mapreduce.jl:34): a fold in another order must not pass for chunk results of the bench's magnitude."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rng = np.random.default_rng(0)
+    differs = 0
+    for _ in range(50):
+        vals = (rng.random(8) * 1e6 + 2.68e8).astype(np.float32)          # 8 chunk sums of 2^30 values of mean 0.25..1.75
+        a = bench.left_fold_f32(list(vals))
+        b = bench.left_fold_f32(list(vals[::-1]))
+        want = np.float32(0)
+        acc = np.float32(vals[0])
+        for v in vals[1:]:
+            acc = np.float32(acc + v)
+        assert a.tobytes() == acc.tobytes()
+        differs += a.tobytes() != b.tobytes()
+    assert differs > 10                                                    # the order is visible in Float32
+    assert bench.rel_err(1.0 + 2e-6, 1.0) > bench.REL_TOL > bench.rel_err(1.0 + 5e-7, 1.0)

@@ -177,21 +177,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {  
           "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
 }
-__device__ __forceinline__ float4 split_tf32(float4& v) {   // v <- hi (tf32, round to nearest), returns lo = tf32(v - hi)
+// fp32 -> (tf32 hi, tf32 lo) with INTEGER arithmetic: round-to-nearest (ties away, the semantics of cvt.rna.tf32.f32) is "add half an ulp of
+// the 13 dropped bits, clear them".  cvt.rna.tf32.f32 issues at a fraction of the ALU rate on sm_100a and made the four converter warps the
+// limiter of the whole kernel (2 conversions per element); IADD / LOP3 / FSUB run at full rate.  The tensor core ignores the low 13 bits of
+// a tf32 operand, so "lo" only needs the rounding add, not the mask.
+__device__ __forceinline__ float tf32_rn_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_rn_lo(float r) { return __uint_as_float(__float_as_uint(r) + 0x1000u); }
+__device__ __forceinline__ float4 split_tf32(float4& v) {   // v <- hi (tf32, round to nearest), returns lo = tf32_rn(v - hi)
     float4 lo;
-    uint32_t h;
-#define DAB_SPLIT1(c)                                                    \
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v.c));               \
-    {                                                                    \
-        const float hf = __uint_as_float(h);                             \
-        const float r = v.c - hf;                                        \
-        uint32_t l;                                                      \
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));             \
-        lo.c = __uint_as_float(l);                                       \
-        v.c = hf;                                                        \
-    }
-    DAB_SPLIT1(x) DAB_SPLIT1(y) DAB_SPLIT1(z) DAB_SPLIT1(w)
-#undef DAB_SPLIT1
+    const float hx = tf32_rn_hi(v.x), hy = tf32_rn_hi(v.y), hz = tf32_rn_hi(v.z), hw = tf32_rn_hi(v.w);
+    lo.x = tf32_rn_lo(__fsub_rn(v.x, hx));
+    lo.y = tf32_rn_lo(__fsub_rn(v.y, hy));
+    lo.z = tf32_rn_lo(__fsub_rn(v.z, hz));
+    lo.w = tf32_rn_lo(__fsub_rn(v.w, hw));
+    v = make_float4(hx, hy, hz, hw);
     return lo;
 }
 
@@ -203,15 +202,10 @@ __device__ __forceinline__ float4 split_tf32(float4& v) {   // v <- hi (tf32, ro
 // 0.93e-6 at k = 8192 on same-sign data.  The default keeps the round-to-nearest split (hi rewritten in place), which stays inside 1e-6.
 __device__ __forceinline__ float4 lo_of_trunc(const float4& v) {   // tf32_rn(v - trunc_tf32(v)), the remainder of the hardware's truncation
     float4 lo;
-#define DAB_LO1(c)                                                                  \
-    {                                                                               \
-        const float r = v.c - __uint_as_float(__float_as_uint(v.c) & 0xffffe000u);  \
-        uint32_t l;                                                                 \
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));                        \
-        lo.c = __uint_as_float(l);                                                  \
-    }
-    DAB_LO1(x) DAB_LO1(y) DAB_LO1(z) DAB_LO1(w)
-#undef DAB_LO1
+    lo.x = tf32_rn_lo(__fsub_rn(v.x, __uint_as_float(__float_as_uint(v.x) & 0xffffe000u)));
+    lo.y = tf32_rn_lo(__fsub_rn(v.y, __uint_as_float(__float_as_uint(v.y) & 0xffffe000u)));
+    lo.z = tf32_rn_lo(__fsub_rn(v.z, __uint_as_float(__float_as_uint(v.z) & 0xffffe000u)));
+    lo.w = tf32_rn_lo(__fsub_rn(v.w, __uint_as_float(__float_as_uint(v.w) & 0xffffe000u)));
     return lo;
 }
 
@@ -273,8 +267,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32x3_kernel(const __grid
         // ===== MMA issuer: one thread, accumulators in tensor memory =====
         if (lane == 0) {
             // instruction descriptor: D = F32, A = B = TF32, A major (1 = MN-major, the untransposed column-major A), B K-major, N, M
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((TA ? 0u : 1u) << 15) | (0u << 16) | ((uint32_t)(TG_N >> 3) << 17) |
-                                   ((uint32_t)(TG_M >> 4) << 24);
+            const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((TA ? 0u : 1u) << 15) | (0u << 16) | ((uint32_t)(TG_M >> 4) << 24);
+            const uint32_t idesc = idesc_base | ((uint32_t)(TG_N >> 3) << 17);            // N = 128
+            const uint32_t idesc2 = idesc_base | ((uint32_t)((2 * TG_N) >> 3) << 17);     // N = 256: B = [b_hi | b_lo], adjacent tiles of the stage
             for (uint32_t kb = 0; kb < nkb; ++kb) {
                 const uint32_t s = kb % TG_STAGES, ph = (kb / TG_STAGES) & 1u;
                 const uint32_t chunk = kb / kc_blocks, acc = chunk & 1u, use = chunk >> 1;
@@ -285,7 +280,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32x3_kernel(const __grid
                 }
                 mbar_wait(bar0 + 8 * (3 + s), ph);                                          // converted tiles are in place
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = sbase + s * TG_STAGE_BYTES, a_lo = a_hi + TG_TILE_BYTES, b_hi = a_hi + 2 * TG_TILE_BYTES, b_lo = a_hi + 3 * TG_TILE_BYTES;
+                const uint32_t a_hi = sbase + s * TG_STAGE_BYTES, a_lo = a_hi + TG_TILE_BYTES, b_hi = a_hi + 2 * TG_TILE_BYTES;   // b_lo follows b_hi
                 const uint32_t d = tmem_base + acc * (2 * TG_N), ds = d + TG_N;            // main (hi*hi) and correction accumulators of this set
 #pragma unroll
                 for (int j = 0; j < TG_K / 8; ++j) {
@@ -297,11 +292,13 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tf32x3_kernel(const __grid
                     const uint32_t aoff = TA ? (uint32_t)j * 32u : (uint32_t)j * 1024u;
                     const uint32_t albo = TA ? 16u : 4096u, asbo = TA ? 1024u : 512u, alay = TA ? 2u : 1u;
                     const uint64_t dah = umma_desc(a_hi + aoff, albo, asbo, alay), dal = umma_desc(a_lo + aoff, albo, asbo, alay);
-                    const uint64_t dbh = umma_desc(b_hi + j * 32u, 16u, 1024u), dbl = umma_desc(b_lo + j * 32u, 16u, 1024u);
+                    const uint64_t dbh = umma_desc(b_hi + j * 32u, 16u, 1024u);
                     const uint32_t first = (chunk_start && j == 0) ? 0u : 1u;
-                    umma_tf32(ds, dal, dbh, idesc, first);                                  // the two correction products (2^-11 of the main one) ...
-                    umma_tf32(ds, dah, dbl, idesc, 1u);                                     // ... sum in their own accumulator
-                    umma_tf32(d, dah, dbh, idesc, first);
+                    // a_hi x [b_hi | b_lo] as ONE N = 256 instruction: columns 0-127 of the accumulator set take the main product, columns
+                    // 128-255 the correction a_hi*b_lo (b_lo sits right behind b_hi in the stage, same 1024-byte atom stride) -- a_hi is
+                    // read from shared memory once instead of twice; then the other correction a_lo x b_hi onto columns 128-255
+                    umma_tf32(d, dah, dbh, idesc2, first);
+                    umma_tf32(ds, dal, dbh, idesc, 1u);
                 }
                 umma_commit(bar0 + 8 * (6 + s));                                            // frees the smem stage when these MMAs have read it
                 if ((kb + 1) % kc_blocks == 0 || kb + 1 == nkb) umma_commit(bar0 + 8 * (9 + acc));   // partial tile complete

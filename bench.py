@@ -354,13 +354,12 @@ def main():
 
     # clocks: the sampler starts BEFORE the warm-up (nvidia-smi needs ~100 ms to deliver its first sample; the K timed steps alone last
     # ~20 ms) and stops after the per-kernel timings, so every sample is taken while this process keeps the GPU busy.  The warm-up
-    # first runs the step for 0.3 s of wall time (untimed): a freshly created context starts from an idle power state, and the first
+    # first runs 160 untimed steps (~0.3 s): a freshly created context starts from an idle power state, and the first
     # few tens of milliseconds of work run at ramping SM / memory clocks (seen once as a 2.04 ms instead of a 1.86 ms step).
     clocks = ClockSampler(rt.device)
     if rank == 0:
         clocks.start()
-    t_ramp = time.perf_counter()
-    while time.perf_counter() - t_ramp < 0.3:
+    for _ in range(160):     # ~0.3 s; a FIXED count: the step contains a collective, every rank must make the same number of calls
         s = step()
     for _ in range(warmup):
         s = step()

@@ -47,6 +47,9 @@ struct dab_ctx {
     long long opt_gemm_kc;  // dab_set_option("gemm_kc"): k extent summed inside tensor memory before a partial tile is drained (default 64)
     int opt_gemm_rawhi;     // dab_set_option("gemm_rawhi"): 1 = raw fp32 tile as the tf32 "hi" operand (hardware truncation), 0 = RN split
     int opt_gemm_simt;      // dab_set_option("gemm_simt"): 1 = force the SIMT tile kernel for Float32 (A/B measurements)
+    int opt_gemv_phase;     // dab_set_option("gemv_phase"): 1 (default) = phase-class kernel for A*x, 0 = the single-wave aligned / unit-wise pair
+    int opt_gemv_t_cols;    // dab_set_option("gemv_t_cols"): columns one thread of the A'*x kernel carries (4 or 8)
+    int opt_gemv_t_waves;   // dab_set_option("gemv_t_waves"): waves of CTAs the A'*x kernel is split into
     int opt_ew_tma;         // dab_set_option("ew_tma"): route aligned unary elementwise launches through the TMA-staged kernel
     char err[512];
 };

@@ -105,6 +105,9 @@ int32_t dab_init(int32_t device, dab_ctx** out) {
     ctx->nranks = 1;
     ctx->fuse_op = -1;
     ctx->opt_combine_timeout_ms = 120000;
+    ctx->opt_gemv_phase = 1;
+    ctx->opt_gemv_t_waves = 4;
+    ctx->opt_gemv_t_cols = 8;
     ctx->cache = new (std::nothrow) dab_alloc_cache();
 #define INIT_CUDA(call)                                                     \
     do {                                                                    \
@@ -219,6 +222,20 @@ int32_t dab_set_option(dab_ctx* ctx, const char* key, int64_t value) {
     }
     if (strcmp(key, "gemm_rawhi") == 0) {
         ctx->opt_gemm_rawhi = value != 0;
+        return DAB_OK;
+    }
+    if (strcmp(key, "gemv_phase") == 0) {
+        ctx->opt_gemv_phase = value != 0;
+        return DAB_OK;
+    }
+    if (strcmp(key, "gemv_t_cols") == 0) {
+        if (value != 4 && value != 8) return dab_fail(ctx, DAB_ERR_ARG, "gemv_t_cols must be 4 or 8");
+        ctx->opt_gemv_t_cols = (int)value;
+        return DAB_OK;
+    }
+    if (strcmp(key, "gemv_t_waves") == 0) {
+        if (value < 1 || value > 64) return dab_fail(ctx, DAB_ERR_ARG, "gemv_t_waves must be in 1..64");
+        ctx->opt_gemv_t_waves = (int)value;
         return DAB_OK;
     }
     if (strcmp(key, "gemm_simt") == 0) {

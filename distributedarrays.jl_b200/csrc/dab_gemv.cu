@@ -144,6 +144,124 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_n_kernel(const T* __restrict_
     }
 }
 
+// ---- r = A x, columns NOT 16-byte aligned ------------------------------------------------------------------------------------------
+// The leading dimension is not a multiple of VEC (the 37/36-row splits defaultdist produces), so column j starts phase(j) =
+// (a0 + j*m) mod VEC elements past a 16-byte boundary.  Columns j and j + VEC share their phase, so the columns are dealt into VEC
+// classes (blockIdx.y % VEC) and a CTA sweeps one class with a column stride of VEC: inside a class every thread's 16-byte word sits at
+// the same offset in every column, i.e. the thread owns rows 4t - p .. 4t - p + 3 for the class's phase p and runs the aligned kernel's
+// loop unchanged.  The two threads per column whose word straddles a column boundary (rows < 0 or >= m belong to the neighbouring
+// columns) mask those elements.  Aligned chunks take the same kernel (every phase is 0, no warp is masked).  Each class writes its own partial vector; gemv_finish adds the classes and the splits in index order.
+template <typename T, int VEC, int U>
+__global__ void __launch_bounds__(GV_THREADS, 4) gemv_n_phase_kernel(const T* __restrict__ A, size_t m, size_t n, const T* __restrict__ x, int lrt,
+                                                                  size_t cols_per_split, int a0, typename GvAcc<T>::type* __restrict__ part) {
+    using Acc = typename GvAcc<T>::type;
+    __shared__ Acc sh[GV_THREADS * VEC];
+    const int RT = 1 << lrt, CL = GV_THREADS >> lrt;
+    const int ri = threadIdx.x & (RT - 1), cl = threadIdx.x >> lrt;
+    const int klass = blockIdx.y % VEC;
+    const size_t split = blockIdx.y / VEC;
+    const int p = (int)(((size_t)a0 + (size_t)klass * (m % VEC)) % VEC);
+    const size_t nk = n > (size_t)klass ? (n - klass + VEC - 1) / VEC : 0;   // columns of this class
+    const size_t jlo = split * cols_per_split;
+    const size_t jhi = (jlo + cols_per_split < nk) ? jlo + cols_per_split : nk;
+    const long long rowbase = (long long)((size_t)blockIdx.x * RT * VEC + (size_t)ri * VEC) - p;
+    Acc acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = Acc(0);
+    // A thread whose word straddles a column boundary must mask the elements of the neighbouring column.  The choice between the plain
+    // and the masked loop is made per WARP (a lane taking its own loop would double the warp's time, and with one wave of CTAs the
+    // slowest warp is the kernel's time); the masked loop issues the same 16-byte loads.
+    const bool active = rowbase < (long long)m;
+    const bool interior = rowbase >= 0 && rowbase + VEC <= (long long)m;
+    const bool plain = __all_sync(0xffffffffu, interior || !active);
+    if (active) {
+        const T* base = A + rowbase + (long long)klass * (long long)m;   // the thread's word in the class's first column
+        const size_t cstride = (size_t)VEC * m;                          // elements between two columns of a class
+        const T* xk = x + klass;
+        size_t j = jlo + cl;
+        const size_t step = (size_t)CL;
+        if (plain) {
+            for (; j + (U - 1) * step < jhi; j += U * step) {
+                GvVec<T, VEC> a[U];
+                T xv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    a[u] = gv_load_stream<T, VEC>(base + (j + u * step) * cstride);
+                    xv[u] = __ldg(xk + (j + u * step) * VEC);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) gv_mac(acc[v], (Acc)a[u].v[v], (Acc)xv[u]);
+            }
+            for (; j < jhi; j += step) {
+                const GvVec<T, VEC> a = gv_load_stream<T, VEC>(base + j * cstride);
+                const Acc xj = (Acc)__ldg(xk + j * VEC);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) gv_mac(acc[v], (Acc)a.v[v], xj);
+            }
+        } else {
+            bool ok[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) ok[v] = rowbase + v >= 0 && rowbase + v < (long long)m;
+            // The only words that reach outside the matrix are the head of column 0 and the tail of column n-1: the lane that meets
+            // one of them takes it element-wise BEFORE the sweep, so that the sweep itself stays branch-free (same loads in flight as
+            // the plain loop).
+            size_t jend = jhi;
+            if (j < jhi) {
+                const Acc zero = Acc(0);
+                if (rowbase < 0 && klass == 0 && j == 0) {                                       // column 0 is this lane's first
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) gv_mac(acc[v], ok[v] ? (Acc)__ldcs(base + v) : zero, (Acc)__ldg(xk));
+                    j += step;
+                }
+                const size_t jl = nk - 1;                                                        // class index of column n-1, if ours
+                if (rowbase + VEC > (long long)m && (size_t)klass == (n - 1) % VEC && jhi == nk && jl >= j && (jl - j) % step == 0) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v)
+                        gv_mac(acc[v], ok[v] ? (Acc)__ldcs(base + jl * cstride + v) : zero, (Acc)__ldg(xk + jl * VEC));
+                    jend = jl;                                                                   // the lane's sweep stops before it
+                }
+            }
+            for (; j + (U - 1) * step < jend; j += U * step) {
+                GvVec<T, VEC> a[U];
+                T xv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    a[u] = gv_load_stream<T, VEC>(base + (j + u * step) * cstride);
+                    xv[u] = __ldg(xk + (j + u * step) * VEC);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) gv_mac(acc[v], ok[v] ? (Acc)a[u].v[v] : Acc(0), (Acc)xv[u]);
+            }
+            for (; j < jend; j += step) {
+                const GvVec<T, VEC> a = gv_load_stream<T, VEC>(base + j * cstride);
+                const Acc xj = (Acc)__ldg(xk + j * VEC);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) gv_mac(acc[v], ok[v] ? (Acc)a.v[v] : Acc(0), xj);
+            }
+        }
+    }
+    if (CL > 1) {  // fold the column lanes in lane order
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) sh[threadIdx.x * VEC + v] = acc[v];
+        __syncthreads();
+        if (cl == 0)
+            for (int c = 1; c < CL; ++c)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[v] += sh[((c << lrt) + ri) * VEC + v];
+    }
+    if (cl == 0) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const long long row = rowbase + v;
+            if (row >= 0 && row < (long long)m) part[(size_t)blockIdx.y * m + (size_t)row] = acc[v];
+        }
+    }
+}
+
 // ---- r = A' x ---------------------------------------------------------------------------------------------------------------
 // grid (column tiles, row splits); lli = log2(LI); a CTA covers G consecutive groups of (256 / LI) * COLS columns
 template <typename T, int VEC, int COLS>
@@ -234,7 +352,8 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_finish_kernel(const typename 
     const size_t k = (size_t)blockIdx.x * GV_THREADS + threadIdx.x;
     if (k >= nout) return;
     Acc acc = part[k];
-    for (int s = 1; s < nsplit; ++s) acc += part[(size_t)s * nout + k];
+#pragma unroll 8
+    for (int s = 1; s < nsplit; ++s) acc += part[(size_t)s * nout + k];   // split order; unrolled so that the loads overlap
     y[k] = (T)acc;
 }
 
@@ -299,10 +418,46 @@ int32_t launch_n(dab_ctx* ctx, const T* A, size_t m, size_t n, const T* x, T* y)
     return launch_n_cfg<T, VEC, 4, 1>(ctx, A, m, n, x, y);
 }
 
+// the phase-class variant (columns not 16-byte aligned): VEC classes x nsplit column splits in gridDim.y, always through the partials
 template <typename T, int VEC>
+int32_t launch_n_phase(dab_ctx* ctx, const T* A, size_t m, size_t n, const T* x, T* y) {
+    using Acc = typename GvAcc<T>::type;
+    constexpr int U = 4;
+    const size_t rvecs = (m + 2 * (VEC - 1)) / VEC;   // words a column can touch at the worst phase
+    int lrt = ceil_log2(rvecs);
+    if (lrt > 8) lrt = 8;
+    const int RT = 1 << lrt, CL = GV_THREADS >> lrt;
+    const size_t gx = (rvecs + RT - 1) / RT;
+    const size_t slots = (size_t)ctx->sm_count * (size_t)dab_resident_ctas((const void*)gemv_n_phase_kernel<T, VEC, U>, GV_THREADS);
+    // four waves of CTAs rather than one: the CTAs holding a masked warp run a little longer and a single wave would wait for them
+    // (measured: tools/sweep_gemv.cu, profiles/r2_sweep_gemv.txt); the partial vectors stay below 1/32 of the matrix bytes
+    size_t want = 4 * slots / (gx * VEC);
+    if (want > n / (32 * VEC * (sizeof(Acc) / sizeof(T)))) want = n / (32 * VEC * (sizeof(Acc) / sizeof(T)));
+    if (want < 1) want = 1;
+    const size_t nk = (n + VEC - 1) / VEC;            // columns of the largest class
+    size_t max_split = nk / ((size_t)CL * U * 4);
+    if (max_split < 1) max_split = 1;
+    size_t nsplit = want < max_split ? want : max_split;
+    if (nsplit * VEC > 65535) nsplit = 65535 / VEC;
+    size_t cps = (nk + nsplit - 1) / nsplit;
+    nsplit = (nk + cps - 1) / cps;
+    const size_t ny = nsplit * VEC;
+    int32_t st = gv_scratch(ctx, ny * m * sizeof(Acc));
+    if (st != DAB_OK) return st;
+    Acc* part = (Acc*)ctx->dim_scratch;
+    DAB_REQUIRE(ctx, gx <= 0x7fffffffull, DAB_ERR_ARG, "dab_gemv: too many row tiles");
+    const int a0 = (int)(((uintptr_t)A / sizeof(T)) % VEC);
+    dim3 grid((unsigned)gx, (unsigned)ny);
+    gemv_n_phase_kernel<T, VEC, U><<<grid, GV_THREADS, 0, ctx->stream>>>(A, m, n, x, lrt, cps, a0, part);
+    DAB_LAUNCHED(ctx);
+    gemv_finish_kernel<T><<<(unsigned)((m + GV_THREADS - 1) / GV_THREADS), GV_THREADS, 0, ctx->stream>>>(part, m, (int)ny, y);
+    DAB_LAUNCHED(ctx);
+    return DAB_OK;
+}
+
+template <typename T, int VEC, int COLS>
 int32_t launch_t(dab_ctx* ctx, const T* A, size_t m, size_t n, const T* x, T* y) {
     using Acc = typename GvAcc<T>::type;
-    constexpr int COLS = 4;
     const size_t rvecs = (m + VEC - 1) / VEC;
     int lli = ceil_log2(rvecs);
     if (lli > 8) lli = 8;
@@ -316,7 +471,8 @@ int32_t launch_t(dab_ctx* ctx, const T* A, size_t m, size_t n, const T* x, T* y)
     const size_t cols_per_cta = (size_t)CB * COLS * G;
     const size_t gx = (n + cols_per_cta - 1) / cols_per_cta;
     const size_t slots = (size_t)ctx->sm_count * (size_t)dab_resident_ctas((const void*)gemv_t_kernel<T, VEC, COLS>, GV_THREADS);
-    const size_t want = slots / gx > 0 ? slots / gx : 1;
+    const size_t waves = ctx->opt_gemv_t_waves > 0 ? (size_t)ctx->opt_gemv_t_waves : 1;
+    const size_t want = waves * slots / gx > 0 ? waves * slots / gx : 1;
     const size_t unit = (size_t)LI * VEC;  // rows one sweep step covers; splits start on a multiple of it (keeps 16-B alignment)
     size_t max_split = m / (unit * 16);
     if (max_split < 1) max_split = 1;
@@ -360,8 +516,18 @@ int32_t gemv_t(dab_ctx* ctx, int32_t trans, const T* A, size_t m, size_t n, cons
     }
     // 16-byte loads need every column start 16-byte aligned: base aligned and m a multiple of VEC (x too for the A' x sweep)
     const bool vec = ((uintptr_t)A % 16 == 0) && (m % VEC == 0) && (!trans || (uintptr_t)x % 16 == 0);
-    if (!trans) return vec ? launch_n<T, VEC>(ctx, A, m, n, x, y) : launch_n<T, 1>(ctx, A, m, n, x, y);
-    return vec ? launch_t<T, VEC>(ctx, A, m, n, x, y) : launch_t<T, 1>(ctx, A, m, n, x, y);
+    if (!trans) {
+        // The phase-class kernel is the default for every chunk big enough to matter: 16-byte loads whatever the alignment of the
+        // columns, and four waves of CTAs (6.7-6.8 TB/s on B200 against 6.4 for the single-wave kernel on aligned chunks and 4.2 for
+        // unit-wise loads on misaligned ones; profiles/r2_gemv_phase.txt).  dab_set_option("gemv_phase", 0) restores the round-1 pair.
+        if (ctx->opt_gemv_phase && (uintptr_t)A % sizeof(T) == 0 && m >= 64 && n >= 4 * VEC) return launch_n_phase<T, VEC>(ctx, A, m, n, x, y);
+        if (vec) return launch_n<T, VEC>(ctx, A, m, n, x, y);
+        return launch_n<T, 1>(ctx, A, m, n, x, y);
+    }
+    // columns a thread carries (x is loaded once per COLS column elements): 8 with 16-byte loads (Float32 32768 x 16384: 6.47 TB/s
+    // against 5.91 with 4; profiles/r2_gemv_phase.txt), dab_set_option("gemv_t_cols", 4) for the A/B measurement
+    if (ctx->opt_gemv_t_cols == 8 && vec) return launch_t<T, VEC, 8>(ctx, A, m, n, x, y);
+    return vec ? launch_t<T, VEC, 4>(ctx, A, m, n, x, y) : launch_t<T, 1, 4>(ctx, A, m, n, x, y);
 }
 
 }  // namespace

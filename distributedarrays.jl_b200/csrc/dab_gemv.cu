@@ -14,6 +14,8 @@
 //       lane order, splits by gemv_finish.
 //   trans = 1 (r = A' x, reduce down each contiguous column):  LI lanes run down a column (16-B loads), a thread carries COLS
 //       adjacent columns so x is loaded once per COLS column elements; the row range is split over gridDim.y.
+//   Columns that do not start on 16-byte boundaries (leading dimension not a multiple of 16 bytes): the *_phase kernels deal the
+//       columns into VEC classes of equal phase and keep the 16-byte loads; A x takes that kernel for aligned chunks as well.
 #include "dab_common.cuh"
 
 namespace {
@@ -345,6 +347,116 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_t_kernel(const T* __restrict_
     }
 }
 
+// ---- r = A' x, columns NOT 16-byte aligned -----------------------------------------------------------------------------------------
+// Same dealing of the columns into VEC phase classes as gemv_n_phase_kernel: a thread carries COLS columns of ONE class (klass, klass +
+// VEC, ...), so the first 16-byte boundary lies `head` = (VEC - phase) % VEC rows below the top of every one of them.  The sweep runs over
+// the words that lie entirely inside the column (16-byte loads; the matching x elements start at x + head, which is in general not
+// 16-byte aligned: element-wise cached loads, or one 16-byte load when it happens to be); the <= VEC-1 rows above the first and below
+// the last full word are added element-wise by two lanes of the first row split.  No load ever leaves the column.
+template <typename T, int VEC, int COLS>
+__global__ void __launch_bounds__(GV_THREADS) gemv_t_phase_kernel(const T* __restrict__ A, size_t m, size_t n, const T* __restrict__ x, int lli,
+                                                                  int G, size_t words_per_split, int a0,
+                                                                  typename GvAcc<T>::type* __restrict__ part, T* __restrict__ y) {
+    using Acc = typename GvAcc<T>::type;
+    __shared__ Acc sh[(GV_THREADS / 32) * COLS];
+    const int LI = 1 << lli, CB = GV_THREADS >> lli;
+    const int li = threadIdx.x & (LI - 1), cb = threadIdx.x >> lli;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int klass = blockIdx.x % VEC;
+    const size_t gblock = blockIdx.x / VEC;
+    const int p = (int)(((size_t)a0 + (size_t)klass * (m % VEC)) % VEC);
+    const size_t head = (size_t)((VEC - p) % VEC);
+    const size_t nfull = (m - head) / VEC;                                   // whole 16-byte words inside a column of this class
+    const size_t tail0 = head + nfull * VEC;                                 // first row below the last full word
+    const size_t nk = n > (size_t)klass ? (n - klass + VEC - 1) / VEC : 0;   // columns of this class
+    const size_t wlo = (size_t)blockIdx.y * words_per_split;
+    const size_t whi = (wlo + words_per_split < nfull) ? wlo + words_per_split : nfull;
+    const size_t cstride = (size_t)VEC * m;                                  // elements between two columns of a class
+    const T* xh = x + head;
+    const bool xal = ((uintptr_t)xh % (sizeof(T) * VEC)) == 0;
+    for (int g = 0; g < G; ++g) {
+        const size_t jj0 = ((gblock * G + g) * CB + cb) * COLS;              // class index of the thread's first column
+        Acc acc[COLS];
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) acc[c] = Acc(0);
+        if (jj0 < nk) {
+            const int nc = (nk - jj0 < (size_t)COLS) ? (int)(nk - jj0) : COLS;
+            const T* c0 = A + ((size_t)klass + (size_t)VEC * jj0) * m;      // top of the first column
+            const T* p0 = c0 + head;                                         // its first full word (16-byte aligned)
+            size_t w = wlo + li;
+            if (nc == COLS) {
+                for (; w < whi; w += LI) {
+                    GvVec<T, VEC> a[COLS], xv;
+#pragma unroll
+                    for (int c = 0; c < COLS; ++c) a[c] = gv_load_stream<T, VEC>(p0 + c * cstride + w * VEC);
+                    if (xal) xv = gv_load_cached<T, VEC>(xh + w * VEC);
+                    else {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) xv.v[v] = __ldg(xh + w * VEC + v);
+                    }
+#pragma unroll
+                    for (int c = 0; c < COLS; ++c)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) gv_mac(acc[c], (Acc)a[c].v[v], (Acc)xv.v[v]);
+                }
+            } else {
+                for (; w < whi; w += LI) {
+#pragma unroll
+                    for (int c = 0; c < COLS; ++c)
+                        if (c < nc) {
+                            const GvVec<T, VEC> a = gv_load_stream<T, VEC>(p0 + c * cstride + w * VEC);
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) gv_mac(acc[c], (Acc)a.v[v], (Acc)__ldg(xh + w * VEC + v));
+                        }
+                }
+            }
+            if (blockIdx.y == 0) {  // the rows outside the full words: lane 0 the head, the next lane the tail
+                if (li == 0)
+                    for (size_t i = 0; i < head; ++i) {
+                        const Acc xi = (Acc)__ldg(x + i);
+#pragma unroll
+                        for (int c = 0; c < COLS; ++c)
+                            if (c < nc) gv_mac(acc[c], (Acc)__ldcs(c0 + c * cstride + i), xi);
+                    }
+                if (li == (LI > 1 ? 1 : 0))
+                    for (size_t i = tail0; i < m; ++i) {
+                        const Acc xi = (Acc)__ldg(x + i);
+#pragma unroll
+                        for (int c = 0; c < COLS; ++c)
+                            if (c < nc) gv_mac(acc[c], (Acc)__ldcs(c0 + c * cstride + i), xi);
+                    }
+            }
+        }
+        // fold the LI lanes of each column group (same tree as gemv_t_kernel)
+        const int W = LI < 32 ? LI : 32;
+        for (int s = W >> 1; s > 0; s >>= 1)
+#pragma unroll
+            for (int c = 0; c < COLS; ++c) acc[c] += __shfl_down_sync(0xffffffffu, acc[c], s, W);
+        if (LI > 32) {
+            if (lane == 0)
+#pragma unroll
+                for (int c = 0; c < COLS; ++c) sh[warp * COLS + c] = acc[c];
+            __syncthreads();
+            if (li == 0) {
+                const int nw = LI >> 5;
+                for (int w2 = 1; w2 < nw; ++w2)
+#pragma unroll
+                    for (int c = 0; c < COLS; ++c) acc[c] += sh[(warp + w2) * COLS + c];
+            }
+            __syncthreads();
+        }
+        if (li == 0 && jj0 < nk) {
+#pragma unroll
+            for (int c = 0; c < COLS; ++c)
+                if (jj0 + c < nk) {
+                    const size_t j = (size_t)klass + (size_t)VEC * (jj0 + c);
+                    if (part) part[(size_t)blockIdx.y * n + j] = acc[c];
+                    else y[j] = (T)acc[c];
+                }
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(GV_THREADS) gemv_finish_kernel(const typename GvAcc<T>::type* __restrict__ part, size_t nout, int nsplit,
                                                                  T* __restrict__ y) {
@@ -498,6 +610,50 @@ int32_t launch_t(dab_ctx* ctx, const T* A, size_t m, size_t n, const T* x, T* y)
     return DAB_OK;
 }
 
+// the phase-class variant of A' x (columns not 16-byte aligned)
+template <typename T, int VEC, int COLS>
+int32_t launch_t_phase(dab_ctx* ctx, const T* A, size_t m, size_t n, const T* x, T* y) {
+    using Acc = typename GvAcc<T>::type;
+    const size_t words = m / VEC;                                  // full words of a column at phase 0 (an upper bound for the others)
+    int lli = ceil_log2(words);
+    if (lli > 8) lli = 8;
+    const int LI = 1 << lli, CB = GV_THREADS >> lli;
+    const size_t group_bytes = (size_t)CB * COLS * m * sizeof(T);
+    size_t Gs = group_bytes ? (65536 + group_bytes - 1) / group_bytes : 1;
+    if (Gs > 16) Gs = 16;
+    if (Gs < 1) Gs = 1;
+    const int G = (int)Gs;
+    const size_t nk = (n + VEC - 1) / VEC;                         // columns of the largest class
+    const size_t cols_per_cta = (size_t)CB * COLS * G;
+    const size_t gx = ((nk + cols_per_cta - 1) / cols_per_cta) * VEC;
+    const size_t slots = (size_t)ctx->sm_count * (size_t)dab_resident_ctas((const void*)gemv_t_phase_kernel<T, VEC, COLS>, GV_THREADS);
+    const size_t waves = ctx->opt_gemv_t_waves > 0 ? (size_t)ctx->opt_gemv_t_waves : 1;
+    const size_t want = waves * slots / gx > 0 ? waves * slots / gx : 1;
+    size_t max_split = words / ((size_t)LI * 16);
+    if (max_split < 1) max_split = 1;
+    size_t nsplit = want < max_split ? want : max_split;
+    if (nsplit > 65535) nsplit = 65535;
+    size_t wps = (words + nsplit - 1) / nsplit;
+    wps = (wps + LI - 1) / LI * LI;
+    nsplit = (words + wps - 1) / wps;
+    Acc* part = nullptr;
+    if (nsplit > 1) {
+        int32_t st = gv_scratch(ctx, nsplit * n * sizeof(Acc));
+        if (st != DAB_OK) return st;
+        part = (Acc*)ctx->dim_scratch;
+    }
+    DAB_REQUIRE(ctx, gx <= 0x7fffffffull, DAB_ERR_ARG, "dab_gemv: too many column tiles");
+    const int a0 = (int)(((uintptr_t)A / sizeof(T)) % VEC);
+    dim3 grid((unsigned)gx, (unsigned)nsplit);
+    gemv_t_phase_kernel<T, VEC, COLS><<<grid, GV_THREADS, 0, ctx->stream>>>(A, m, n, x, lli, G, wps, a0, part, y);
+    DAB_LAUNCHED(ctx);
+    if (part) {
+        gemv_finish_kernel<T><<<(unsigned)((n + GV_THREADS - 1) / GV_THREADS), GV_THREADS, 0, ctx->stream>>>(part, n, (int)nsplit, y);
+        DAB_LAUNCHED(ctx);
+    }
+    return DAB_OK;
+}
+
 template <typename T>
 __global__ void gv_zero_kernel(T* y, size_t n) {
     const size_t k = (size_t)blockIdx.x * GV_THREADS + threadIdx.x;
@@ -527,6 +683,9 @@ int32_t gemv_t(dab_ctx* ctx, int32_t trans, const T* A, size_t m, size_t n, cons
     // columns a thread carries (x is loaded once per COLS column elements): 8 with 16-byte loads (Float32 32768 x 16384: 6.47 TB/s
     // against 5.91 with 4; profiles/r2_gemv_phase.txt), dab_set_option("gemv_t_cols", 4) for the A/B measurement
     if (ctx->opt_gemv_t_cols == 8 && vec) return launch_t<T, VEC, 8>(ctx, A, m, n, x, y);
+    // misaligned columns: the phase-class kernel keeps the 16-byte loads (gemv_phase = 0: unit-wise loads, the round-1 kernel)
+    if (!vec && ctx->opt_gemv_phase && (uintptr_t)A % sizeof(T) == 0 && (uintptr_t)x % sizeof(T) == 0 && m >= 64 && n >= 4 * VEC)
+        return launch_t_phase<T, VEC, 4>(ctx, A, m, n, x, y);   // 4 columns per thread: 8 cost 128 registers here (6.4-6.8 vs 5.4-6.1 TB/s)
     return vec ? launch_t<T, VEC, 4>(ctx, A, m, n, x, y) : launch_t<T, 1, 4>(ctx, A, m, n, x, y);
 }
 

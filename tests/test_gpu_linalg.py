@@ -62,50 +62,63 @@ def test_gemv_kernel_all_shapes(dab, rt1, dtype, trans):
         _check_matvec(_gemv(dab, rt1, A, x, trans), A, x, trans)
 
 
-def _gemv_offset(dab, rt, A, x, off, phase=1):
-    """A * x with the matrix placed `off` elements past a 256-byte aligned allocation (every column phase of the 16-byte words)."""
+def _gemv_offset(dab, rt, A, x, off, phase=1, trans=0, xoff=0, cols=8):
+    """A * x (or A' * x) with the matrix placed `off` elements and x `xoff` elements past a 256-byte aligned allocation (every phase
+    of the 16-byte words)."""
     from darray_b200 import _lib
     m, n = A.shape
     flat = np.zeros(m * n + off, dtype=A.dtype)
     flat[off:] = np.asfortranarray(A).reshape(-1, order="F")
+    xf = np.zeros(x.size + xoff, dtype=A.dtype)
+    xf[xoff:] = x
     dA = dab.B200Array.from_numpy(rt, flat)
-    dx = dab.B200Array.from_numpy(rt, x)
-    dr = dab.B200Array.empty(rt, (m,), A.dtype)
+    dx = dab.B200Array.from_numpy(rt, xf)
+    dr = dab.B200Array.empty(rt, (n if trans else m,), A.dtype)
     rt.set_option("gemv_phase", phase)
+    rt.set_option("gemv_t_cols", cols)
     try:
-        _lib.call("dab_gemv", rt.ctx, dab.dab_dtype(A.dtype), 0, C.c_void_p(dA.ptr + off * A.dtype.itemsize), m, n, C.c_void_p(dx.ptr),
+        isz = A.dtype.itemsize
+        _lib.call("dab_gemv", rt.ctx, dab.dab_dtype(A.dtype), int(trans), C.c_void_p(dA.ptr + off * isz), m, n, C.c_void_p(dx.ptr + xoff * isz),
                   C.c_void_p(dr.ptr))
         out = dr.to_numpy()
     finally:
         rt.set_option("gemv_phase", 1)
+        rt.set_option("gemv_t_cols", 8)
     for b in (dA, dx, dr):
         b.free()
     return out
 
 
+@pytest.mark.parametrize("trans", [0, 1])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64])
-def test_gemv_misaligned_columns_phase_classes(dab, rt1, dtype):
-    """A*x when the columns do not start on 16-byte boundaries (leading dimension not a multiple of 16 bytes and / or a misaligned
-    base): the phase-class kernel against the oracle, for every phase of the base pointer, and against the unit-wise kernel."""
-    rng = np.random.default_rng(77)
-    for (m, n) in [(65, 17), (67, 16), (257, 4096), (1001, 515), (1023, 4097), (4099, 63), (32769, 77), (64, 1000), (1026, 130)]:
+def test_gemv_misaligned_columns_phase_classes(dab, rt1, dtype, trans):
+    """A*x and A'*x when the columns do not start on 16-byte boundaries (leading dimension not a multiple of 16 bytes and / or a
+    misaligned base, x misaligned too): the phase-class kernels against the oracle, for every phase of the base pointer, and against
+    the unit-wise kernels."""
+    rng = np.random.default_rng(77 + trans)
+    for (m, n) in [(65, 17), (67, 16), (257, 4096), (1001, 515), (1023, 4097), (4099, 63), (32769, 77), (64, 1000), (1026, 130), (66, 35)]:
+        k = m if trans else n
         if np.dtype(dtype).kind == "f":
             A = rng.standard_normal((m, n)).astype(dtype)
-            x = rng.standard_normal(n).astype(dtype)
+            x = rng.standard_normal(k).astype(dtype)
         else:
             hi = 2 ** 28 if dtype == np.int32 else 2 ** 60
             A = rng.integers(-hi, hi, (m, n)).astype(dtype)
-            x = rng.integers(-hi, hi, n).astype(dtype)
-        for off in range(16 // np.dtype(dtype).itemsize):
-            got = _gemv_offset(dab, rt1, A, x, off)
-            _check_matvec(got, A, x, 0)
+            x = rng.integers(-hi, hi, k).astype(dtype)
+        nph = 16 // np.dtype(dtype).itemsize
+        for off in range(nph):
+            xoff = (off * 3 + 1) % nph if trans else 0
+            got = _gemv_offset(dab, rt1, A, x, off, trans=trans, xoff=xoff)
+            _check_matvec(got, A, x, trans)
+            if trans:
+                _check_matvec(_gemv_offset(dab, rt1, A, x, off, trans=1, xoff=0, cols=4), A, x, 1)
             if off in (0, 1):
-                unit = _gemv_offset(dab, rt1, A, x, off, phase=0)
-                if dtype == np.float32:                                      # fp64 carriers: the column order cannot show
+                unit = _gemv_offset(dab, rt1, A, x, off, phase=0, trans=trans, xoff=xoff)
+                if dtype == np.float32:                                      # fp64 carriers: the summation order cannot show
                     assert np.all(np.abs(got - unit) <= np.spacing(np.abs(unit)))
                 elif dtype == np.float64:                                    # a different (still fixed) order of the fp64 sums
-                    scale = np.abs(A) @ np.abs(x)
-                    assert np.all(np.abs(got - unit) <= 1e-14 * scale)
+                    M = A.T if trans else A
+                    assert np.all(np.abs(got - unit) <= 1e-14 * (np.abs(M) @ np.abs(x)))
                 else:
                     assert np.array_equal(got, unit)
 

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """A*x (K9, trans = 0) on Float32 / Float64 chunks whose columns are NOT 16-byte aligned: the phase-class kernel (default) against the
 round-1 pair (dab_set_option gemv_phase=0: single-wave aligned kernel / unit-wise loads), aligned shapes next to misaligned ones; then
-A'*x (trans = 1) over the number of CTA waves (dab_set_option gemv_t_waves).  CUDA events, 10 reps, algorithmic GB/s."""
+A'*x (trans = 1): unit-wise kernel (gemv_phase=0) against the phase-class kernel over the CTA waves (gemv_t_waves) and the columns a
+thread carries (gemv_t_cols).  CUDA events, 10 reps, algorithmic GB/s."""
 import ctypes as C
 import os
 import sys
@@ -54,15 +55,17 @@ for dtype, shapes in ((np.float32, [(32768, 16384), (32767, 16385), (32769, 1638
         _lib.call("dab_fill", rt.ctx, dab.dab_dtype(dtype), C.c_void_p(xt.ptr), xt.size, C.c_void_p(one.ctypes.data))
         fnt = lambda: _lib.call("dab_gemv", rt.ctx, dab.dab_dtype(dtype), 1, C.c_void_p(ch.ptr), m, n, C.c_void_p(xt.ptr), C.c_void_p(rr.ptr))  # noqa: E731
         ref = None
-        for waves, cols in ((1, 4), (2, 4), (4, 4), (8, 4), (1, 8), (4, 8)):
+        for phase, waves, cols in ((0, 4, 8), (1, 1, 4), (1, 4, 4), (1, 1, 8), (1, 4, 8)):
+            rt.set_option("gemv_phase", phase)
             rt.set_option("gemv_t_waves", waves)
             rt.set_option("gemv_t_cols", cols)
             ms = timed(fnt)
             out = rr.to_numpy()
             ref = out if ref is None else ref
             ok = bool(np.all(np.abs(out - ref) <= np.spacing(np.abs(ref))))
-            print(f"gemv T {np.dtype(dtype).name} {m:>8d} x {n:<8d} gemv_t_waves={waves} cols={cols}: {ms:8.4f} ms {m * n * es / ms / 1e6:8.1f} GB/s  (= waves 1 to 1 ulp: {ok})",
-                  flush=True)
+            print(f"gemv T {np.dtype(dtype).name} {m:>8d} x {n:<8d} gemv_phase={phase} waves={waves} cols={cols}: {ms:8.4f} ms {m * n * es / ms / 1e6:8.1f} GB/s"
+                  f"  (= first to 1 ulp: {ok})", flush=True)
+        rt.set_option("gemv_phase", 1)
         rt.set_option("gemv_t_waves", 4)
         rt.set_option("gemv_t_cols", 8)
         xt.free()

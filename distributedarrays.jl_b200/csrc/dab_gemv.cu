@@ -583,7 +583,7 @@ int32_t launch_t(dab_ctx* ctx, const T* A, size_t m, size_t n, const T* x, T* y)
     const size_t cols_per_cta = (size_t)CB * COLS * G;
     const size_t gx = (n + cols_per_cta - 1) / cols_per_cta;
     const size_t slots = (size_t)ctx->sm_count * (size_t)dab_resident_ctas((const void*)gemv_t_kernel<T, VEC, COLS>, GV_THREADS);
-    const size_t waves = ctx->opt_gemv_t_waves > 0 ? (size_t)ctx->opt_gemv_t_waves : 1;
+    const size_t waves = (ctx->opt_gemv_t_waves > 0 && n >= 64) ? (size_t)ctx->opt_gemv_t_waves : 1;
     const size_t want = waves * slots / gx > 0 ? waves * slots / gx : 1;
     const size_t unit = (size_t)LI * VEC;  // rows one sweep step covers; splits start on a multiple of it (keeps 16-B alignment)
     size_t max_split = m / (unit * 16);
@@ -676,15 +676,19 @@ int32_t gemv_t(dab_ctx* ctx, int32_t trans, const T* A, size_t m, size_t n, cons
         // The phase-class kernel is the default for every chunk big enough to matter: 16-byte loads whatever the alignment of the
         // columns, and four waves of CTAs (6.7-6.8 TB/s on B200 against 6.4 for the single-wave kernel on aligned chunks and 4.2 for
         // unit-wise loads on misaligned ones; profiles/r2_gemv_phase.txt).  dab_set_option("gemv_phase", 0) restores the round-1 pair.
-        if (ctx->opt_gemv_phase && (uintptr_t)A % sizeof(T) == 0 && m >= 64 && n >= 4 * VEC) return launch_n_phase<T, VEC>(ctx, A, m, n, x, y);
+        // Where it pays: the VEC class partials cost 2*VEC*m carriers of traffic (16/n of the Float32 matrix bytes) and a short column
+        // leaves row lanes idle -- an aligned chunk switches kernels only when that is below 2 % (measured 4194304 x 128: 5.8 vs 6.4
+        // TB/s, 128 x 4194304: 3.0 vs 5.4), a misaligned one as soon as it beats the unit-wise loads' -35 %.
+        const bool phase_ok = ctx->opt_gemv_phase && (uintptr_t)A % sizeof(T) == 0;
+        if (phase_ok && (vec ? (m >= 4096 && n >= 1024) : (m >= 256 && n >= 64))) return launch_n_phase<T, VEC>(ctx, A, m, n, x, y);
         if (vec) return launch_n<T, VEC>(ctx, A, m, n, x, y);
         return launch_n<T, 1>(ctx, A, m, n, x, y);
     }
     // columns a thread carries (x is loaded once per COLS column elements): 8 with 16-byte loads (Float32 32768 x 16384: 6.47 TB/s
     // against 5.91 with 4; profiles/r2_gemv_phase.txt), dab_set_option("gemv_t_cols", 4) for the A/B measurement
-    if (ctx->opt_gemv_t_cols == 8 && vec) return launch_t<T, VEC, 8>(ctx, A, m, n, x, y);
+    if (ctx->opt_gemv_t_cols == 8 && vec && n >= 64) return launch_t<T, VEC, 8>(ctx, A, m, n, x, y);
     // misaligned columns: the phase-class kernel keeps the 16-byte loads (gemv_phase = 0: unit-wise loads, the round-1 kernel)
-    if (!vec && ctx->opt_gemv_phase && (uintptr_t)A % sizeof(T) == 0 && (uintptr_t)x % sizeof(T) == 0 && m >= 64 && n >= 4 * VEC)
+    if (!vec && ctx->opt_gemv_phase && (uintptr_t)A % sizeof(T) == 0 && (uintptr_t)x % sizeof(T) == 0 && m >= 256 && n >= 64)
         return launch_t_phase<T, VEC, 4>(ctx, A, m, n, x, y);   // 4 columns per thread: 8 cost 128 registers here (6.4-6.8 vs 5.4-6.1 TB/s)
     return vec ? launch_t<T, VEC, 4>(ctx, A, m, n, x, y) : launch_t<T, 1, 4>(ctx, A, m, n, x, y);
 }
@@ -716,12 +720,16 @@ __global__ void __launch_bounds__(256) transpose_box_kernel(U* __restrict__ dst,
     const size_t tr = blockIdx.x % tiles_r, tc = blockIdx.x / tiles_r;  // consecutive CTAs walk down the source rows (address order)
     const size_t r0 = tr * TR_TILE, c0 = tc * TR_TILE;
     constexpr int TY = 256 / TR_TILE;
+    constexpr int NK = TR_TILE / TY;                       // tile rows a thread moves: all NK loads are issued before the first store
     const int tx = threadIdx.x & (TR_TILE - 1), ty = threadIdx.x / TR_TILE;
-#pragma unroll 4
-    for (int k = ty; k < TR_TILE; k += TY) {
-        const size_t r = r0 + tx, c = c0 + k;
-        if (r < rows && c < cols) tile[k][tx] = src[r + c * src_ld];
+    U v[NK];
+#pragma unroll
+    for (int q = 0; q < NK; ++q) {
+        const size_t r = r0 + tx, c = c0 + ty + q * TY;
+        v[q] = (r < rows && c < cols) ? src[r + c * src_ld] : U{};
     }
+#pragma unroll
+    for (int q = 0; q < NK; ++q) tile[ty + q * TY][tx] = v[q];
     __syncthreads();
 #pragma unroll 4
     for (int k = ty; k < TR_TILE; k += TY) {

@@ -99,6 +99,8 @@ _SIGS = {
     "dab_transpose_box": (_i32, [_vp, _i32, _vp, _sz, _vp, _sz, _sz, _sz]),
     "dab_sort": (_i32, [_vp, _i32, _vp, _vp, _vp, _sz]),
     "dab_sorted_split": (_i32, [_vp, _i32, _vp, _sz, _vp, _i32, C.POINTER(C.c_ulonglong)]),
+    "dab_sort_by_key": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _sz, _sz]),
+    "dab_sort_by_key_scratch_bytes": (_i32, [_i32, _sz, C.POINTER(_sz)]),
     "dab_comm_unique_id": (_i32, [_vp]),
     "dab_comm_init_rank": (_i32, [_vp, _vp, _i32, _i32]),
     "dab_comm_destroy": (_i32, [_vp]),

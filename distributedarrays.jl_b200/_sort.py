@@ -13,6 +13,12 @@ scan each sorted chunk for the first ``x > boundaries[i+1]``       ``dab_sorted_
 The result is bit-identical to the reference's for NaN-free input (a sorted vector has one representation once -0.0 < +0.0 is
 fixed); chunk sizes follow from the same boundaries, so the layout matches too.  NaNs sort last; inside the NaN block the
 reference keeps input order, the radix sort orders by payload.
+
+``sort(d; by = f)`` (``:by`` is accepted at src/sort.jl:111 and travels in ``kwargs...`` to every local sort, :8, :22, :61, and to the
+sort of the gathered samples, :77; the split compares ``by(x) > by(boundaries[i+1])``, :32): ``f`` is traced like a broadcast
+closure, ``keys = f.(chunk)`` is ONE fused elementwise kernel, ``dab_sort_by_key`` orders the values stably by those keys (K11 on
+packed key|position words), the split runs on ``f.(sorted chunk)``, and the few hundred samples / boundaries get their keys from the
+same kernel so that host and device agree bit for bit on ``f``.
 """
 from __future__ import annotations
 
@@ -87,6 +93,72 @@ def _sort_chunk(rt, src_ptr: int, n: int, dt: np.dtype, out: B200Array):
         tmp.free()
 
 
+class _KeyFn:
+    """``by`` traced once for the element type of ``d``: the expression tree, the key dtype, and the launches that use it."""
+
+    def __init__(self, rt, by, dt: np.dtype):
+        from . import _broadcast as bc
+        self.rt, self.bc, self.vtag = rt, bc, bc.tag_of(dt)
+        e = bc.trace(by, [self.vtag])
+        if e.jt == "bool":
+            e = bc.convert(e, "i32")                            # false < true: order Bool keys as 0 / 1
+        self.expr = e
+        self.kdt = np.dtype(bc._NPT[e.jt])                      # Float32 Float64 Int32 Int64: the key types dab_sort_by_key serves
+
+    def keys_of(self, vals: B200Array) -> B200Array:
+        """``by.(vals)`` on the device (one fused elementwise launch), as a temporary."""
+        keys = B200Array.empty(self.rt, vals.shape, self.kdt, temp=True)
+        self.bc.run_local(self.rt, self.expr, keys, [self.bc.LocalArg(arr=vals, tag=self.vtag)])
+        return keys
+
+    def keys_of_host(self, vals: np.ndarray) -> np.ndarray:
+        """``by.(vals)`` for a small host vector (samples, boundaries), computed by the same kernel as the chunks' keys."""
+        vals = np.ascontiguousarray(vals)
+        if vals.size == 0:
+            return np.empty(0, dtype=self.kdt)
+        dv = B200Array.from_numpy(self.rt, vals)
+        dk = self.keys_of(dv)
+        out = dk.to_numpy()
+        dk.free()
+        dv.free()
+        return out
+
+    def sort_chunk(self, src: B200Array, out: B200Array):
+        """``out = sort(src; by)``: values ordered stably by their keys."""
+        n = src.size
+        if n == 0:
+            return
+        keys = self.keys_of(src)
+        need = C.c_size_t()
+        _lib.check(_lib.lib().dab_sort_by_key_scratch_bytes(dab_dtype(self.kdt), n, C.byref(need)))
+        scratch = B200Array.empty(self.rt, (need.value,), np.uint8, temp=True)
+        _lib.call("dab_sort_by_key", self.rt.ctx, dab_dtype(self.kdt), C.c_void_p(keys.ptr), src.dtype.itemsize, C.c_void_p(src.ptr),
+                  C.c_void_p(out.ptr), C.c_void_p(scratch.ptr), need.value, n)
+        scratch.free()
+        keys.free()
+
+
+def key_order(keys: np.ndarray) -> np.ndarray:
+    """Permutation of a stable ``isless`` sort of a (tiny) host key vector: -0.0 before +0.0, NaNs last in input order."""
+    k = np.asarray(keys)
+    if k.dtype.kind != "f":
+        return np.argsort(k, kind="stable")
+    nan = np.isnan(k)
+    return np.lexsort((~np.signbit(k) & ~nan, np.where(nan, 0, k), nan))
+
+
+def boundaries_from_samples_by(samples: np.ndarray, sample_keys: np.ndarray, nparts: int, dt: np.dtype) -> np.ndarray:
+    """src/sort.jl:77-85 with ``by``: ``sort!(samples; by)`` is a stable sort by the samples' keys; the rest as without ``by``."""
+    s = np.asarray(samples).astype(dt)[key_order(sample_keys)].copy()
+    if len(s) == 0:
+        raise _lib.ArgumentError(_lib.ERR_ARG, "sort: empty sample")
+    s[0] = _typemin(dt)
+    step = len(s) // nparts
+    b = [s[(x - 1) * step] for x in range(1, nparts + 1)]
+    b.append(_typemax(dt))
+    return np.asarray(b, dtype=dt)
+
+
 def sort_exchange_plan(pids, sizes, rank_of, my_rank: int):
     """Who ships which piece where: piece j of source worker p (``sizes[p][j]`` keys, the run ending at split point j of p's sorted
     chunk) goes to worker ``pids[j]`` and lands at offset ``sum of the earlier sources' pieces`` of its receive buffer (the
@@ -113,7 +185,9 @@ def sort_exchange_plan(pids, sizes, rank_of, my_rank: int):
 def sort(d: DArray, sample=True, by=None, alg=None, **kwargs) -> DArray:  # noqa: A001 - mirrors Base.sort
     """``sort(d::DVector; sample=true, alg, by)`` (reference src/sort.jl:107-170).  ``sample``: True (<= 512 sampled keys per
     worker balance the parts), False (uniform between min(d) and max(d)), a ``(min, max)`` tuple, or an array used as the sample.
-    ``alg`` is accepted and ignored: a keys-only sort has one result whatever the algorithm."""
+    ``by``: a traceable key function (same closures as broadcast / map); values are ordered stably by ``by(x)``.
+    ``alg`` is accepted and ignored: a keys-only sort has one result whatever the algorithm, and the keyed sort is stable like
+    Julia's default."""
     return sort_with_boundaries(d, sample, by, alg, **kwargs)[0]
 
 
@@ -121,14 +195,13 @@ def sort_with_boundaries(d: DArray, sample=True, by=None, alg=None, **kwargs):
     """``sort`` plus the ``boundaries`` vector it partitioned with (what compute_boundaries returns, src/sort.jl:66-88)."""
     if kwargs:
         raise _lib.ArgumentError(_lib.ERR_ARG, "Only `alg`, `by` and `sample` are supported as keyword arguments")
-    if by is not None:
-        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "sort(d; by=f): key functions are not served by the B200 backend")
     if d.ndim != 1:
         raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, "sort is defined for a DVector")
     dt = d.dtype
     if dt not in _SORT_DTYPES:
         raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"sort: eltype {dt} (served: Float32 Float64 Int32 Int64)")
     rt = d.rt
+    kf = _KeyFn(rt, by, dt) if by is not None else None         # traced before any launch: an untraceable `by` raises here
     pids = list(d.layout.pids)
     nparts = len(pids)
     if nparts > 256:
@@ -155,7 +228,10 @@ def sort_with_boundaries(d: DArray, sample=True, by=None, alg=None, **kwargs):
     srt: Dict[int, B200Array] = {}
     for pid, ch in d.chunks.items():
         out = B200Array.empty(rt, (ch.size,), dt, temp=True)
-        _sort_chunk(rt, ch.ptr, ch.size, dt, out)
+        if kf is None:
+            _sort_chunk(rt, ch.ptr, ch.size, dt, out)
+        else:
+            kf.sort_chunk(ch, out)
         srt[pid] = out
 
     # ---- boundaries
@@ -185,15 +261,24 @@ def sort_with_boundaries(d: DArray, sample=True, by=None, alg=None, **kwargs):
         rows = rt.allgather_small(dev_ptr=stage.ptr, nbytes=wpr * SLOT * isz, dtype=dt)
         stage.free()
         everyone = {pid: rows[rt.rank_of(pid)][((pid - 1) % wpr) * SLOT:((pid - 1) % wpr) * SLOT + counts[pid]] for pid in pids}
-        boundaries = boundaries_from_samples(np.concatenate([everyone[p] for p in pids]), nparts, dt)
+        samples = np.concatenate([everyone[p] for p in pids])
+        if kf is None:
+            boundaries = boundaries_from_samples(samples, nparts, dt)
+        else:                                                   # sort!(samples; by) (src/sort.jl:77): every rank holds the same samples
+            boundaries = boundaries_from_samples_by(samples, kf.keys_of_host(samples), nparts, dt)
 
     # ---- split every sorted chunk at the boundaries (src/sort.jl:26-40): sizes[src pid][destination index]
     sizes_mine: Dict[int, List[int]] = {}
     ends: Dict[int, List[int]] = {}
-    bnd = np.ascontiguousarray(boundaries[1:])
+    # with `by` the scan compares by(x) > by(boundaries[i+1]) (src/sort.jl:32): the same search on the keys of the sorted chunk
+    bnd = np.ascontiguousarray(boundaries[1:] if kf is None else kf.keys_of_host(boundaries[1:]))
+    split_dt = dt if kf is None else kf.kdt
     for pid, s in srt.items():
         cnt = (C.c_ulonglong * nparts)()
-        _lib.call("dab_sorted_split", rt.ctx, dab_dtype(dt), C.c_void_p(s.ptr), s.size, C.c_void_p(bnd.ctypes.data), nparts, cnt)
+        ks = s if kf is None or s.size == 0 else kf.keys_of(s)
+        _lib.call("dab_sorted_split", rt.ctx, dab_dtype(split_dt), C.c_void_p(ks.ptr), s.size, C.c_void_p(bnd.ctypes.data), nparts, cnt)
+        if ks is not s:
+            ks.free()                                           # dab_sorted_split returned with the counts: the keys are no longer read
         e, prev = [], 0
         for i in range(nparts):
             prev = max(prev, int(cnt[i]))                   # the scan for piece i starts where piece i-1 ended
@@ -246,7 +331,10 @@ def sort_with_boundaries(d: DArray, sample=True, by=None, alg=None, **kwargs):
             chunks[pids[j]] = buf
             continue
         out = B200Array.empty(rt, (totals[j],), dt)
-        _sort_chunk(rt, buf.ptr, totals[j], dt, out)
+        if kf is None:
+            _sort_chunk(rt, buf.ptr, totals[j], dt, out)
+        else:
+            kf.sort_chunk(buf, out)
         buf.free()
         chunks[pids[j]] = out
     layout = layout_from_chunk_shapes([(totals[j],) for j in keep], (len(keep),), [pids[j] for j in keep])

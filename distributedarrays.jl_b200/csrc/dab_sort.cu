@@ -18,49 +18,13 @@
 #include <utility>
 
 #include "dab_common.cuh"
+#include "dab_sort_key.cuh"
 
 namespace {
 
 constexpr int ST_THREADS = 256;
 constexpr int ST_KPT = 8;                        // keys per thread (16 left the scatter at 111 registers = 2 CTAs per SM, latency-bound)
 constexpr int ST_TILE = ST_THREADS * ST_KPT;     // 2048 keys per CTA
-
-// ---- order-preserving bijection raw bits <-> unsigned key ----------------------------------------------------------------------
-template <typename T> struct SortKey;
-template <> struct SortKey<int32_t> {
-    using U = uint32_t;
-    static constexpr int DIGITS = 4;
-    __host__ __device__ static U enc(U u) { return u ^ 0x80000000u; }
-    __host__ __device__ static U dec(U k) { return k ^ 0x80000000u; }
-};
-template <> struct SortKey<int64_t> {
-    using U = uint64_t;
-    static constexpr int DIGITS = 8;
-    __host__ __device__ static U enc(U u) { return u ^ 0x8000000000000000ull; }
-    __host__ __device__ static U dec(U k) { return k ^ 0x8000000000000000ull; }
-};
-// floats: negatives reversed below the positives (so -0.0 < +0.0), then rotated down by C so that -Inf is key 0 and the
-// sign-bit NaNs (which the reversal put below -Inf) wrap around to the very top, above the positive NaNs: NaNs last, bijective.
-template <> struct SortKey<float> {
-    using U = uint32_t;
-    static constexpr int DIGITS = 4;
-    static constexpr U C = 0x007FFFFFu;
-    __host__ __device__ static U enc(U u) { return ((u & 0x80000000u) ? ~u : (u | 0x80000000u)) - C; }
-    __host__ __device__ static U dec(U k) {
-        k += C;
-        return (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
-    }
-};
-template <> struct SortKey<double> {
-    using U = uint64_t;
-    static constexpr int DIGITS = 8;
-    static constexpr U C = 0x000FFFFFFFFFFFFFull;
-    __host__ __device__ static U enc(U u) { return ((u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull)) - C; }
-    __host__ __device__ static U dec(U k) {
-        k += C;
-        return (k & 0x8000000000000000ull) ? (k ^ 0x8000000000000000ull) : ~k;
-    }
-};
 
 // Lanes of the warp whose 8-bit digit equals mine (dg = 256 marks "no key"; those lanes group together): 9 ballots.  On sm_100a
 // __match_any_sync costs one round per DISTINCT value in the warp (measured ~45 clk per warp-step on random digits); the bitwise

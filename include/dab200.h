@@ -272,9 +272,21 @@ int32_t dab_transpose_box(dab_ctx* ctx, int32_t elem_bytes, void* dst, size_t ds
  * sort!(lp_sorting)  of scatter_n_sort_localparts (:61).  Ascending in Julia's isless order (-0.0 < 0.0,
  * NaNs last, bit patterns preserved).  LSD radix sort, 8-bit digits; passes whose digit is constant over
  * the chunk are skipped.  tmp: scratch of n elements, distinct from in/out (may be NULL when n <= 1024 and
- * in != out); in == out sorts in place.  Synchronises the ctx stream once (digit histogram read-back).
- * dtypes: F32 F64 I32 I64. */
+ * in != out); in == out sorts in place.  Asynchronous on the ctx stream (histograms, pass selection and buffer
+ * ping-pong are planned on the device).  dtypes: F32 F64 I32 I64. */
 int32_t dab_sort(dab_ctx* ctx, int32_t dtype, const void* in, void* out, void* tmp, size_t n);
+
+/* vals_out = vals reordered by the STABLE ascending order of keys: the  sort(lp; by = f)  /  sort!(lp_sorting; by = f)  of the
+ * samplesort with a key function (src/sort.jl:8, 22, 61; `by` is accepted at :111) once the caller has evaluated keys = f.(lp)
+ * (dab_broadcast_expr).  Key order is Julia's isless (-0.0 < 0.0; NaN keys last and equal to each other), elements with equal keys
+ * keep their input order (Julia's default algorithm for a keyed sort is stable).  A 32-bit radix key and the element's position are
+ * packed into one Int64 word per element and sorted by dab_sort (two rounds, least-significant half first, for 64-bit keys); the
+ * low halves of the sorted words are the permutation applied to vals.  key dtypes F32 F64 I32 I64; val_bytes 4 or 8; n < 2^32;
+ * vals_out must not alias vals.  scratch: device memory of at least dab_sort_by_key_scratch_bytes() bytes, 16-byte aligned.
+ * Asynchronous on the ctx stream. */
+int32_t dab_sort_by_key(dab_ctx* ctx, int32_t key_dtype, const void* keys, int32_t val_bytes, const void* vals, void* vals_out,
+                        void* scratch, size_t scratch_bytes, size_t n);
+int32_t dab_sort_by_key_scratch_bytes(int32_t key_dtype, size_t n, size_t* bytes);
 
 /* Split points of a sorted chunk for the boundaries of the samplesort (src/sort.jl:28-40): for each of the
  * nb (<= 256) host values bounds[i] (dtype elements), counts_host[i] = the number of leading elements the

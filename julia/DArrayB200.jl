@@ -20,6 +20,7 @@
 #   src/linalg.jl:95-97,141 localpart(A)*xj, localpart(A)'*xj   Base.:*                                 dab_gemv
 #   src/linalg.jl:1-17   transpose!(lp, rp)               LinearAlgebra.transpose! / adjoint!        dab_transpose_box
 #   src/sort.jl:8,22,61  sort(localpart(d)), sort!(lp)    Base.sort / Base.sort!                     dab_sort
+#   src/sort.jl:8,22,61  sort(localpart(d); by = f)       sort_by (keys = f.(a) by broadcast)        dab_sort_by_key
 module DArrayB200
 
 using Distributed, DistributedArrays, LinearAlgebra
@@ -263,12 +264,25 @@ function Base.sort!(a::B200Array{T,1}; kw...) where {T}
                 ctx(), dab_dtype(T), a.ptr, a.ptr, tmp.ptr, length(a)), ctx())
     a
 end
-function Base.sort(a::B200Array{T,1}; kw...) where {T}
+function sort_keys(a::B200Array{T,1}) where {T}
     out = B200Array{T,1}(undef, size(a)); tmp = B200Array{T,1}(undef, size(a))
     check(ccall((:dab_sort, libdab), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t),
                 ctx(), dab_dtype(T), a.ptr, out.ptr, tmp.ptr, length(a)), ctx())
     out
 end
+
+# sort(localpart(d); by = f) / sort!(lp_sorting; by = f)  (src/sort.jl:8, 22, 61 with the :by keyword of :111): keys = f.(a) through
+# the broadcast lowering (one fused kernel), then the values are ordered stably by the keys (packed key|position words sorted by K11).
+function sort_by(a::B200Array{T,1}, keys::B200Array{K,1}) where {T,K}
+    n = length(a); need = Ref{Csize_t}(0)
+    check(ccall((:dab_sort_by_key_scratch_bytes, libdab), Int32, (Int32, Csize_t, Ref{Csize_t}), dab_dtype(K), n, need), ctx())
+    out = B200Array{T,1}(undef, size(a)); scratch = B200Array{UInt8,1}(undef, (Int(need[]),))
+    check(ccall((:dab_sort_by_key, libdab), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Csize_t),
+                ctx(), dab_dtype(K), keys.ptr, sizeof(T), a.ptr, out.ptr, scratch.ptr, need[], n), ctx())
+    out
+end
+# keyword arguments do not take part in dispatch: ONE method serves both spellings
+Base.sort(a::B200Array{T,1}; by = identity, kw...) where {T} = by === identity ? sort_keys(a) : sort_by(a, by.(a))
 
 # localpart(A) * Bjk, transpose(localpart(A)) * Bjk inside _matmatmul!  (src/linalg.jl:218-226): K12, tcgen05 3xTF32 for Float32
 function gemm(transA::Bool, A::B200Array{T,2}, B::B200Array{T,2}) where {T}

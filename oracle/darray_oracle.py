@@ -957,27 +957,61 @@ def sort_uniform_sample(lb, ub, nparts: int, dt) -> np.ndarray:
     return np.asarray(vals).astype(dt)
 
 
-def sort_split_points(sorted_lp: np.ndarray, boundaries: np.ndarray) -> List[int]:
-    """The scan of scatter_n_sort_localparts (src/sort.jl:26-50): piece i = sorted[p_sorted : first x > boundaries[i+1])."""
+def jl_sortperm_stable(keys: np.ndarray) -> np.ndarray:
+    """Permutation of a STABLE sort of ``keys`` in ``isless`` order (-0.0 before +0.0; NaNs last and equal to each other, so
+    they keep their input order): what ``sort(v; by = f)`` applies to ``v`` with ``keys = f.(v)`` (Julia's default algorithm for a
+    keyed sort is stable)."""
+    k = np.asarray(keys)
+    if k.dtype.kind != "f":
+        return np.argsort(k, kind="stable")
+    nan = np.isnan(k)
+    return np.lexsort((~np.signbit(k) & ~nan, np.where(nan, 0, k), nan))        # last key is the primary one; lexsort is stable
+
+
+def jl_sort_by(v: np.ndarray, by: Callable) -> np.ndarray:
+    """``sort(v; by = by)``."""
+    v = np.asarray(v)
+    return v[jl_sortperm_stable(by(v))] if len(v) else v.copy()
+
+
+def sort_split_points(sorted_lp: np.ndarray, boundaries: np.ndarray, by: Optional[Callable] = None) -> List[int]:
+    """The scan of scatter_n_sort_localparts (src/sort.jl:26-50): piece i = sorted[p_sorted : first x with by(x) > by(boundaries[i+1]))."""
     ends, p = [], 0
     n = len(sorted_lp)
+    keys = sorted_lp if by is None else by(np.asarray(sorted_lp))
+    bkeys = boundaries if by is None else by(np.asarray(boundaries))
     for i in range(len(boundaries) - 1):
         with np.errstate(invalid="ignore"):
-            gt = sorted_lp[p:] > boundaries[i + 1]
+            gt = keys[p:] > bkeys[i + 1]
         p_till = p + int(np.argmax(gt)) if gt.any() else n
         ends.append(p_till)
         p = p_till
     return ends
 
 
-def darray_sort(d: ODArray, sample=True):
-    """``sort(d::DVector; sample)`` (src/sort.jl:107-170).  Returns (ODArray of the sorted vector, boundaries)."""
+def darray_sort(d: ODArray, sample=True, by: Optional[Callable] = None):
+    """``sort(d::DVector; sample, by)`` (src/sort.jl:107-170).  Returns (ODArray of the sorted vector, boundaries).  ``by`` is a
+    NumPy-vectorised key function: local sorts and the sort of the gathered samples order by ``by(x)`` (``kwargs...`` at :8, :22, :61,
+    :77), an explicit ``sample`` array is sorted WITHOUT it (:148), and the split compares ``by(x) > by(boundaries[i+1])`` (:32).
+    Pieces are appended in source order (the reference appends in arrival order, which is not deterministic).
+
+    Reference behaviour kept as it is: the scan hands out ``np`` pieces and whatever follows the last split point is sent to NOBODY
+    (:26-50).  Without ``by`` the last boundary is ``typemax(T)``, nothing exceeds it and the last piece runs to the end; with a key
+    function for which ``by(typemax(T))`` is not the largest key (``x -> -x``, ``x -> rem(x, 7)``) the elements whose key exceeds
+    ``by(typemax(T))`` are dropped from the result -- the restatement (and the product) drop exactly the same elements."""
     nparts = len(d.pids)
     dt = d.chunks[0].dtype
-    srt = [jl_sort(c) for c in d.chunks]
+    lsort = jl_sort if by is None else (lambda v: jl_sort_by(v, by))
+    srt = [lsort(c) for c in d.chunks]
     if sample is True:
         samples = np.concatenate([s[list(sort_sample_indices(len(s)))] for s in srt])
-        boundaries = sort_boundaries_from_samples(samples, nparts, dt)
+        if by is None:
+            boundaries = sort_boundaries_from_samples(samples, nparts, dt)
+        else:
+            s = jl_sort_by(samples.astype(dt), by).copy()
+            s[0] = _typemin(dt)
+            step = len(s) // nparts
+            boundaries = np.asarray([s[(x - 1) * step] for x in range(1, nparts + 1)] + [_typemax(dt)], dtype=dt)
     else:
         if sample is False:
             lo = min(c.min() for c in d.chunks)
@@ -989,11 +1023,13 @@ def darray_sort(d: ODArray, sample=True):
     recv = [[] for _ in range(nparts)]
     for s in srt:
         p = 0
-        for i, e in enumerate(sort_split_points(s, boundaries)):
+        for i, e in enumerate(sort_split_points(s, boundaries, by)):
             recv[i].append(s[p:e])
             p = e
-    parts = [jl_sort(np.concatenate(r)) for r in recv]
+    parts = [lsort(np.concatenate(r)) for r in recv]
     keep = [i for i, p in enumerate(parts) if len(p) > 0]       # zero-length parts are dropped (src/sort.jl:163-168)
+    if not keep:
+        raise ValueError("ArgumentError: sort left no non-empty part (DArray(refs) of an empty list of refs)")
     sizes = [len(parts[i]) for i in keep]
     starts = np.concatenate([[1], 1 + np.cumsum(sizes)]).astype(int)
     out = ODArray((int(sum(sizes)),), (len(keep),), [d.pids[i] for i in keep],

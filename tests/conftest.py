@@ -39,3 +39,32 @@ def rt2(dab):
     rt = dab.init(workers_per_rank=2, use_dist=False)
     yield rt
     dab.d_closeall()
+
+
+@pytest.fixture()
+def hostmem(dab, monkeypatch):
+    """CPU-only runs of the HOST logic above the C ABI: installs ``tests/hostmem_abi.py`` (an emulation of the entry points that
+    ``sort`` drives, over host memory) in place of libdab200.so for one test, and removes every trace of it afterwards.  Test
+    infrastructure; the product never sees it."""
+    import sys
+
+    import hostmem_abi
+
+    lib_mod = sys.modules["darray_b200._lib"]
+    rt_mod = sys.modules["darray_b200.runtime"]
+    bc_mod = sys.modules["darray_b200._broadcast"]
+    saved_lib, saved_rt = lib_mod._lib, rt_mod._RT
+    assert saved_rt is None, "a real runtime is alive: the host-memory emulation must not share a process state with it"
+    fake = hostmem_abi.HostMemABI()
+    lib_mod._lib = fake
+    monkeypatch.setattr(bc_mod, "run_local", hostmem_abi.run_local)
+    try:
+        yield fake
+    finally:
+        try:
+            dab.d_closeall()
+            if rt_mod._RT is not None:
+                rt_mod._RT.shutdown()                      # ctx = None: late finalizers become no-ops instead of reaching the real library
+        finally:
+            rt_mod._RT = saved_rt
+            lib_mod._lib = saved_lib

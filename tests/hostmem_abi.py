@@ -1,0 +1,280 @@
+"""TEST INFRASTRUCTURE -- an emulation of the part of the C ABI (include/dab200.h) that ``sort(d::DVector)`` drives, over HOST memory.
+
+Why: the host logic above the ABI (``distributedarrays.jl_b200/_sort.py``: sampling, boundaries, split, piece exchange, the ``by``
+composition) can otherwise only run on a GPU box.  With this module installed by the ``hostmem`` fixture the real ``Runtime`` /
+``DArray`` / ``sort`` code runs unchanged on a CPU-only machine against "device pointers" that are addresses of host buffers, and the
+result is compared with the oracle.  It is never importable from the product: the package has no reference to it, and
+``_lib.lib()`` keeps failing loudly when ``libdab200.so`` is missing.
+
+What is emulated follows the KERNELS' algorithms, not a NumPy shortcut, wherever the algorithm is the thing under test:
+  * ``dab_sort`` / ``dab_sort_by_key`` sort through the same order-preserving radix-key bijection as ``dab_sort_key.cuh``;
+    ``dab_sort_by_key`` packs ``radix_key << 32 | position`` into signed 64-bit words (top bit flipped), sorts the words, runs the
+    second round on the high half for 64-bit keys and gathers by the low halves -- the composition of ``dab_sortby.cu`` step by step;
+  * ``dab_sorted_split`` is the binary search of ``sort_bounds_kernel`` (NaN bound, -0.0 bound, all-NaN tail);
+  * ``dab_copy_box`` is the 4-D box copy.
+Traced closures are evaluated by a small NumPy interpreter of the expression tree (``eval_expr``) in place of the NVRTC kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+F32, F64, I32, I64, U8 = range(5)
+_NP = {F32: np.dtype(np.float32), F64: np.dtype(np.float64), I32: np.dtype(np.int32), I64: np.dtype(np.int64), U8: np.dtype(np.uint8)}
+SIGN64 = np.uint64(0x8000000000000000)
+
+
+# ---- dab_sort_key.cuh in NumPy ------------------------------------------------------------------------------------------------
+def radix_enc(raw: np.ndarray, code: int) -> np.ndarray:
+    """raw: the keys' bit patterns as uint32 / uint64."""
+    with np.errstate(over="ignore"):
+        if code == I32:
+            return raw ^ np.uint32(0x80000000)
+        if code == I64:
+            return raw ^ SIGN64
+        if code == F32:
+            top, c = np.uint32(0x80000000), np.uint32(0x007FFFFF)
+        else:
+            top, c = SIGN64, np.uint64(0x000FFFFFFFFFFFFF)
+        return np.where((raw & top) != 0, ~raw, raw | top) - c
+
+
+def radix_dec(k: np.ndarray, code: int) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        if code == I32:
+            return k ^ np.uint32(0x80000000)
+        if code == I64:
+            return k ^ SIGN64
+        if code == F32:
+            top, c = np.uint32(0x80000000), np.uint32(0x007FFFFF)
+        else:
+            top, c = SIGN64, np.uint64(0x000FFFFFFFFFFFFF)
+        k = k + c
+        return np.where((k & top) != 0, k ^ top, ~k)
+
+
+def _utype(code: int):
+    return np.uint32 if code in (I32, F32) else np.uint64
+
+
+def by_radix_key(raw: np.ndarray, code: int) -> np.ndarray:
+    """``by_radix_key`` of dab_sortby.cu: all NaN keys collapse to the largest key."""
+    e = radix_enc(raw, code)
+    if code in (F32, F64):
+        u = _utype(code)
+        absmask = u(0x7FFFFFFF) if code == F32 else u(0x7FFFFFFFFFFFFFFF)
+        inf = u(0x7F800000) if code == F32 else u(0x7FF0000000000000)
+        e = np.where((raw & absmask) > inf, ~u(0), e)
+    return e
+
+
+# ---- memory -----------------------------------------------------------------------------------------------------------------------
+def _addr(x) -> int:
+    if x is None:
+        return 0
+    if isinstance(x, int):
+        return x
+    if isinstance(x, C.c_void_p):
+        return x.value or 0
+    if isinstance(x, C.Array):
+        return C.addressof(x)
+    if hasattr(x, "_obj"):          # byref(...)
+        return C.addressof(x._obj)
+    raise TypeError(type(x))
+
+
+def _view(ptr, n: int, dt) -> np.ndarray:
+    dt = np.dtype(dt)
+    if n == 0:
+        return np.empty(0, dtype=dt)
+    buf = (C.c_char * (n * dt.itemsize)).from_address(_addr(ptr))
+    return np.frombuffer(buf, dtype=dt, count=n)
+
+
+def _sz4(a):
+    return [int(v) for v in a]
+
+
+class HostMemABI:
+    """Duck-types the ``ctypes.CDLL`` of libdab200.so for the entry points listed in the module docstring."""
+
+    def __init__(self):
+        self.blocks = {}
+        self.launches = 0
+        self.calls = []
+
+    # -- lifecycle / diagnostics
+    def dab_abi_version(self):
+        return 1
+
+    def dab_device_count(self, n):
+        n._obj.value = 1
+        return 0
+
+    def dab_init(self, device, ctx):
+        ctx._obj.value = 0xDAB
+        return 0
+
+    def dab_shutdown(self, ctx):
+        return 0
+
+    def dab_last_error(self, ctx):
+        return b"hostmem_abi"
+
+    def dab_status_string(self, st):
+        return b"hostmem_abi status"
+
+    def dab_sync(self, ctx):
+        return 0
+
+    def dab_launch_count(self, ctx, out):
+        out._obj.value = self.launches
+        return 0
+
+    # -- buffers
+    def _alloc(self, ctx, nbytes, out):
+        buf = C.create_string_buffer(max(int(nbytes), 1) + 256)
+        base = (C.addressof(buf) + 255) & ~255
+        self.blocks[base] = buf
+        out._obj.value = base
+        return 0
+
+    def _free(self, ctx, p):
+        self.blocks.pop(_addr(p), None)
+        return 0
+
+    dab_alloc = dab_alloc_async = _alloc
+    dab_free = dab_free_async = _free
+
+    def _copy(self, ctx, dst, src, n):
+        n = int(n)
+        if n:
+            C.memmove(_addr(dst), _addr(src), n)
+        return 0
+
+    dab_h2d = dab_d2h = dab_d2d = _copy
+
+    # -- dab_copy_box (4-D box, column-major)
+    def dab_copy_box(self, ctx, elem_bytes, dst, dst_shape, dst_off, src, src_shape, src_off, extent):
+        dsh, dof, ssh, sof, ext = map(_sz4, (dst_shape, dst_off, src_shape, src_off, extent))
+        dt = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[int(elem_bytes)]
+        if min(ext) == 0:
+            return 0
+        d = _view(dst, int(np.prod(dsh)), dt).reshape(dsh, order="F")
+        s = _view(src, int(np.prod(ssh)), dt).reshape(ssh, order="F")
+        d[tuple(slice(o, o + e) for o, e in zip(dof, ext))] = s[tuple(slice(o, o + e) for o, e in zip(sof, ext))]
+        self.launches += 1
+        return 0
+
+    # -- K11
+    def dab_sort(self, ctx, dtype, inp, out, tmp, n):
+        n, u = int(n), _utype(dtype)
+        if n:
+            raw = _view(inp, n, u).copy()
+            _view(out, n, u)[:] = radix_dec(np.sort(radix_enc(raw, dtype), kind="stable"), dtype)
+            self.launches += 1
+        return 0
+
+    def dab_sort_by_key_scratch_bytes(self, key_dtype, n, out):
+        rounds = 2 if key_dtype in (F64, I64) else 1
+        out._obj.value = (2 + rounds) * ((int(n) * 8 + 255) & ~255)
+        return 0
+
+    def dab_sort_by_key(self, ctx, key_dtype, keys, val_bytes, vals, vals_out, scratch, scratch_bytes, n):
+        n = int(n)
+        if n == 0:
+            return 0
+        need = C.c_size_t()
+        self.dab_sort_by_key_scratch_bytes(key_dtype, n, C.byref(need))
+        assert int(scratch_bytes) >= need.value and _addr(scratch) % 16 == 0 and _addr(vals) != _addr(vals_out)
+        ws = (n * 8 + 255) & ~255
+        base = _addr(scratch)
+        words, tmp, s1, s2 = (base + k * ws for k in range(4))
+        e = by_radix_key(_view(keys, n, _utype(key_dtype)), key_dtype).astype(np.uint64)
+        pos = np.arange(n, dtype=np.uint64)
+
+        def pack(h):                                            # sortby_pack_kernel
+            _view(words, n, np.uint64)[:] = ((h << np.uint64(32)) | pos) ^ SIGN64
+
+        if key_dtype in (F32, I32):
+            pack(e)
+            self.dab_sort(ctx, I64, words, s1, tmp, n)
+            perm = (_view(s1, n, np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        else:
+            pack(e & np.uint64(0xFFFFFFFF))
+            self.dab_sort(ctx, I64, words, s1, tmp, n)
+            p1 = (_view(s1, n, np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.int64)
+            pack(e[p1] >> np.uint64(32))
+            self.dab_sort(ctx, I64, words, s2, tmp, n)
+            perm = p1[(_view(s2, n, np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.int64)]
+        vt = {4: np.uint32, 8: np.uint64}[int(val_bytes)]
+        _view(vals_out, n, vt)[:] = _view(vals, n, vt)[perm]    # sortby_gather_kernel
+        self.launches += 2
+        return 0
+
+    def dab_sorted_split(self, ctx, dtype, sorted_p, n, bounds_host, nb, counts):
+        n, nb, u = int(n), int(nb), _utype(dtype)
+        raw = _view(sorted_p, n, u)
+        enc = radix_enc(raw, dtype)
+        b = _view(bounds_host, nb, u).copy()
+        isf = dtype in (F32, F64)
+        absmask = (u(0x7FFFFFFF) if dtype == F32 else u(0x7FFFFFFFFFFFFFFF)) if isf else None
+        inf = (u(0x7F800000) if dtype == F32 else u(0x7FF0000000000000)) if isf else None
+        for t in range(nb):
+            braw = b[t]
+            if isf and (braw & absmask) > inf:                  # x > NaN is never true
+                counts[t] = n
+                continue
+            if isf and (braw & absmask) == 0:
+                braw = u(0)                                     # -0.0 bounds like +0.0
+            kb = radix_enc(np.array([braw], dtype=u), dtype)[0]
+            lo = int(np.searchsorted(enc, kb, side="right"))
+            rest_nan = isf and lo < n and (raw[lo] & absmask) > inf
+            counts[t] = n if rest_nan else lo
+        self.launches += 1
+        return 0
+
+
+# ---- NumPy interpreter of a traced expression (stands in for dab_unary / dab_affine / dab_broadcast_expr) ---------------------
+def eval_expr(e, args):
+    from darray_b200 import _broadcast as bc
+    npt = bc._NPT
+    if e.op == "arg":
+        return args[e.val]
+    if e.op == "const":
+        return npt[e.jt].type(e.val)
+    if e.op == "convert":
+        return np.asarray(eval_expr(e.args[0], args)).astype(npt[e.jt])
+    a = [eval_expr(x, args) for x in e.args]
+    with np.errstate(all="ignore"):
+        if e.op == "ifelse":
+            return np.where(a[0], a[1], a[2])
+        two = {"add": np.add, "sub": np.subtract, "mul": np.multiply, "div": np.divide, "rem": np.fmod, "mod": np.mod,
+               "max": np.maximum, "min": np.minimum, "pow": np.power, "and": np.bitwise_and, "or": np.bitwise_or, "xor": np.bitwise_xor,
+               "lt": np.less, "le": np.less_equal, "gt": np.greater, "ge": np.greater_equal, "eq": np.equal, "ne": np.not_equal}
+        if e.op in two:
+            r = two[e.op](a[0], a[1])
+        elif e.op == "idiv":
+            r = np.trunc(np.asarray(a[0], dtype=np.float64) / np.asarray(a[1], dtype=np.float64))
+        else:
+            one = {"neg": np.negative, "abs": np.abs, "abs2": lambda x: x * x, "sqrt": np.sqrt, "inv": lambda x: 1 / x, "floor": np.floor,
+                   "ceil": np.ceil, "sign": np.sign, "sin": np.sin, "cos": np.cos, "tan": np.tan, "exp": np.exp, "log": np.log,
+                   "tanh": np.tanh, "isnan": np.isnan}
+            r = one[e.op](a[0])
+        return np.asarray(r).astype(npt[e.jt])
+
+
+def run_local(rt, expr, out, largs):
+    """Replacement of ``_broadcast.run_local`` for dense same-shape arguments and scalars."""
+    if out.size == 0:
+        return
+    vals = []
+    for a in largs:
+        if a.arr is not None:
+            assert a.arr.size == out.size
+            vals.append(_view(a.arr.ptr, a.arr.size, a.arr.dtype).copy())
+        else:
+            vals.append(a.scalar)
+    r = np.broadcast_to(np.asarray(eval_expr(expr, vals)), (out.size,)).astype(out.dtype)
+    _view(out.ptr, out.size, out.dtype)[:] = r

@@ -67,3 +67,142 @@ def test_host_boundary_logic_matches_oracle():
         for nparts in (1, 2, 3, 8):
             assert np.array_equal(_sort.boundaries_from_samples(s, nparts, dt), orc.sort_boundaries_from_samples(s, nparts, dt))
             assert np.array_equal(_sort.uniform_sample(s.min(), s.max(), nparts, dt), orc.sort_uniform_sample(s.min(), s.max(), nparts, dt))
+
+
+# ---- sort(d; by = f): oracle, the dab_sort_by_key composition, and the host flow of _sort.py over the host-memory ABI emulation ----
+
+def _by_cases(T):
+    """(traced closure for the product, NumPy-vectorised twin for the oracle)."""
+    import darray_b200 as dab
+    cases = [(lambda x: -x, lambda v: -v), (lambda x: abs(x), lambda v: np.abs(v)), (lambda x: x, lambda v: v)]
+    if np.dtype(T).kind == "i":
+        cases += [(lambda x: dab.rem(x, 7), lambda v: np.fmod(v, np.dtype(T).type(7))),              # many equal keys: stability
+                  (lambda x: x * 0.5, lambda v: v * 0.5),                                            # Float64 keys of Int values
+                  (lambda x: x > 3, lambda v: (v > 3).astype(np.int32))]                             # Bool keys
+    else:
+        cases += [(lambda x: dab.floor(x * 4), lambda v: np.floor(v * np.dtype(T).type(4))),
+                  (lambda x: dab.ifelse(x > 0.5, x, 1 - x), lambda v: np.where(v > 0.5, v, 1 - v))]
+    return cases
+
+
+def _by_data(T, n, rng):
+    if np.dtype(T).kind == "i":
+        return rng.integers(-50, 50, n).astype(T)
+    a = rng.random(n).astype(T)
+    if n >= 8:                                                                   # signed zeros, infinities and NaNs among the values
+        a[rng.integers(0, n, 3)] = [-0.0, np.inf, -np.inf]
+    return a
+
+
+def _multiset_contains(big, small):
+    ub, cb = np.unique(big.view(np.uint8).reshape(len(big), -1), axis=0, return_counts=True)
+    us, cs = np.unique(small.view(np.uint8).reshape(len(small), -1), axis=0, return_counts=True)
+    have = {bytes(r): c for r, c in zip(ub, cb)}
+    return all(have.get(bytes(r), 0) >= c for r, c in zip(us, cs))
+
+
+def test_oracle_sort_by():
+    rng = np.random.default_rng(5)
+    for T in (np.int64, np.float64, np.float32, np.int32):
+        tmax = np.array([orc._typemax(np.dtype(T))], dtype=T)
+        for n in (1, 10, 1000, 5000):
+            a = _by_data(T, n, rng)
+            for _, nby in _by_cases(T):
+                ka = nby(a)
+                with np.errstate(invalid="ignore"):
+                    kept = ~(ka > nby(tmax)[0])                 # the reference never ships an element whose key exceeds by(typemax(T))
+                want = a[kept][orc.jl_sortperm_stable(ka[kept])]
+                for nw in (1, 3, 8):
+                    if n < nw:
+                        continue
+                    # one worker: ONE piece, cut at the first key above by(typemax(T)); several workers: only the tail behind the LAST
+                    # split point is lost, so a key function whose maximum is by(typemax(T)) loses nothing
+                    try:
+                        d2, b = orc.darray_sort(orc.distribute(a, nworkers=nw), True, by=nby)
+                    except ValueError:
+                        assert not kept.all()
+                        continue
+                    got = orc.to_array(d2)
+                    k = nby(got)
+                    assert _multiset_contains(a, got) and (len(got) == n if kept.all() else len(got) <= n)
+                    with np.errstate(invalid="ignore"):
+                        assert not np.any(k[1:] < k[:-1])                             # ordered by key
+                    if nw == 1:
+                        assert np.array_equal(got, want, equal_nan=True)              # sort(a; by) of the shipped elements, stable
+    # NaN keys are equal to each other: they keep input order at the end; -0.0 keys sort before +0.0 keys
+    v = np.array([3.0, np.nan, -0.0, 0.0, 1.0, np.nan, -0.0], dtype=np.float64)
+    tag = np.arange(7, dtype=np.float64)
+    assert list(orc.jl_sortperm_stable(v)) == [2, 6, 3, 4, 0, 1, 5]
+    assert list(orc.jl_sort_by(tag, lambda t: v[t.astype(int)])) == [2, 6, 3, 4, 0, 1, 5]
+
+
+def test_sort_by_key_composition_matches_stable_order():
+    """The packed-word composition of dab_sortby.cu (emulated step by step in tests/hostmem_abi.py) against a stable isless argsort."""
+    import ctypes as C
+
+    import hostmem_abi as hm
+    fake = hm.HostMemABI()
+    rng = np.random.default_rng(11)
+    for code, kt in ((hm.F32, np.float32), (hm.F64, np.float64), (hm.I32, np.int32), (hm.I64, np.int64)):
+        for n in (1, 2, 33, 4097):
+            if np.dtype(kt).kind == "f":
+                keys = rng.standard_normal(n).astype(kt)
+                keys[rng.integers(0, n, max(1, n // 8))] = rng.choice(np.array([np.nan, -np.nan, 0.0, -0.0, np.inf, -np.inf], dtype=kt), max(1, n // 8))
+                keys = np.round(keys, 1)                                            # many ties
+                if n > 30:                                                          # NaNs with different payloads are still ONE key
+                    raw = keys.view(np.uint32 if kt == np.float32 else np.uint64)
+                    raw[5] = raw.dtype.type(0x7FC00123 if kt == np.float32 else 0x7FF8000000000123)
+                    raw[9] = raw.dtype.type(0xFFC00001 if kt == np.float32 else 0xFFF8000000000001)
+            else:
+                keys = rng.integers(np.iinfo(kt).min, np.iinfo(kt).max, n, dtype=kt)
+                keys[rng.integers(0, n, max(1, n // 2))] = kt(7)
+                if n > 30:
+                    keys[:4] = [np.iinfo(kt).min, np.iinfo(kt).max, -1, 0]
+            for vt in (np.float32, np.int64):
+                vals = np.arange(n).astype(vt)
+                out = np.empty_like(vals)
+                need = C.c_size_t()
+                fake.dab_sort_by_key_scratch_bytes(code, n, C.byref(need))
+                scratch = np.zeros(need.value + 16, dtype=np.uint8)
+                sp = (scratch.ctypes.data + 15) & ~15
+                assert fake.dab_sort_by_key(None, code, keys.ctypes.data, vals.itemsize, vals.ctypes.data, out.ctypes.data, sp, need.value, n) == 0
+                assert np.array_equal(out, vals[orc.jl_sortperm_stable(keys)]), (kt, vt, n)
+    # the radix-key bijection itself: monotone in isless order and invertible
+    f = np.array([-np.inf, -1.5, -0.0, 0.0, 1e-30, 2.0, np.inf, np.nan], dtype=np.float32)
+    e = hm.radix_enc(f.view(np.uint32), hm.F32)
+    assert np.all(e[1:] > e[:-1]) and np.array_equal(hm.radix_dec(e, hm.F32), f.view(np.uint32))
+    d = f.astype(np.float64)
+    e = hm.radix_enc(d.view(np.uint64), hm.F64)
+    assert np.all(e[1:] > e[:-1]) and np.array_equal(hm.radix_dec(e, hm.F64), d.view(np.uint64))
+
+
+@pytest.mark.parametrize("T", [np.int64, np.float64, np.float32, np.int32])
+@pytest.mark.parametrize("nw", [1, 2, 8])
+def test_host_sort_flow_with_and_without_by(hostmem, dab, T, nw):
+    """_sort.py end to end on the host-memory ABI: result, boundaries and result layout equal the oracle's, for every `sample` kind."""
+    rt = dab.init(workers_per_rank=nw, use_dist=False)
+    rng = np.random.default_rng(17 + nw)
+    for n in (nw, 97, 3000):
+        a = _by_data(T, n, rng)
+        od = orc.distribute(a, nworkers=nw)
+        d = dab.distribute(a)
+        assert d.layout.indices == od.indices
+        smp = _by_data(T, 64, rng)
+        lohi = (T(-60), T(60)) if np.dtype(T).kind == "i" else (T(0), T(1))
+        for sample in (True, lohi, smp):
+            for tby, nby in [(None, None)] + _by_cases(T):
+                try:
+                    want, wb = orc.darray_sort(od, sample, by=nby)
+                except ValueError:                              # every key exceeds by(typemax(T)): nothing is shipped (see the oracle's docstring)
+                    with pytest.raises(dab.ArgumentError):
+                        dab.sort_with_boundaries(d, sample, tby)
+                    continue
+                got, gb = dab.sort_with_boundaries(d, sample, tby)
+                assert np.array_equal(gb, wb, equal_nan=True), (n, sample is True, tby)
+                assert got.layout.indices == want.indices and list(got.layout.pids) == list(want.pids)
+                ga, wa = dab.to_array(got), orc.to_array(want)
+                assert ga.dtype == wa.dtype and np.array_equal(ga.view(np.uint8), wa.view(np.uint8)), (n, sample is True, tby)
+                got.close()
+        d.close()
+    assert hostmem.launches > 0
+    rt.shutdown()

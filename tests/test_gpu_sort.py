@@ -139,7 +139,7 @@ def test_darray_sort_other_types_and_errors(dab, rt8):
         dab.sort(d, rev=True)                                                     # only alg, by, sample (src/sort.jl:112-114)
     with pytest.raises(dab.ArgumentError):
         dab.sort(d, sample="yes")
-    with pytest.raises(dab.UnsupportedError):
-        dab.sort(d, by=abs)
+    with pytest.raises(TypeError):
+        dab.sort(d, by=lambda x: x if x > 0 else -x)                              # a key function must be traceable (no data-dependent branches)
     with pytest.raises(dab.ArgumentError):
         dab.sort(dab.distribute(rng.random(100)), sample=(-np.inf, 1.0))

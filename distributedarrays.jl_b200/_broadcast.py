@@ -310,8 +310,36 @@ def match_affine(e: Expr):
 def _pad4(v, fill=1):
     v = list(v)
     if len(v) > 4:
-        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "broadcast over more than 4 dimensions is not served")
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "broadcast whose dimensions do not collapse to 4 groups (see collapse_dims) is not served")
     return v + [fill] * (4 - len(v))
+
+
+def collapse_dims(out_shape, arg_shapes):
+    """Merge neighbouring dimensions of a broadcast that every array argument treats alike -- dense in both, or extruded (size 1,
+    src/broadcast.jl:112-113) in both -- and drop the dimensions of extent 1.  A dense column-major argument addresses a merged group
+    exactly as it addressed the separate dimensions (the stride of dim d+1 is stride(d) * extent(d)), so the kernel sees fewer
+    dimensions and the same elements: ``(2,3,4,5,6) .+ (2,3,1,1,6)`` becomes ``(6,20,6) .+ (6,1,6)``, and any number of same-shape
+    arguments becomes 1-D.  Returns (collapsed out shape, [collapsed shape per argument])."""
+    nd = len(out_shape)
+    shapes = [tuple(int(v) for v in sh) + (1,) * (nd - len(sh)) for sh in arg_shapes]
+    groups: List[Tuple[int, List[int]]] = []
+    for d in range(nd):
+        o = int(out_shape[d])
+        ext = [sh[d] for sh in shapes]
+        for e, sh in zip(ext, arg_shapes):
+            if e != o and e != 1:
+                raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"arrays could not be broadcast: {tuple(sh)} vs {tuple(out_shape)}")
+        if o == 1:
+            continue
+        if groups:
+            po, pext = groups[-1]
+            if all((pe == po and e == o) or (pe == 1 and e == 1) for pe, e in zip(pext, ext)):
+                groups[-1] = (po * o, [pe * e for pe, e in zip(pext, ext)])
+                continue
+        groups.append((o, ext))
+    if not groups:
+        groups = [(1, [1] * len(shapes))]
+    return tuple(g[0] for g in groups), [tuple(g[1][k] for g in groups) for k in range(len(shapes))]
 
 
 def _dense_strides(shape):
@@ -395,7 +423,13 @@ def run_local(rt, expr: Expr, out: B200Array, largs: List[LocalArg]):
         # element; a C cast would silently truncate
         raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"broadcast of {expr.jt} values into a {out_tag} destination (InexactError semantics) is not served")
     src = codegen(convert(expr, out_tag)).encode()
-    oshape = _pad4(out.shape)
+    oshape_nd, ashapes = tuple(out.shape), {k: tuple(a.arr.shape) for k, a in enumerate(largs) if a.arr is not None}
+    if len(oshape_nd) > 4 or any(len(sh) > 4 for sh in ashapes.values()):
+        # the kernel walks a 4-D box: more dimensions are served when they collapse to <= 4 groups (always for same-shape arguments)
+        keys = sorted(ashapes)
+        oshape_nd, coll = collapse_dims(oshape_nd, [ashapes[k] for k in keys])
+        ashapes = dict(zip(keys, coll))
+    oshape = _pad4(oshape_nd)
     nargs = len(largs)
     if nargs > 8:
         raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "more than 8 broadcast arguments are not served")
@@ -407,7 +441,7 @@ def run_local(rt, expr: Expr, out: B200Array, largs: List[LocalArg]):
         dts[k] = dab_dtype(_NPT[a.tag])
         if a.arr is not None:
             ptrs[k] = a.arr.ptr
-            ash = _pad4(a.arr.shape)
+            ash = _pad4(ashapes[k])
             dense = _dense_strides(ash)
             for d in range(4):
                 if ash[d] == oshape[d]:

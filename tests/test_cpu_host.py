@@ -291,3 +291,48 @@ def test_bench_parity_fold_check_detects_a_swapped_order():
         differs += a.tobytes() != b.tobytes()
     assert differs > 10                                                    # the order is visible in Float32
     assert bench.rel_err(1.0 + 2e-6, 1.0) > bench.REL_TOL > bench.rel_err(1.0 + 5e-7, 1.0)
+
+
+def test_collapse_dims_addresses_the_same_elements():
+    """``collapse_dims`` (broadcast over more than 4 dimensions): walking the collapsed box with dense / zero strides must read exactly
+    the elements NumPy's broadcasting reads."""
+    from darray_b200 import _broadcast as bc
+    from darray_b200 import _lib
+
+    def walk(out_shape, arg_shapes, arrays):
+        oc, ac = bc.collapse_dims(out_shape, arg_shapes)
+        assert len(oc) <= 4, (out_shape, arg_shapes, oc)
+        o4 = list(oc) + [1] * (4 - len(oc))
+        n = int(np.prod(o4))
+        idx = np.unravel_index(np.arange(n), o4, order="F")
+        res = []
+        for sh, a in zip(ac, arrays):
+            s4 = list(sh) + [1] * (4 - len(sh))
+            dense = bc._dense_strides(s4)
+            strides = [dense[d] if s4[d] == o4[d] else 0 for d in range(4)]
+            assert all(s4[d] in (o4[d], 1) for d in range(4))
+            off = sum(idx[d] * strides[d] for d in range(4))
+            res.append(a.reshape(-1, order="F")[off])
+        return n, res
+
+    rng = np.random.default_rng(3)
+    cases = [((2, 3, 4, 5, 6), [(2, 3, 4, 5, 6), (2, 3, 1, 1, 6)]),
+             ((2, 3, 4, 5, 6), [(2, 3, 4, 5, 6), (2, 3, 4, 5, 6), (1, 1, 1, 1, 1)]),
+             ((6, 5, 4, 3, 4, 5), [(6, 5, 4, 3, 4, 5), (6, 1, 4, 3, 1, 1), (1, 5, 1, 1, 1, 1)]),
+             ((3, 1, 2, 1, 4, 1, 5), [(3, 1, 2, 1, 4, 1, 5), (3, 1, 1, 1, 4)]),
+             ((1, 1, 1, 1, 1), [(1, 1, 1, 1, 1)]),
+             ((4, 3, 2, 2, 3), [(4, 1, 2, 1, 3), (1, 3, 1, 2, 1)])]
+    for out_shape, arg_shapes in cases[:5]:
+        arrays = [rng.standard_normal(sh) for sh in arg_shapes]
+        n, res = walk(out_shape, arg_shapes, arrays)
+        assert n == int(np.prod(out_shape))
+        for sh, a, r in zip(arg_shapes, arrays, res):
+            full = tuple(sh) + (1,) * (len(out_shape) - len(sh))
+            want = np.broadcast_to(a.reshape(full), out_shape).reshape(-1, order="F")
+            assert np.array_equal(r, want), (out_shape, sh)
+    assert bc.collapse_dims((2, 3, 4, 5, 6), [(2, 3, 4, 5, 6)] * 3)[0] == (720,)
+    assert bc.collapse_dims((2, 3, 4, 5, 6), [(2, 3, 4, 5, 6), (2, 3, 1, 1, 6)]) == ((6, 20, 6), [(6, 20, 6), (6, 1, 6)])
+    oc, _ = bc.collapse_dims(*cases[5])                       # alternating extrusion patterns do not merge: 5 groups stay
+    assert len(oc) == 5
+    with pytest.raises(_lib.DimensionMismatch):
+        bc.collapse_dims((2, 3, 4, 5, 6), [(2, 3, 4, 5, 7)])

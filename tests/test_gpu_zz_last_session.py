@@ -1,12 +1,16 @@
-"""GPU parity tests for ``sort(d; by = f)``: ``dab_sort_by_key`` (dab_sortby.cu) and the keyed samplesort of ``_sort.py``
-(reference src/sort.jl:8, 22, 32, 61, 77, 111).
+"""GPU parity tests for what the LAST session of round 2 added after the round's GPU budget was spent:
 
-STATUS: written after the round's GPU budget was spent -- these tests have NOT been executed on hardware yet.  What is verified on CPU:
-the composition (key|position words, two rounds for 64-bit keys, gather) step by step in ``tests/hostmem_abi.py`` against a stable
-``isless`` argsort, and the whole host flow of ``_sort.py`` against the oracle (``tests/test_cpu_sort.py``).  What only a B200 can
-verify: the two small kernels and their ctypes bindings.  The module therefore runs LAST (file name) and is marked
-``xfail(strict=False)``: a pass is reported as XPASS, a failure cannot hide a regression elsewhere or turn the tier red for code
-that was never claimed as measured."""
+  * ``sort(d; by = f)``: ``dab_sort_by_key`` (dab_sortby.cu) and the keyed samplesort of ``_sort.py`` (reference src/sort.jl:8, 22, 32,
+    61, 77, 111);
+  * general broadcasts over more than 4 dimensions (``collapse_dims`` in ``_broadcast.py``; reference src/broadcast.jl is N-d).
+
+STATUS: these tests have NOT been executed on hardware yet.  What is verified on CPU: the sort-by-key composition (key|position words,
+two rounds for 64-bit keys, gather) step by step in ``tests/hostmem_abi.py`` against a stable ``isless`` argsort, the whole host flow
+of ``_sort.py`` against the oracle (``tests/test_cpu_sort.py``), and that the collapsed box of ``collapse_dims`` addresses exactly the
+elements NumPy's broadcasting reads (``tests/test_cpu_host.py``).  What only a B200 can verify: the two small sort-by-key kernels,
+their ctypes bindings, and the N-d broadcast through the real NVRTC kernel.  The module therefore runs LAST (file name) and is marked
+``xfail(strict=False)``: a pass is reported as XPASS, a failure cannot hide a regression elsewhere or turn the tier red for code that
+was never claimed as measured."""
 import ctypes as C
 
 import numpy as np
@@ -15,7 +19,7 @@ import pytest
 from oracle import darray_oracle as orc
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="sort(d; by=f): new in the last session of round 2, never executed on a GPU (budget spent)")]
+              pytest.mark.xfail(strict=False, reason="added in the last session of round 2, never executed on a GPU (budget spent)")]
 
 
 def _sort_by_key(dab, rt, keys, vals):
@@ -94,3 +98,28 @@ def test_darray_sort_by(dab, rt8, T):
                     assert np.array_equal(ch.to_numpy().view(np.uint8), o2.chunks[o2.pids.index(pid)].view(np.uint8)), (n, tby)
                 d2.close()
         d.close()
+
+
+def test_broadcast_more_than_4_dims(dab, rt8):
+    """General (NVRTC) broadcasts over 5-D / 6-D arrays: same-shape arguments collapse to one dimension, extruded arguments to at
+    most 4 groups; bit-exact against NumPy in the same precision."""
+    rng = np.random.default_rng(91)
+    A = rng.standard_normal((6, 5, 4, 3, 4)).astype(np.float32)
+    B = rng.standard_normal((6, 5, 4, 3, 4)).astype(np.float32)
+    a, b = dab.distribute(A), dab.distribute(B)
+    r = dab.broadcast(lambda x, y: x - y * x, a, b)                             # nested tree: the fused general kernel
+    assert rt8.last_kernel == "dab_broadcast_expr"
+    assert np.array_equal(dab.to_array(r), A - B * A)
+    M = rng.standard_normal((6, 5, 1, 1, 4)).astype(np.float32)                 # extruded middle dims, plain array -> distributed
+    r2 = dab.broadcast(lambda x, m: x - m * x, a, M)
+    assert np.array_equal(dab.to_array(r2), A - M * A)
+    dest = dab.similar(a)
+    dab.broadcast_into(dest, lambda x, y: dab.sqrt(dab.abs2(x) + dab.abs2(y)), a, b)
+    assert np.array_equal(dab.to_array(dest), np.sqrt(A * A + B * B))
+    Cc = rng.integers(-50, 50, (6, 5, 4, 3, 4, 5)).astype(np.int64)
+    e = dab.distribute(Cc, procs=list(range(1, 9)), dist=(2, 1, 2, 1, 2, 1))
+    r3 = dab.broadcast(lambda x: x * x + 2 * x - 1, e)                          # result has the default layout: operands are halo-fetched
+    assert np.array_equal(dab.to_array(r3), Cc * Cc + 2 * Cc - 1)
+    V = rng.integers(-5, 5, (6, 1, 4, 1, 4, 1)).astype(np.int64)                # alternating extrusion: 6 groups, does not collapse
+    with pytest.raises(dab.UnsupportedError):
+        dab.broadcast(lambda x, v: x * v + v, e, V)

@@ -458,6 +458,11 @@ int32_t dab_gemm(dab_ctx* ctx, int32_t dtype, int32_t transA, size_t m, size_t n
     if (m == 0 || n == 0) return DAB_OK;
     DAB_REQUIRE(ctx, C && (k == 0 || (A && B)), DAB_ERR_ARG, "dab_gemm: null pointer");
     DAB_REQUIRE(ctx, ldc >= m && (k == 0 || (lda >= (transA ? k : m) && ldb >= k)), DAB_ERR_ARG, "dab_gemm: leading dimension smaller than the rows");
+    // B with ONE column (A * b for a DMatrix b of width 1, the narrowest block of a column-split B): the product is the matrix-vector
+    // product K9 already serves at the HBM roofline (one read of A, fp64 / wrap-around carriers); a 128-wide tensor-core tile would spend
+    // 127/128 of its MMAs on padding and stream A at the shared-memory rate.  Needs a dense A (lda == rows), which is what a chunk is.
+    if (n == 1 && k > 0 && lda == (transA ? k : m) && (dtype == DAB_F32 || dtype == DAB_F64 || dtype == DAB_I32 || dtype == DAB_I64))
+        return dab_gemv(ctx, dtype, transA ? 1 : 0, A, lda, transA ? m : k, B, C);
     switch (dtype) {
         case DAB_F32: {
             const bool big = m < ((size_t)1 << 31) && n < ((size_t)1 << 31) && k < ((size_t)1 << 31);

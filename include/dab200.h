@@ -256,7 +256,8 @@ int32_t dab_gemv(dab_ctx* ctx, int32_t dtype, int32_t trans, const void* A, size
  * _matmatmul! (src/linalg.jl:218-226); the caller scales C by beta and adds alpha * R per tile exactly as the reference (:232-252).
  * Float32 with 16-byte aligned bases and leading dimensions: TMA-fed tcgen05 (3xTF32 error-compensated, TMEM accumulators drained
  * every "gemm_kc" k for fp32 round-to-nearest accumulation); otherwise and for Float64 / Int32 / Int64: shared-memory tiled FMA kernel
- * (integers wrap like Julia's).  R is overwritten. */
+ * (integers wrap like Julia's).  n == 1 with a dense A (lda == its row count) IS a matrix-vector product and is served by K9
+ * (dab_gemv: one read of A at the HBM roofline).  R is overwritten. */
 int32_t dab_gemm(dab_ctx* ctx, int32_t dtype, int32_t transA, size_t m, size_t n, size_t k, const void* A, size_t lda, const void* B,
                  size_t ldb, void* C, size_t ldc);
 

@@ -2,6 +2,7 @@
 
   * ``sort(d; by = f)``: ``dab_sort_by_key`` (dab_sortby.cu) and the keyed samplesort of ``_sort.py`` (reference src/sort.jl:8, 22, 32,
     61, 77, 111);
+  * ``dab_gemm`` with a one-column B routed to K9 (``dab_gemv``) -- host-side dispatch only, both kernels are GPU-tested on their own;
   * general broadcasts over more than 4 dimensions (``collapse_dims`` in ``_broadcast.py``; reference src/broadcast.jl is N-d).
 
 STATUS: these tests have NOT been executed on hardware yet.  What is verified on CPU: the sort-by-key composition (key|position words,
@@ -123,3 +124,29 @@ def test_broadcast_more_than_4_dims(dab, rt8):
     V = rng.integers(-5, 5, (6, 1, 4, 1, 4, 1)).astype(np.int64)                # alternating extrusion: 6 groups, does not collapse
     with pytest.raises(dab.UnsupportedError):
         dab.broadcast(lambda x, v: x * v + v, e, V)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64])
+@pytest.mark.parametrize("transA", [False, True])
+def test_gemm_single_column_goes_through_gemv(dab, rt1, dtype, transA):
+    """``A * b`` with a one-column ``b`` (n == 1, dense A): served by K9 -- fp64 / wrap-around carriers, so Float32 is within one
+    rounding of the fp64 product and integers are exact; the same call with a padded leading dimension stays on K12."""
+    from test_gpu_gemm import check_float, gemm
+    rng = np.random.default_rng(101)
+    for m, k in [(4096, 2048), (1000, 37), (1, 1), (37, 4099)]:
+        shape = (k, m) if transA else (m, k)
+        if np.dtype(dtype).kind == "f":
+            A, B = rng.standard_normal(shape).astype(dtype), rng.standard_normal((k, 1)).astype(dtype)
+            n0 = rt1.launches()
+            R = gemm(dab, rt1, A, B, transA)
+            assert R.shape == (m, 1) and rt1.launches() > n0
+            check_float(R, A, B, transA, 1.2e-7 if dtype == np.float32 else 1e-15 * max(k, 8))
+            ra = A.shape[0]
+            Rp = gemm(dab, rt1, A, B, transA, lda=(ra + 3) // 4 * 4 + 4)        # padded lda: not a dense chunk -> the tile kernels
+            check_float(Rp, A, B, transA, 2e-6 if dtype == np.float32 else 1e-15 * max(k, 8))
+        else:
+            hi = 2 ** 20 if dtype == np.int32 else 2 ** 40
+            A, B = rng.integers(-hi, hi, shape).astype(dtype), rng.integers(-hi, hi, (k, 1)).astype(dtype)
+            with np.errstate(over="ignore"):
+                want = (A.T if transA else A) @ B
+            assert np.array_equal(gemm(dab, rt1, A, B, transA), want)

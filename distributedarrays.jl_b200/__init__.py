@@ -11,8 +11,8 @@ importing works anywhere, but the first op without the built extension or withou
 """
 from . import _lib
 from ._lib import ArgumentError, DabError, DimensionMismatch, UnsupportedError
-from ._broadcast import (Expr, abs2, broadcast, broadcast_into, ceil, cos, exp, floor, ifelse, inv, isnan, jl_max, jl_min,
-                        log, map_, map_bang, map_inplace, map_localparts, mod, rem, sign, sin, sqrt, tan, tanh)
+from ._broadcast import (Expr, Int128, abs2, broadcast, broadcast_into, ceil, cos, exp, floor, ifelse, inv, isnan, jl_max, jl_min,
+                        log, map_, map_bang, map_inplace, map_localparts, mod, rem, sign, sin, sqrt, tan, tanh, widen)
 from ._darray import (B200Array, DArray, SubDArray, allowscalar, dab_dtype, np_dtype, copyto, d_closeall, darray, darray_from_chunks, darray_like,
                      dfill, distribute, dones, drand, dzeros, fill_, localindices, localpart, locate, makelocal, pinned_empty, procs,
                      registry_size, similar, to_array)

@@ -24,17 +24,30 @@ from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
+from builtins import any as builtins_any
+
 from . import _lib
 from ._darray import B200Array, DArray, dab_dtype, darray, makelocal
 from .layout import shape_of
 from .runtime import runtime
 
 # Julia-type tags and the promotion lattice
-_RANK = {"bool": 0, "i32": 1, "i64": 2, "f32": 3, "f64": 4}
-_NPT = {"bool": np.dtype(np.bool_), "i32": np.dtype(np.int32), "i64": np.dtype(np.int64), "f32": np.dtype(np.float32),
-        "f64": np.dtype(np.float64)}
+_RANK = {"bool": 0, "i32": 1, "i64": 2, "i128": 3, "f32": 4, "f64": 5}
+
+
+class _TagTypes(dict):
+    """Julia type tag -> array element type.  ``i128`` (Int128) exists only as a VALUE type inside ``mapreduce`` (``f`` widens its
+    argument, test/darray.jl:286-294): there are no Int128 arrays, so every place that needs an element type for it refuses."""
+
+    def __missing__(self, tag):
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"values of type {tag} have no array element type on the B200 backend "
+                                    "(Int128 is served as the value type of mapreduce(f, op, d) only)")
+
+
+_NPT = _TagTypes({"bool": np.dtype(np.bool_), "i32": np.dtype(np.int32), "i64": np.dtype(np.int64), "f32": np.dtype(np.float32),
+                  "f64": np.dtype(np.float64)})
 _TAG = {v: k for k, v in _NPT.items()}
-_CT = {"bool": "bool", "i32": "int", "i64": "long long", "f32": "float", "f64": "double"}
+_CT = {"bool": "bool", "i32": "int", "i64": "long long", "i128": "i128", "f32": "float", "f64": "double"}
 
 
 def tag_of(dtype) -> str:
@@ -182,12 +195,31 @@ def convert(a: Expr, jt: str) -> Expr:
             v = float(np.float32(v))
         elif jt == "f64":
             v = float(v)
-        elif jt in ("i32", "i64"):
+        elif jt in ("i32", "i64", "i128"):
             v = int(v)
         else:
             v = bool(v)
         return Expr("const", (), jt, v)
     return Expr("convert", (a,), jt)
+
+
+def Int128(x) -> Expr:
+    """``Int128(x)`` inside a map function: the value continues in 128-bit wrap-around integer arithmetic
+    (``mapreduce(x -> Int128(x)^2 + 2*Int128(x) - 1, *, d)`` -- the exactness test of test/darray.jl:286-294)."""
+    return convert(Expr.wrap(x), "i128")
+
+
+def widen(x) -> Expr:
+    """Julia's ``widen``: Int32 -> Int64, Int64 -> Int128, Float32 -> Float64."""
+    e = Expr.wrap(x)
+    to = {"bool": "i64", "i32": "i64", "i64": "i128", "f32": "f64"}.get(e.jt)
+    if to is None:
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"widen({e.jt}) is not served")
+    return convert(e, to)
+
+
+def uses_tag(e: Expr, tag: str) -> bool:
+    return e.jt == tag or builtins_any(uses_tag(a, tag) for a in e.args)
 
 
 def ifelse(c, a, b) -> Expr:
@@ -257,6 +289,9 @@ def _lit(jt: str, v) -> str:
         return "((int)%d)" % int(v)
     if jt == "i64":
         return "((long long)%dLL)" % int(v)
+    if jt == "i128":
+        v = int(v) % (1 << 128)                                  # two's complement words; a literal cannot be wider than 64 bits in C
+        return "((i128)(((u128)0x%016xULL << 64) | (u128)0x%016xULL))" % (v >> 64, v & ((1 << 64) - 1))
     return "true" if v else "false"
 
 
@@ -418,6 +453,8 @@ def run_local(rt, expr: Expr, out: B200Array, largs: List[LocalArg]):
         return
     # ---- general fused kernel (NVRTC)
     rt.last_kernel = "dab_broadcast_expr"
+    if uses_tag(expr, "i128"):
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "Int128 values are served inside mapreduce(f, op, d) only, not in a broadcast")
     if expr.jt[0] == "f" and out_tag[0] != "f":
         # dest .= f.(...) with an integer/Bool destination and float values: Julia converts exactly or throws InexactError per
         # element; a C cast would silently truncate

@@ -14,7 +14,7 @@ SO_PATH = os.path.join(_HERE, "csrc", "libdab200.so")
 
 # ---- enums (include/dab200.h) ----------------------------------------------------------------------------
 OK, ERR_CUDA, ERR_ARG, ERR_EMPTY, ERR_DIM_MISMATCH, ERR_NCCL, ERR_UNSUPPORTED, ERR_NVRTC, ERR_NOMEM = range(9)
-F32, F64, I32, I64, U8 = range(5)
+F32, F64, I32, I64, U8, I128 = range(6)     # I128: value type of dab_mapreduce_expr only
 SUM, PROD, MAX, MIN, ALL, ANY, COUNT, EXTREMA = range(8)
 MAP_ID, MAP_ABS, MAP_ABS2, MAP_NEG, MAP_SQRT, MAP_INV, MAP_FLOOR, MAP_CEIL, MAP_SIGN = range(9)
 MAP_EQ, MAP_NE, MAP_LT, MAP_LE, MAP_GT, MAP_GE, MAP_ISNAN, MAP_NONZERO = range(16, 24)

@@ -123,6 +123,24 @@ def _fold(host: np.ndarray, pids: Sequence[int], rdt: np.dtype, op: int):
     return out[0], vals
 
 
+def _int128(b: bytes) -> int:
+    return int.from_bytes(b, "little", signed=True)
+
+
+def wrap128(v: int) -> int:
+    """Two's-complement wrap-around of Int128 machine arithmetic."""
+    v &= (1 << 128) - 1
+    return v - (1 << 128) if v >> 127 else v
+
+
+def fold128(vals: Sequence[int], op: int) -> int:
+    """``reduce(op, results)`` (src/mapreduce.jl:34) for Int128 chunk results: left fold in procs(d) order, wrapping like Julia."""
+    acc = vals[0]
+    for v in vals[1:]:
+        acc = wrap128(acc + v) if op == _lib.SUM else wrap128(acc * v) if op == _lib.PROD else (max(acc, v) if op == _lib.MAX else min(acc, v))
+    return acc
+
+
 def _check_nonempty(d: DArray, opc: int):
     if opc in (_lib.MAX, _lib.MIN):
         for pid in d.layout.pids:
@@ -154,12 +172,18 @@ def _mapreduce_expr(expr: Expr, opc: int, d: DArray, others: Sequence, return_pa
         raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "more than 8 mapreduce arguments are not served")
     _check_nonempty(d, opc)
     val_tag = expr.jt
-    val_code = dab_dtype(NPT[val_tag])
+    wide = val_tag == "i128"                     # Int128 VALUES (f widens its argument): the 16-byte slot is the result
+    if wide and opc not in (_lib.SUM, _lib.PROD, _lib.MAX, _lib.MIN):
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "Int128 values are reduced with + * max min only")
+    val_code = _lib.I128 if wide else dab_dtype(NPT[val_tag])
     if val_tag == "bool" and opc == _lib.SUM:
         opc_k = _lib.COUNT                       # sum of Bools == count (Int64)
     else:
         opc_k = opc
-    rdt = np.dtype(np.int64) if val_tag in ("bool", "i32", "i64") and opc in (_lib.SUM, _lib.PROD, _lib.ALL, _lib.ANY, _lib.COUNT) else NPT[val_tag]
+    if wide:
+        rdt = np.dtype((np.void, 16))            # raw slot bytes; decoded to Python ints below
+    else:
+        rdt = np.dtype(np.int64) if val_tag in ("bool", "i32", "i64") and opc in (_lib.SUM, _lib.PROD, _lib.ALL, _lib.ANY, _lib.COUNT) else NPT[val_tag]
     src = codegen(expr).encode()
     from ._broadcast import _finish_remote_reads
     remote = _prepare_remote_reads(d.layout, rt, [a for a in others if isinstance(a, DArray)])
@@ -167,7 +191,7 @@ def _mapreduce_expr(expr: Expr, opc: int, d: DArray, others: Sequence, return_pa
 
     def launch(pid, ch, slot_ptr):
         if ch.size == 0:
-            return _empty_slot(rt, opc, rdt, slot_ptr)
+            return _empty_slot(rt, opc, np.dtype(np.int64) if wide else rdt, slot_ptr)   # 0 / 1 zero-extended = the Int128 identity
         I = d.layout.localindices(pid)
         largs = [_localise(rt, a, I, pid) for a in args]
         n = len(largs)
@@ -187,6 +211,10 @@ def _mapreduce_expr(expr: Expr, opc: int, d: DArray, others: Sequence, return_pa
         for t in temps:
             t.free()
         _finish_remote_reads(rt, remote)
+    if wide:
+        vals = [_int128(host[16 * (pid - 1):16 * pid].tobytes()) for pid in d.layout.pids]
+        res = fold128(vals, opc)
+        return (res, vals) if return_partials else res
     res, vals = _fold(host, d.layout.pids, rdt, opc if opc != _lib.COUNT else _lib.SUM)
     return (res, vals) if return_partials else res
 

@@ -129,6 +129,26 @@ template <typename T, int N> struct __align__(sizeof(T) * N) VecN { T v[N]; };
 template <typename T> DEV T bits_as(u64 b) { T r; memcpy(&r, &b, sizeof(T)); return r; }
 )PRELUDE";
 
+// Int128 as the VALUE type of a fused map + reduce (f widens its argument: x -> Int128(x)^2 + 2 Int128(x) - 1, test/darray.jl:286-294).
+// Appended to the prelude -- and NVRTC's --device-int128 switched on -- only for sources that mention the type, so every other generated
+// kernel is byte-for-byte what it was.
+const char* kPreludeI128 = R"PRELUDE(
+typedef __int128 i128;
+typedef unsigned __int128 u128;
+DEV i128 jl_add(i128 a, i128 b) { return (i128)((u128)a + (u128)b); }
+DEV i128 jl_sub(i128 a, i128 b) { return (i128)((u128)a - (u128)b); }
+DEV i128 jl_mul(i128 a, i128 b) { return (i128)((u128)a * (u128)b); }
+DEV i128 jl_neg(i128 a) { return (i128)((u128)0 - (u128)a); }
+DEV i128 jl_abs(i128 a) { return a < 0 ? (i128)((u128)0 - (u128)a) : a; }
+DEV i128 jl_max(i128 a, i128 b) { return a > b ? a : b; }
+DEV i128 jl_min(i128 a, i128 b) { return a < b ? a : b; }
+DEV i128 jl_and(i128 a, i128 b) { return a & b; }
+DEV i128 jl_or(i128 a, i128 b) { return a | b; }
+DEV i128 jl_xor(i128 a, i128 b) { return a ^ b; }
+)PRELUDE";
+
+bool mentions_i128(const char* expr) { return expr && strstr(expr, "i128") != nullptr; }
+
 const char* ctype_of(int32_t dt) {
     switch (dt) {
         case DAB_F32: return "float";
@@ -139,6 +159,9 @@ const char* ctype_of(int32_t dt) {
         default: return nullptr;
     }
 }
+
+// value type of dab_mapreduce_expr: the array element types plus Int128
+const char* vtype_of(int32_t dt) { return dt == DAB_I128 ? "i128" : ctype_of(dt); }
 
 struct BcParamsHost {
     void* out;
@@ -371,14 +394,14 @@ std::string build_source(const char* expr, int32_t out_dt, int nargs, const int3
     return s;
 }
 
-int32_t compile_cubin(dab_ctx* ctx, const std::string& src, std::vector<char>* cubin_out) {
+int32_t compile_cubin(dab_ctx* ctx, const std::string& src, std::vector<char>* cubin_out, bool int128 = false) {
     Nvrtc& rt = nvrtc();
     if (!rt.ok) return dab_fail(ctx, DAB_ERR_NVRTC, "NVRTC unavailable: %s", rt.why);
     nvrtcProgram prog;
     nvrtcResult r = rt.CreateProgram(&prog, src.c_str(), "dab_broadcast.cu", 0, nullptr, nullptr);
     if (r != NVRTC_SUCCESS) return dab_fail(ctx, DAB_ERR_NVRTC, "nvrtcCreateProgram: %s", rt.GetErrorString(r));
-    const char* opts[] = {"--gpu-architecture=sm_100a", "-fmad=false", "--std=c++17", "-lineinfo", "-default-device"};
-    r = rt.CompileProgram(prog, 5, opts);
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-fmad=false", "--std=c++17", "-lineinfo", "-default-device", "--device-int128"};
+    r = rt.CompileProgram(prog, int128 ? 6 : 5, opts);
     if (r != NVRTC_SUCCESS) {
         size_t ls = 0;
         rt.GetProgramLogSize(prog, &ls);
@@ -434,7 +457,16 @@ struct MrSpec {
 
 bool mr_spec(int32_t val_dt, int32_t op, MrSpec* sp) {
     const bool flt = val_dt == DAB_F32 || val_dt == DAB_F64, boolean = val_dt == DAB_U8;
-    const char* vt = ctype_of(val_dt);
+    const char* vt = vtype_of(val_dt);
+    if (val_dt == DAB_I128) {  // tile, carrier and result are all Int128; + and * wrap, so any grouping gives the same bits
+        switch (op) {
+            case DAB_SUM: *sp = {vt, vt, vt, "jl_add(a, b)", "jl_add(a, b)", "0"}; return true;
+            case DAB_PROD: *sp = {vt, vt, vt, "jl_mul(a, b)", "jl_mul(a, b)", "1"}; return true;
+            case DAB_MAX: *sp = {vt, vt, vt, "jl_max(a, b)", "jl_max(a, b)", "((u128)1 << 127)"}; return true;
+            case DAB_MIN: *sp = {vt, vt, vt, "jl_min(a, b)", "jl_min(a, b)", "(~((u128)1 << 127))"}; return true;
+            default: return false;
+        }
+    }
     switch (op) {
         case DAB_SUM:
         case DAB_COUNT:
@@ -485,7 +517,9 @@ struct MrFinalHost {
 
 std::string build_mr_source(const char* expr, int32_t val_dt, int32_t op, int nargs, const int32_t* dts, const bool* is_arr, const MrSpec& sp) {
     std::string s = kPrelude;
-    s += std::string("typedef ") + ctype_of(val_dt) + " VAL_T;\n";
+    if (val_dt == DAB_I128 || mentions_i128(expr)) s += kPreludeI128;
+    if (val_dt == DAB_I128) s += "#define DAB_ACC16 1\n";   // 16-byte carrier: shuffles and the result slot move four words
+    s += std::string("typedef ") + vtype_of(val_dt) + " VAL_T;\n";
     for (int k = 0; k < nargs; ++k) s += std::string("typedef ") + ctype_of(dts[k]) + " T" + std::to_string(k) + ";\n";
     s += std::string("typedef ") + sp.tile_t + " TILE_T;\ntypedef " + sp.acc_t + " ACC_T;\ntypedef " + sp.out_t + " OUT_T;\n";
     s += "#define DAB_EXPR (";
@@ -498,6 +532,12 @@ std::string build_mr_source(const char* expr, int32_t val_dt, int32_t op, int na
 struct MrParams { const void* ptr[8]; u64 scalar[8]; u64 n; void* partials; int tiles_per_cta; };
 struct MrFinal { const void* partials; void* out; i64 n; unsigned int nparts; int mode; };
 DEV ACC_T acc_shfl(ACC_T v, int d) {
+#ifdef DAB_ACC16
+    int w[4]; memcpy(w, &v, 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = __shfl_down_sync(0xffffffffu, w[k], d);
+    ACC_T r; memcpy(&r, w, 16); return r;
+#else
     if (sizeof(ACC_T) == 8) {
         i64 x; memcpy(&x, &v, 8);
         int lo = __shfl_down_sync(0xffffffffu, (int)(x & 0xffffffffll), d), hi = __shfl_down_sync(0xffffffffu, (int)(x >> 32), d);
@@ -508,6 +548,7 @@ DEV ACC_T acc_shfl(ACC_T v, int d) {
         x = __shfl_down_sync(0xffffffffu, x, d);
         ACC_T r; memcpy(&r, &x, sizeof(ACC_T)); return r;
     }
+#endif
 }
 DEV ACC_T block_reduce(ACC_T acc, ACC_T* smem) {
 #pragma unroll
@@ -539,11 +580,15 @@ extern "C" __global__ void __launch_bounds__(256) dab_mr_final(MrFinal p) {
         if (p.mode == 1) res = (OUT_T)(acc == (ACC_T)p.n);
         else if (p.mode == 2) res = (OUT_T)(acc != (ACC_T)0);
         else res = (OUT_T)acc;
+#ifdef DAB_ACC16
+        memcpy(p.out, &res, 16);
+#else
         u64 w0 = 0, w1 = 0;
         memcpy(&w0, &res, sizeof(OUT_T));
         memcpy(&w1, &acc, sizeof(ACC_T));
         ((u64*)p.out)[0] = w0;
         ((u64*)p.out)[1] = w1;
+#endif
     }
 }
 )MR";
@@ -716,7 +761,7 @@ int32_t dab_mapreduce_expr(dab_ctx* ctx, const char* expr, int32_t val_dtype, in
     DAB_ENTER(ctx);
     DAB_REQUIRE(ctx, expr && out_dev, DAB_ERR_ARG, "dab_mapreduce_expr: null pointer");
     DAB_REQUIRE(ctx, nargs >= 1 && nargs <= 8 && arg_dtypes && arg_ptrs && arg_scalars, DAB_ERR_ARG, "dab_mapreduce_expr: bad argument table");
-    DAB_REQUIRE(ctx, ctype_of(val_dtype), DAB_ERR_ARG, "dab_mapreduce_expr: bad value dtype %d", val_dtype);
+    DAB_REQUIRE(ctx, vtype_of(val_dtype), DAB_ERR_ARG, "dab_mapreduce_expr: bad value dtype %d", val_dtype);
     DAB_REQUIRE(ctx, n > 0, DAB_ERR_EMPTY, "dab_mapreduce_expr: empty input (the host runtime handles n == 0)");
     MrSpec sp;
     if (!mr_spec(val_dtype, op, &sp))
@@ -742,7 +787,8 @@ int32_t dab_mapreduce_expr(dab_ctx* ctx, const char* expr, int32_t val_dtype, in
             Driver& drv = driver();
             if (!drv.ok) return dab_fail(ctx, DAB_ERR_NVRTC, "CUDA driver API unavailable: %s", drv.why);
             std::vector<char> cubin;
-            int32_t st = compile_cubin(ctx, build_mr_source(expr, val_dtype, op, nargs, arg_dtypes, is_arr, sp), &cubin);
+            int32_t st = compile_cubin(ctx, build_mr_source(expr, val_dtype, op, nargs, arg_dtypes, is_arr, sp), &cubin,
+                                       val_dtype == DAB_I128 || mentions_i128(expr));
             if (st != DAB_OK) return st;
             CUmodule mod;
             if (drv.ModuleLoadData(&mod, cubin.data()) != CUDA_SUCCESS) return dab_fail(ctx, DAB_ERR_NVRTC, "cuModuleLoadData failed");
@@ -788,7 +834,7 @@ int32_t dab_mapreduce_expr(dab_ctx* ctx, const char* expr, int32_t val_dtype, in
 // Diagnostic twin of dab_jit_compile_check for the fused map+reduce kernels.
 int32_t dab_jit_compile_check_reduce(const char* expr, int32_t val_dtype, int32_t op, int32_t nargs, const int32_t* arg_dtypes,
                                      const int32_t* arg_is_array, size_t* cubin_bytes) {
-    if (!expr || !ctype_of(val_dtype) || nargs < 1 || nargs > 8 || !arg_dtypes || !arg_is_array)
+    if (!expr || !vtype_of(val_dtype) || nargs < 1 || nargs > 8 || !arg_dtypes || !arg_is_array)
         return dab_fail(nullptr, DAB_ERR_ARG, "dab_jit_compile_check_reduce: bad argument");
     MrSpec sp;
     if (!mr_spec(val_dtype, op, &sp)) return dab_fail(nullptr, DAB_ERR_UNSUPPORTED, "op %d on value dtype %d not served", op, val_dtype);
@@ -798,7 +844,8 @@ int32_t dab_jit_compile_check_reduce(const char* expr, int32_t val_dtype, int32_
         is_arr[k] = arg_is_array[k] != 0;
     }
     std::vector<char> cubin;
-    int32_t st = compile_cubin(nullptr, build_mr_source(expr, val_dtype, op, nargs, arg_dtypes, is_arr, sp), &cubin);
+    int32_t st = compile_cubin(nullptr, build_mr_source(expr, val_dtype, op, nargs, arg_dtypes, is_arr, sp), &cubin,
+                               val_dtype == DAB_I128 || mentions_i128(expr));
     if (st != DAB_OK) return st;
     if (cubin_bytes) *cubin_bytes = cubin.size();
     return DAB_OK;

@@ -57,7 +57,9 @@ enum {
 };
 
 /* ---- element types ----------------------------------------------------------------- */
-enum { DAB_F32 = 0, DAB_F64 = 1, DAB_I32 = 2, DAB_I64 = 3, DAB_U8 = 4 /* Bool */ };
+enum { DAB_F32 = 0, DAB_F64 = 1, DAB_I32 = 2, DAB_I64 = 3, DAB_U8 = 4 /* Bool */,
+       DAB_I128 = 5 /* Int128: ONLY as the value type of dab_mapreduce_expr (f widens, e.g. x -> Int128(x)^2; test/darray.jl:286-294);
+                       there are no arrays of it.  Its result fills the whole 16-byte slot (two's complement, little endian). */ };
 
 /* ---- reduce operators  (op argument of Base.mapreduce; src/mapreduce.jl:31) ----------- */
 enum {
@@ -187,7 +189,8 @@ int32_t dab_jit_compile_check(const char* expr, int32_t out_dtype, int32_t nargs
 /* Fused map + reduce of an arbitrary traced expression over one localpart, ONE pass over HBM:  mapreduce(f, op, args...)
  * (reference src/mapreduce.jl:31 with a general closure f; dot(x, y) = mapreduce(*, +, x, y); d == a via all(x .== y)).
  * expr / args as in dab_broadcast_expr but all array arguments are dense with n elements (linear indexing); val_dtype is the
- * type of the expression's value.  The 16-byte result slot at out_dev has the layout of dab_reduce.  NVRTC-compiled, cached. */
+ * type of the expression's value.  The 16-byte result slot at out_dev has the layout of dab_reduce (val_dtype DAB_I128, ops SUM / PROD /
+ * MAX / MIN: the slot IS the Int128 result; wrap-around arithmetic like Julia's).  NVRTC-compiled, cached. */
 int32_t dab_mapreduce_expr(dab_ctx* ctx, const char* expr, int32_t val_dtype, int32_t op, size_t n, int32_t nargs, const int32_t* arg_dtypes,
                            const void* const* arg_ptrs, const uint64_t* arg_scalars, void* out_dev);
 int32_t dab_jit_compile_check_reduce(const char* expr, int32_t val_dtype, int32_t op, int32_t nargs, const int32_t* arg_dtypes,

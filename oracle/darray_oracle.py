@@ -501,6 +501,26 @@ def darray_mapreduce(f, op: str, d: ODArray, simd=None):
     return np.asarray(r)[()], results
 
 
+def wrap_int128(v: int) -> int:
+    """Two's-complement wrap-around of Julia's Int128 machine arithmetic."""
+    v &= (1 << 128) - 1
+    return v - (1 << 128) if v >> 127 else v
+
+
+def darray_mapreduce_int128(f: Callable[[int], int], op: str, d: ODArray) -> int:
+    """``mapreduce(f, op, DA)`` for an Int128-valued ``f`` on an integer DArray -- the exactness test of test/darray.jl:286-294
+    (``f in (x -> Int128(2x), x -> Int128(x^2), x -> Int128(x^2 + 2x - 1))``, ``op in (+, *)``).  Per worker
+    ``mapreduce(f, op, localpart)`` (src/mapreduce.jl:31), then the caller's left fold (:34); + and * in Int128 wrap, so every
+    grouping gives the same bits -- which is what makes the reference's ``== 0`` test meaningful.  Python integers, exact."""
+    def red(vals):
+        acc = vals[0]
+        for v in vals[1:]:
+            acc = wrap_int128(acc + v if op == "+" else acc * v)
+        return acc
+    parts = [red([wrap_int128(f(int(x))) for x in c.reshape(-1, order="F")]) for c in d.chunks if c.size]
+    return red(parts)
+
+
 def darray_all(pred, d: ODArray) -> bool:
     """src/mapreduce.jl:97-104."""
     return all(bool(np.all(pred(ch))) for ch in d.chunks)

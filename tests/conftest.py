@@ -58,6 +58,14 @@ def hostmem(dab, monkeypatch):
     fake = hostmem_abi.HostMemABI()
     lib_mod._lib = fake
     monkeypatch.setattr(bc_mod, "run_local", hostmem_abi.run_local)
+    real_codegen = bc_mod.codegen
+
+    def recording_codegen(e):                                  # lets the emulated dab_mapreduce_expr find the tree behind a source string
+        src = real_codegen(e)
+        fake.exprs[src.encode()] = e
+        return src
+
+    monkeypatch.setattr(bc_mod, "codegen", recording_codegen)
     try:
         yield fake
     finally:

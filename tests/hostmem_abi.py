@@ -12,7 +12,10 @@ What is emulated follows the KERNELS' algorithms, not a NumPy shortcut, wherever
     second round on the high half for 64-bit keys and gathers by the low halves -- the composition of ``dab_sortby.cu`` step by step;
   * ``dab_sorted_split`` is the binary search of ``sort_bounds_kernel`` (NaN bound, -0.0 bound, all-NaN tail);
   * ``dab_copy_box`` is the 4-D box copy.
-Traced closures are evaluated by a small NumPy interpreter of the expression tree (``eval_expr``) in place of the NVRTC kernel.
+Traced closures are evaluated by a small NumPy interpreter of the expression tree (``eval_expr``) in place of the NVRTC kernel;
+``dab_mapreduce_expr`` is emulated for Int128-valued map functions (the fixture records which traced expression each generated
+source string came from), so that the host side of ``mapreduce(x -> Int128(x)^2 ..., op, d)`` -- slot decoding, the wrap-around
+fold over the workers -- runs on CPU.
 """
 from __future__ import annotations
 
@@ -103,6 +106,7 @@ class HostMemABI:
         self.blocks = {}
         self.launches = 0
         self.calls = []
+        self.exprs = {}                                         # generated source -> traced Expr (filled by the fixture's codegen wrapper)
 
     # -- lifecycle / diagnostics
     def dab_abi_version(self):
@@ -213,6 +217,29 @@ class HostMemABI:
         self.launches += 2
         return 0
 
+    # -- fused map + reduce of a traced expression, Int128 values only (the other value types need dab_combine_ordered etc.)
+    def dab_mapreduce_expr(self, ctx, src, val_dtype, op, n, nargs, dts, ptrs, scal, out):
+        assert int(val_dtype) == 5, "hostmem_abi emulates dab_mapreduce_expr for Int128 values only"
+        expr = self.exprs[src]
+        n = int(n)
+        args = []
+        for k in range(int(nargs)):
+            p = ptrs[k]
+            if p:
+                args.append(_view(p, n, _NP[int(dts[k])] if int(dts[k]) != U8 else np.bool_).copy())
+            else:
+                args.append(np.frombuffer(int(scal[k]).to_bytes(8, "little"), dtype=_NP[int(dts[k])])[0])
+        vals = [int(v) for v in np.broadcast_to(eval_expr(expr, args), (n,))]
+        mask = (1 << 128) - 1
+        acc = vals[0]
+        for v in vals[1:]:
+            acc = {0: acc + v, 1: acc * v, 2: max(acc, v), 3: min(acc, v)}[int(op)]
+            acc &= mask
+            acc = acc - (1 << 128) if acc >> 127 else acc
+        C.memmove(_addr(out), (acc & mask).to_bytes(16, "little"), 16)
+        self.launches += 2
+        return 0
+
     def dab_sorted_split(self, ctx, dtype, sorted_p, n, bounds_host, nb, counts):
         n, nb, u = int(n), int(nb), _utype(dtype)
         raw = _view(sorted_p, n, u)
@@ -243,7 +270,9 @@ def eval_expr(e, args):
     if e.op == "arg":
         return args[e.val]
     if e.op == "const":
-        return npt[e.jt].type(e.val)
+        return _wrap128(int(e.val)) if e.jt == "i128" else npt[e.jt].type(e.val)
+    if e.jt == "i128" or any(x.jt == "i128" for x in e.args):
+        return _eval_i128(e, args)
     if e.op == "convert":
         return np.asarray(eval_expr(e.args[0], args)).astype(npt[e.jt])
     a = [eval_expr(x, args) for x in e.args]
@@ -263,6 +292,32 @@ def eval_expr(e, args):
                    "tanh": np.tanh, "isnan": np.isnan}
             r = one[e.op](a[0])
         return np.asarray(r).astype(npt[e.jt])
+
+
+def _wrap128(v: int) -> int:
+    v &= (1 << 128) - 1
+    return v - (1 << 128) if v >> 127 else v
+
+
+def _eval_i128(e, args):
+    """Int128 sub-expressions on object arrays of Python ints, wrapped to 128 bits after every operation."""
+    import operator
+    if e.op == "const":
+        return _wrap128(int(e.val))
+    a = [eval_expr(x, args) for x in e.args]
+    if e.op == "convert":
+        if e.jt == "i128":
+            return np.vectorize(lambda v: _wrap128(int(v)), otypes=[object])(a[0])
+        from darray_b200 import _broadcast as bc
+        return np.vectorize(float, otypes=[np.float64])(a[0]).astype(bc._NPT[e.jt])   # Int128 -> float
+    if e.op in ("lt", "le", "gt", "ge", "eq", "ne"):
+        return np.vectorize(getattr(operator, e.op), otypes=[bool])(a[0], a[1])
+    two = {"add": operator.add, "sub": operator.sub, "mul": operator.mul, "max": max, "min": min, "and": operator.and_, "or": operator.or_,
+           "xor": operator.xor}
+    if e.op in two:
+        return np.vectorize(lambda x, y: _wrap128(two[e.op](int(x), int(y))), otypes=[object])(a[0], a[1])
+    one = {"neg": operator.neg, "abs": abs, "abs2": lambda x: x * x}
+    return np.vectorize(lambda x: _wrap128(one[e.op](int(x))), otypes=[object])(a[0])
 
 
 def run_local(rt, expr, out, largs):

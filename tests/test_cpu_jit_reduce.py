@@ -2,6 +2,9 @@
 (op, value type) combination the host runtime can request, and unsupported combinations are refused, not silently served."""
 import ctypes as C
 
+import numpy as np
+import pytest
+
 
 def _check(dab, f, tags, op, arrays=None):
     from darray_b200 import _lib
@@ -38,3 +41,73 @@ def test_fused_mapreduce_refuses_unsupported(dab):
     assert st == _lib.ERR_UNSUPPORTED
     st, _, err = _check(dab, lambda v: v * 2, ["f32"], _lib.ALL)          # all() of non-Bool values
     assert st == _lib.ERR_UNSUPPORTED
+
+
+# ---- Int128 as the value type of mapreduce (reference test/darray.jl:286-294: exact mapreduce of Int128-valued f) -----------------------
+
+def test_int128_tracer_and_kernels_compile():
+    import ctypes as C
+
+    import darray_b200 as dab
+    from darray_b200 import _broadcast as bc
+    from darray_b200 import _lib
+    e = bc.trace(lambda x: dab.Int128(x) ** 2 + 2 * dab.Int128(x) - 1, ["i64"])
+    assert e.jt == "i128" and bc.uses_tag(e, "i128")
+    assert bc.trace(lambda x: dab.widen(x) * dab.widen(x), ["i64"]).jt == "i128"
+    assert bc.trace(lambda x: dab.widen(x), ["i32"]).jt == "i64" and bc.trace(lambda x: dab.widen(x), ["f32"]).jt == "f64"
+    assert bc.trace(lambda x: dab.Int128(x) * 1.5, ["i64"]).jt == "f64"            # promote_type(Int128, Float64) == Float64
+    assert bc.trace(lambda x: dab.Int128(x) + x, ["i32"]).jt == "i128"
+    with pytest.raises(dab.UnsupportedError):
+        bc._NPT["i128"]                                                             # no arrays of Int128
+    src = bc.codegen(e).encode()
+    L = _lib.lib()
+    for op in (_lib.SUM, _lib.PROD, _lib.MAX, _lib.MIN):
+        nbytes = C.c_size_t()
+        st = L.dab_jit_compile_check_reduce(src, _lib.I128, op, 1, (C.c_int32 * 1)(_lib.I64), (C.c_int32 * 1)(1), C.byref(nbytes))
+        assert st == 0 and nbytes.value > 1000, L.dab_last_error(None)
+    assert L.dab_jit_compile_check_reduce(src, _lib.I128, _lib.ALL, 1, (C.c_int32 * 1)(_lib.I64), (C.c_int32 * 1)(1), C.byref(nbytes)) == _lib.ERR_UNSUPPORTED
+    # an Int128 intermediate under a Float64 value: the i128 prelude rides along
+    src2 = bc.codegen(bc.trace(lambda x: (dab.Int128(x) * dab.Int128(x)) * 1.0, ["i64"])).encode()
+    assert L.dab_jit_compile_check_reduce(src2, _lib.F64, _lib.SUM, 1, (C.c_int32 * 1)(_lib.I64), (C.c_int32 * 1)(1), C.byref(nbytes)) == 0
+    # literals wider than 64 bits and negative ones survive the two-word spelling
+    lit = bc._lit("i128", -3)
+    assert "0xffffffffffffffffULL << 64" in lit and "0xfffffffffffffffdULL" in lit
+
+
+def test_int128_fold_wraps_like_julia():
+    from darray_b200 import _lib
+    from darray_b200._mapreduce import fold128, wrap128
+    assert wrap128(2 ** 127) == -2 ** 127 and wrap128(-2 ** 127 - 1) == 2 ** 127 - 1 and wrap128(5) == 5
+    assert fold128([2 ** 126, 2 ** 126], _lib.SUM) == -2 ** 127
+    assert fold128([34 ** 20, 34 ** 10], _lib.PROD) == wrap128(34 ** 30)
+    assert fold128([-5, 7, 3], _lib.MAX) == 7 and fold128([-5, 7, 3], _lib.MIN) == -5
+
+
+def test_int128_mapreduce_host_flow(hostmem, dab):
+    """The reference's exactness test (test/darray.jl:286-294) through the host runtime on the host-memory ABI: random 1:5 vectors of
+    length 2..30, f in {2x, x^2, x^2 + 2x - 1} widened to Int128, op in {+, *}; the result equals Python's exact integers wrapped
+    to 128 bits (the product of 30 values up to 34 does not fit 64 bits)."""
+    from darray_b200._mapreduce import wrap128
+    rng = np.random.default_rng(286)
+    fs = [(lambda x: 2 * dab.Int128(x), lambda v: 2 * v), (lambda x: dab.Int128(x) ** 2, lambda v: v * v),
+          (lambda x: dab.Int128(x) ** 2 + 2 * dab.Int128(x) - 1, lambda v: v * v + 2 * v - 1)]
+    for nw in (1, 2, 8):
+        dab.init(workers_per_rank=nw, use_dist=False)
+        for _ in range(8):
+            a = rng.integers(1, 6, int(rng.integers(max(2, nw), 31))).astype(np.int64)
+            d = dab.distribute(a)
+            for tf, pf in fs:
+                vals = [pf(int(v)) for v in a]
+                assert dab.mapreduce(tf, "+", d) == wrap128(sum(vals))
+                prod = 1
+                for v in vals:
+                    prod *= v
+                got = dab.mapreduce(tf, "*", d)
+                assert isinstance(got, int) and got == wrap128(prod)
+            assert dab.mapreduce(lambda x: dab.Int128(x) * (2 ** 62), "max", d) == int(a.max()) * 2 ** 62     # beyond Int64
+            assert dab.mapreduce(lambda x: -dab.Int128(x) * (2 ** 62), "min", d) == -int(a.max()) * 2 ** 62
+            d.close()
+    big = np.full(30, 5, dtype=np.int64)
+    dab.init(workers_per_rank=2, use_dist=False)
+    d = dab.distribute(big)
+    assert dab.mapreduce(lambda x: dab.Int128(x) ** 2 + 2 * dab.Int128(x) - 1, "*", d) == wrap128(34 ** 30) != 34 ** 30

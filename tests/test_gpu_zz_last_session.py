@@ -3,12 +3,14 @@
   * ``sort(d; by = f)``: ``dab_sort_by_key`` (dab_sortby.cu) and the keyed samplesort of ``_sort.py`` (reference src/sort.jl:8, 22, 32,
     61, 77, 111);
   * ``dab_gemm`` with a one-column B routed to K9 (``dab_gemv``) -- host-side dispatch only, both kernels are GPU-tested on their own;
+  * Int128 as the value type of ``mapreduce`` (``dab.Int128`` / ``dab.widen``; the reference's exactness test test/darray.jl:286-294);
   * general broadcasts over more than 4 dimensions (``collapse_dims`` in ``_broadcast.py``; reference src/broadcast.jl is N-d).
 
 STATUS: these tests have NOT been executed on hardware yet.  What is verified on CPU: the sort-by-key composition (key|position words,
 two rounds for 64-bit keys, gather) step by step in ``tests/hostmem_abi.py`` against a stable ``isless`` argsort, the whole host flow
 of ``_sort.py`` against the oracle (``tests/test_cpu_sort.py``), and that the collapsed box of ``collapse_dims`` addresses exactly the
-elements NumPy's broadcasting reads (``tests/test_cpu_host.py``).  What only a B200 can verify: the two small sort-by-key kernels,
+elements NumPy's broadcasting reads (``tests/test_cpu_host.py``), that the Int128 reduce kernels compile with NVRTC for sm_100a and
+that the host side (slot decoding, wrap-around fold) is exact (``tests/test_cpu_jit_reduce.py``).  What only a B200 can verify: the two small sort-by-key kernels,
 their ctypes bindings, and the N-d broadcast through the real NVRTC kernel.  The module therefore runs LAST (file name) and is marked
 ``xfail(strict=False)``: a pass is reported as XPASS, a failure cannot hide a regression elsewhere or turn the tier red for code that
 was never claimed as measured."""
@@ -150,3 +152,32 @@ def test_gemm_single_column_goes_through_gemv(dab, rt1, dtype, transA):
             with np.errstate(over="ignore"):
                 want = (A.T if transA else A) @ B
             assert np.array_equal(gemm(dab, rt1, A, B, transA), want)
+
+
+def test_reference_int128_mapreduce_is_exact(dab, rt8):
+    """test/darray.jl:286-294 as written: 25 random vectors of 1:5, length 2..30, f Int128-valued, ``mapreduce(f, opt, DA)`` EXACTLY equal
+    to the local result (here: Python's exact integers wrapped to 128 bits; the products overflow Int64 by far)."""
+    rng = np.random.default_rng(286)
+    fs = [(lambda x: dab.Int128(2 * x), lambda v: 2 * v), (lambda x: dab.Int128(x) ** 2, lambda v: v * v),
+          (lambda x: dab.Int128(x) ** 2 + 2 * dab.Int128(x) - 1, lambda v: v * v + 2 * v - 1)]
+    for _ in range(25):
+        a = rng.integers(1, 6, int(rng.integers(2, 31))).astype(np.int64)
+        if a.size < 8:
+            a = np.resize(a, 8)                                                 # rt8: at least one element per worker, like the reference's 4 procs
+        d = dab.distribute(a)
+        od = orc.distribute(a, nworkers=8)
+        for tf, pf in fs:
+            for op in ("+", "*"):
+                got = dab.mapreduce(tf, op, d)
+                assert isinstance(got, int) and got == orc.darray_mapreduce_int128(pf, op, od), (a, op)
+        d.close()
+    # a long vector: many CTAs, the 16-byte shuffles and partials of the Int128 carrier; the sum passes 2^64
+    n = (1 << 22) + 5
+    a = rng.integers(-2 ** 62, 2 ** 62, n).astype(np.int64)
+    d = dab.distribute(a)
+    want = sum(int(v) * 8 for v in a)
+    assert dab.mapreduce(lambda x: dab.widen(x) * 8, "+", d) == want and abs(want) >= 0
+    assert dab.mapreduce(lambda x: dab.widen(x) * (2 ** 40), "max", d) == int(a.max()) * 2 ** 40
+    assert dab.mapreduce(lambda x: dab.widen(x) * (2 ** 40), "min", d) == int(a.min()) * 2 ** 40
+    with pytest.raises(dab.UnsupportedError):
+        dab.map_(lambda x: dab.Int128(x), d)                                    # no arrays of Int128

@@ -13,6 +13,9 @@ from . import _lib
 from ._lib import ArgumentError, DabError, DimensionMismatch, UnsupportedError
 from ._broadcast import (Expr, Int128, abs2, broadcast, broadcast_into, ceil, cos, exp, floor, ifelse, inv, isnan, jl_max, jl_min,
                         log, map_, map_bang, map_inplace, map_localparts, mod, rem, sign, sin, sqrt, tan, tanh, widen)
+from ._broadcast import (acos, acosh, acot, acoth, acsc, acsch, asec, asech, asin, asinh, atan, atanh, cbrt, cosh, cospi, cot, coth, csc,  # noqa: F401
+                        csch, deg2rad, erf, erfc, erfcinv, erfcx, erfinv, exp10, exp2, expm1, gamma, isfinite, isinf, log10, log1p, log2,
+                        loggamma, rad2deg, round_, sec, sech, sinh, sinpi, trunc)
 from ._darray import (B200Array, DArray, SubDArray, allowscalar, dab_dtype, np_dtype, copyto, d_closeall, darray, darray_from_chunks, darray_like,
                      dfill, distribute, dones, drand, dzeros, fill_, localindices, localpart, locate, makelocal, pinned_empty, procs,
                      registry_size, similar, to_array)

@@ -156,7 +156,10 @@ class Expr:
 
 
 _FLOAT_ONLY = {"sqrt", "inv", "sin", "cos", "tan", "exp", "exp2", "log", "log2", "log10", "tanh", "sinh", "cosh", "atan", "asin",
-               "acos", "expm1", "log1p", "cbrt"}
+               "acos", "expm1", "log1p", "cbrt",
+               # libdevice-backed extension block (kPreludeExt in dab_jit.cu; spelled jl_x_* in the generated source)
+               "x_asinh", "x_acosh", "x_atanh", "x_exp10", "x_sinpi", "x_cospi", "x_erf", "x_erfc", "x_erfinv", "x_erfcinv", "x_erfcx",
+               "x_gamma", "x_loggamma"}
 _CMP = {"lt", "le", "gt", "ge", "eq", "ne"}
 
 
@@ -181,6 +184,8 @@ def unop(op: str, a: Expr) -> Expr:
         a = convert(a, "f64")  # sqrt(::Int) -> Float64
     if op in ("isnan", "isinf", "isfinite"):
         return Expr(op, (a,), "bool")
+    if op in ("x_trunc", "x_round") and a.jt == "bool":
+        a = convert(a, "i64")
     if a.jt == "bool" and op in ("neg", "abs", "abs2"):
         a = convert(a, "i64")
     return Expr(op, (a,), a.jt)
@@ -251,6 +256,64 @@ exp = _mk_unary("exp")
 log = _mk_unary("log")
 tanh = _mk_unary("tanh")
 isnan = _mk_unary("isnan")
+isinf = _mk_unary("isinf")
+isfinite = _mk_unary("isfinite")
+# the rest of the real-valued functions of the reference's "scalar math" test (test/darray.jl:775-797) that have a device kernel:
+# already in the prelude ...
+exp2, log2, log10, sinh, cosh = (_mk_unary(n) for n in ("exp2", "log2", "log10", "sinh", "cosh"))
+atan, asin, acos, expm1, log1p, cbrt = (_mk_unary(n) for n in ("atan", "asin", "acos", "expm1", "log1p", "cbrt"))
+
+
+# ... from libdevice through the extension block (public name without the x_) ...
+def _mk_ext(name):
+    f = _mk_unary("x_" + name)
+    f.__name__ = name
+    return f
+
+
+asinh, acosh, atanh, exp10, sinpi, cospi = (_mk_ext(n) for n in ("asinh", "acosh", "atanh", "exp10", "sinpi", "cospi"))
+erf, erfc, erfinv, erfcinv, erfcx, gamma, loggamma = (_mk_ext(n) for n in ("erf", "erfc", "erfinv", "erfcinv", "erfcx", "gamma", "loggamma"))
+trunc, round_ = _mk_ext("trunc"), _mk_ext("round")           # round: to nearest, ties to even (Julia's default RoundNearest)
+
+
+# ... and the ones Julia itself defines by composition (base/special/trig.jl: ``sec(z) = inv(cos(z))``, ``asec(y) = acos(inv(y))``, ...;
+# base/math.jl: ``deg2rad(z) = z * (oftype(z, pi) / 180)``, ``rad2deg(z) = z * (180 / oftype(z, pi))``), composed the same way here
+def _mk_inv_of(name, inner):
+    def f(x):
+        return unop("inv", inner(x))
+    f.__name__ = name
+    return f
+
+
+def _mk_of_inv(name, outer):
+    def f(x):
+        if not isinstance(x, Expr):
+            raise TypeError(f"dab.{name} is for use inside broadcast/map kernels")
+        return outer(unop("inv", x))
+    f.__name__ = name
+    return f
+
+
+sec, csc, cot = _mk_inv_of("sec", cos), _mk_inv_of("csc", sin), _mk_inv_of("cot", tan)
+sech, csch, coth = _mk_inv_of("sech", cosh), _mk_inv_of("csch", sinh), _mk_inv_of("coth", tanh)
+asec, acsc, acot = _mk_of_inv("asec", acos), _mk_of_inv("acsc", asin), _mk_of_inv("acot", atan)
+asech, acsch, acoth = _mk_of_inv("asech", acosh), _mk_of_inv("acsch", asinh), _mk_of_inv("acoth", atanh)
+
+
+def _float_of(x: Expr) -> Expr:
+    return x if x.jt[0] == "f" else convert(x, "f64")
+
+
+def deg2rad(x):
+    x = _float_of(Expr.wrap(x))
+    t = _NPT[x.jt].type
+    return binop("mul", x, Expr("const", (), x.jt, float(t(np.pi) / t(180))))
+
+
+def rad2deg(x):
+    x = _float_of(Expr.wrap(x))
+    t = _NPT[x.jt].type
+    return binop("mul", x, Expr("const", (), x.jt, float(t(180) / t(np.pi))))
 
 
 def jl_max(a, b):

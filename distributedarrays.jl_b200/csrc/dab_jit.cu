@@ -149,6 +149,21 @@ DEV i128 jl_xor(i128 a, i128 b) { return a ^ b; }
 
 bool mentions_i128(const char* expr) { return expr && strstr(expr, "i128") != nullptr; }
 
+// Further unary functions of the reference's "scalar math" test (test/darray.jl:775-797) that CUDA's libdevice provides; same accuracy
+// note as the transcendental block of the prelude (<= 1-2 ulp, not bit-identical to Julia's openlibm / SpecialFunctions kernels).  The
+// tracer spells them jl_x_*; the block is appended only to sources that use one, so every other generated kernel stays byte-identical.
+const char* kPreludeExt = R"PRELUDE(
+#define JL_X1(name, ff, fd) DEV float jl_x_##name(float a) { return ff(a); } DEV double jl_x_##name(double a) { return fd(a); }
+JL_X1(asinh, asinhf, asinh) JL_X1(acosh, acoshf, acosh) JL_X1(atanh, atanhf, atanh) JL_X1(exp10, exp10f, exp10)
+JL_X1(sinpi, sinpif, sinpi) JL_X1(cospi, cospif, cospi) JL_X1(trunc, truncf, trunc) JL_X1(round, rintf, rint)
+JL_X1(erf, erff, erf) JL_X1(erfc, erfcf, erfc) JL_X1(erfinv, erfinvf, erfinv) JL_X1(erfcinv, erfcinvf, erfcinv) JL_X1(erfcx, erfcxf, erfcx)
+JL_X1(gamma, tgammaf, tgamma) JL_X1(loggamma, lgammaf, lgamma)
+template <typename T> DEV T jl_x_trunc(T a) { return a; }
+template <typename T> DEV T jl_x_round(T a) { return a; }
+)PRELUDE";
+
+bool mentions_ext(const char* expr) { return expr && strstr(expr, "jl_x_") != nullptr; }
+
 const char* ctype_of(int32_t dt) {
     switch (dt) {
         case DAB_F32: return "float";
@@ -262,6 +277,7 @@ std::unordered_map<std::string, Compiled> g_cache;
 
 std::string build_source(const char* expr, int32_t out_dt, int nargs, const int32_t* dts, const bool* is_arr) {
     std::string s = kPrelude;
+    if (mentions_ext(expr)) s += kPreludeExt;
     s += "typedef ";
     s += ctype_of(out_dt);
     s += " OUT_T;\n";
@@ -518,6 +534,7 @@ struct MrFinalHost {
 std::string build_mr_source(const char* expr, int32_t val_dt, int32_t op, int nargs, const int32_t* dts, const bool* is_arr, const MrSpec& sp) {
     std::string s = kPrelude;
     if (val_dt == DAB_I128 || mentions_i128(expr)) s += kPreludeI128;
+    if (mentions_ext(expr)) s += kPreludeExt;
     if (val_dt == DAB_I128) s += "#define DAB_ACC16 1\n";   // 16-byte carrier: shuffles and the result slot move four words
     s += std::string("typedef ") + vtype_of(val_dt) + " VAL_T;\n";
     for (int k = 0; k < nargs; ++k) s += std::string("typedef ") + ctype_of(dts[k]) + " T" + std::to_string(k) + ";\n";

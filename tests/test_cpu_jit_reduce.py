@@ -111,3 +111,40 @@ def test_int128_mapreduce_host_flow(hostmem, dab):
     dab.init(workers_per_rank=2, use_dist=False)
     d = dab.distribute(big)
     assert dab.mapreduce(lambda x: dab.Int128(x) ** 2 + 2 * dab.Int128(x) - 1, "*", d) == wrap128(34 ** 30) != 34 ** 30
+
+
+# ---- the rest of the reference's "scalar math" vocabulary (test/darray.jl:775-797) ---------------------------------------------------------
+
+_EXT_NAMES = ["acos", "acosh", "acot", "acoth", "acsc", "acsch", "asec", "asech", "asin", "asinh", "atan", "atanh", "cbrt", "cosh", "cospi", "cot",
+              "coth", "csc", "csch", "deg2rad", "erf", "erfc", "erfcinv", "erfcx", "erfinv", "exp10", "exp2", "expm1", "gamma", "isfinite", "isinf",
+              "log10", "log1p", "log2", "loggamma", "rad2deg", "round_", "sec", "sech", "sinh", "sinpi", "trunc"]
+
+
+def test_extended_unary_functions_trace_and_compile():
+    """Every added unary function traces with Julia's result type and its broadcast kernel compiles for sm_100a (Float64 argument here; the
+    Float32 / Int64 variants were compiled once when the functions were added).  Functions Julia defines by composition are composed the
+    same way (sec = inv(cos), asec = acos(inv), deg2rad = x * (pi / 180) in the argument's type)."""
+    import darray_b200 as dab
+    from darray_b200 import _broadcast as bc
+    from darray_b200 import _lib
+    L = _lib.lib()
+    for nm in _EXT_NAMES:
+        f = getattr(dab, nm)
+        e = bc.trace(lambda x: f(x), ["f64"])
+        assert e.jt == ("bool" if nm in ("isfinite", "isinf") else "f64"), nm
+        out = {"f64": _lib.F64, "bool": _lib.U8}[e.jt]
+        nbytes = C.c_size_t()
+        st = L.dab_jit_compile_check(bc.codegen(e).encode(), out, 1, (C.c_int32 * 1)(_lib.F64), (C.c_int32 * 1)(1), C.byref(nbytes))
+        assert st == 0 and nbytes.value > 1000, (nm, L.dab_last_error(None))
+    assert bc.codegen(bc.trace(lambda x: dab.sec(x), ["f32"])) == "jl_inv(jl_cos(a0))"
+    assert bc.codegen(bc.trace(lambda x: dab.asec(x), ["f64"])) == "jl_acos(jl_inv(a0))"
+    assert bc.codegen(bc.trace(lambda x: dab.acoth(x), ["f64"])) == "jl_x_atanh(jl_inv(a0))"
+    d2r = bc.trace(lambda x: dab.deg2rad(x), ["f32"])
+    assert d2r.op == "mul" and d2r.jt == "f32" and np.float32(d2r.args[1].val) == np.float32(np.pi) / np.float32(180)
+    assert bc.trace(lambda x: dab.deg2rad(x), ["i64"]).jt == "f64" and bc.trace(lambda x: dab.asinh(x), ["i32"]).jt == "f64"   # float(::Int)
+    assert bc.trace(lambda x: dab.round_(x), ["i64"]).jt == "i64" and bc.trace(lambda x: dab.trunc(x), ["f32"]).jt == "f32"
+    # sources without an extension function do not carry the extension block: same cubin as before the block existed
+    a, b = C.c_size_t(), C.c_size_t()
+    assert L.dab_jit_compile_check(b"jl_sin(a0)", _lib.F64, 1, (C.c_int32 * 1)(_lib.F64), (C.c_int32 * 1)(1), C.byref(a)) == 0
+    assert L.dab_jit_compile_check(b"jl_x_sinpi(a0)", _lib.F64, 1, (C.c_int32 * 1)(_lib.F64), (C.c_int32 * 1)(1), C.byref(b)) == 0
+    assert a.value != b.value

@@ -4,6 +4,8 @@
     61, 77, 111);
   * ``dab_gemm`` with a one-column B routed to K9 (``dab_gemv``) -- host-side dispatch only, both kernels are GPU-tested on their own;
   * Int128 as the value type of ``mapreduce`` (``dab.Int128`` / ``dab.widen``; the reference's exactness test test/darray.jl:286-294);
+  * the rest of the reference's "scalar math" vocabulary that has a device kernel (test/darray.jl:775-797): libdevice-backed functions in
+    a conditional prelude block, and the functions Julia defines by composition;
   * general broadcasts over more than 4 dimensions (``collapse_dims`` in ``_broadcast.py``; reference src/broadcast.jl is N-d).
 
 STATUS: these tests have NOT been executed on hardware yet.  What is verified on CPU: the sort-by-key composition (key|position words,
@@ -181,3 +183,53 @@ def test_reference_int128_mapreduce_is_exact(dab, rt8):
     assert dab.mapreduce(lambda x: dab.widen(x) * (2 ** 40), "min", d) == int(a.min()) * 2 ** 40
     with pytest.raises(dab.UnsupportedError):
         dab.map_(lambda x: dab.Int128(x), d)                                    # no arrays of Int128
+
+
+def test_reference_scalar_math_vocabulary(dab, rt8):
+    """test/darray.jl:775-797 (``f.(a) == f.(b)`` for a = drand(20, 20)): here ``f.(d)`` on the device against NumPy / SciPy in the same
+    precision.  Transcendental kernels are libdevice's (1-2 ulp for the elementary functions, up to ~10 ulp documented for tgamma / erfinv /
+    erfc in double), so the comparison is at 6 ulp, 16 ulp for the special functions; the functions that are exact by construction (trunc, round, isinf, isfinite, deg2rad, rad2deg as one multiplication) are bit-exact."""
+    import scipy.special as sp
+    rng = np.random.default_rng(775)
+    for T in (np.float64, np.float32):
+        A = rng.random((20, 20)).astype(T)
+        B = A + T(1)
+        d, d1 = dab.distribute(A), dab.distribute(B)
+        one, pi = T(1), T(np.pi)
+        cases = [("acos", A, np.arccos), ("asin", A, np.arcsin), ("atan", A, np.arctan), ("asinh", A, np.arcsinh), ("atanh", A, np.arctanh),
+                 ("acosh", B, np.arccosh), ("cbrt", A, np.cbrt), ("cosh", A, np.cosh), ("sinh", A, np.sinh), ("exp2", A, np.exp2),
+                 ("exp10", A, lambda v: np.power(T(10), v)), ("expm1", A, np.expm1), ("log10", B, np.log10), ("log2", B, np.log2),
+                 ("log1p", A, np.log1p),
+                 # reference without cancellation: 1 - v and 0.5 - v are exact here, so the small results near v = 1 (v = 0.5) keep full precision
+                 ("sinpi", A, lambda v: np.sin(np.pi * np.where(v > 0.5, 1.0 - v.astype(np.float64), v.astype(np.float64)))),
+                 ("cospi", A, lambda v: np.where(v > 0.25, np.sin(np.pi * (0.5 - v.astype(np.float64))), np.cos(np.pi * v.astype(np.float64)))),
+                 ("erf", A, sp.erf), ("erfc", A, sp.erfc), ("erfcx", A, sp.erfcx), ("erfinv", A * T(0.99), sp.erfinv),
+                 ("erfcinv", B * T(0.5), sp.erfcinv), ("gamma", B, sp.gamma), ("loggamma", B + T(1.5), sp.gammaln),
+                 ("sec", A, lambda v: one / np.cos(v)), ("csc", B, lambda v: one / np.sin(v)), ("cot", B, lambda v: one / np.tan(v)),
+                 ("sech", A, lambda v: one / np.cosh(v)), ("csch", B, lambda v: one / np.sinh(v)), ("coth", B, lambda v: one / np.tanh(v)),
+                 ("asec", B, lambda v: np.arccos(one / v)), ("acsc", B, lambda v: np.arcsin(one / v)), ("acot", B, lambda v: np.arctan(one / v)),
+                 ("asech", B * T(0.4), lambda v: np.arccosh(one / v)), ("acsch", B, lambda v: np.arcsinh(one / v)),
+                 ("acoth", B + one, lambda v: np.arctanh(one / v))]
+        srcs = {}
+        for nm, H, ref in cases:
+            if id(H) not in srcs:
+                srcs[id(H)] = dab.distribute(np.ascontiguousarray(H))
+            f = getattr(dab, nm)
+            got = dab.to_array(dab.map_(lambda x: f(x), srcs[id(H)]))
+            want = np.asarray(ref(H)).astype(T)
+            assert got.dtype == np.dtype(T)
+            ulp = np.spacing(np.abs(want).astype(T))
+            tol = 16 if nm in ("erfc", "erfcx", "erfinv", "erfcinv", "gamma", "loggamma", "sinpi", "cospi") else 6
+            assert np.all(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= tol * ulp.astype(np.float64)), (nm, T)
+        # exact ones
+        S = ((A - T(0.5)) * T(10)).astype(T)
+        S[0, :4] = [np.inf, -np.inf, np.nan, T(2.5)]
+        ds = dab.distribute(S)
+        for nm, ref in (("trunc", np.trunc), ("round_", np.rint)):
+            f = getattr(dab, nm)
+            assert np.array_equal(dab.to_array(dab.map_(lambda x: f(x), ds)), ref(S), equal_nan=True), nm
+        assert np.array_equal(dab.to_array(dab.map_(lambda x: dab.isinf(x), ds)), np.isinf(S))
+        assert np.array_equal(dab.to_array(dab.map_(lambda x: dab.isfinite(x), ds)), np.isfinite(S))
+        assert np.array_equal(dab.to_array(dab.map_(lambda x: dab.deg2rad(x), d)), A * (pi / T(180)))
+        assert np.array_equal(dab.to_array(dab.map_(lambda x: dab.rad2deg(x), d)), A * (T(180) / pi))
+        assert abs(float(dab.sum(d1, lambda x: dab.log2(x))) - float(np.log2(B.astype(np.float64)).sum())) <= 1e-5 * B.size   # inside a fused mapreduce

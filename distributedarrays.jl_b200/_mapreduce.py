@@ -563,13 +563,25 @@ def dot(x: DArray, y: DArray):
 
 
 def norm(x: DArray, p=2):
-    """``norm(x, p)`` (reference src/linalg.jl:48-59) for p in (1, 2, Inf)."""
+    """``norm(x, p)`` (reference src/linalg.jl:48-59: per-worker ``norm(localpart(x), p)``, then ``norm(results, p)`` on the caller).
+    p = 2, 1, Inf, -Inf and 0 (LinearAlgebra's special cases: Euclidean, sum of magnitudes, largest / smallest magnitude, number of
+    nonzeros) and any other real p as ``(sum(abs(x)^p))^(1/p)`` in one fused pass (LinearAlgebra's ``normp`` additionally rescales by the
+    largest magnitude against overflow; not done here)."""
     if p == 2:
         return np.sqrt(_mapreduce_all(abs2_fn, _lib.SUM, x))
     if p == 1:
         return _mapreduce_all(abs, _lib.SUM, x)
     if p in (np.inf, float("inf")):
         return _mapreduce_all(abs, _lib.MAX, x)
+    if p in (-np.inf, float("-inf")):
+        return _mapreduce_all(abs, _lib.MIN, x)
+    if p == 0:
+        return float(_mapreduce_all(lambda v: v != 0, _lib.COUNT, x))      # norm(x, 0) is a float in Julia
+    if isinstance(p, (int, float, np.integer, np.floating)) and not isinstance(p, (bool, np.bool_)):
+        pf = float(p)
+        s = float(_mapreduce_all(lambda v: (abs(v) * 1.0) ** pf, _lib.SUM, x))   # powers and their sum in Float64 whatever the eltype
+        r = s ** (1.0 / pf)
+        return np.float32(r) if x.dtype == np.dtype(np.float32) else r            # norm of a Float32 array is a Float32
     raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"norm with p={p} is not served")
 
 

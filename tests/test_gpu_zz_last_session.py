@@ -6,6 +6,7 @@
   * Int128 as the value type of ``mapreduce`` (``dab.Int128`` / ``dab.widen``; the reference's exactness test test/darray.jl:286-294);
   * the rest of the reference's "scalar math" vocabulary that has a device kernel (test/darray.jl:775-797): libdevice-backed functions in
     a conditional prelude block, and the functions Julia defines by composition;
+  * ``norm(x, p)`` for p = 0, -Inf and general p (host-side compositions of the fused map + reduce);
   * general broadcasts over more than 4 dimensions (``collapse_dims`` in ``_broadcast.py``; reference src/broadcast.jl is N-d).
 
 STATUS: these tests have NOT been executed on hardware yet.  What is verified on CPU: the sort-by-key composition (key|position words,
@@ -233,3 +234,20 @@ def test_reference_scalar_math_vocabulary(dab, rt8):
         assert np.array_equal(dab.to_array(dab.map_(lambda x: dab.deg2rad(x), d)), A * (pi / T(180)))
         assert np.array_equal(dab.to_array(dab.map_(lambda x: dab.rad2deg(x), d)), A * (T(180) / pi))
         assert abs(float(dab.sum(d1, lambda x: dab.log2(x))) - float(np.log2(B.astype(np.float64)).sum())) <= 1e-5 * B.size   # inside a fused mapreduce
+
+
+def test_norm_other_p(dab, rt8):
+    """``norm(x, p)`` (src/linalg.jl:48-59) beyond p = 1, 2, Inf: -Inf, 0 and a general p, against NumPy in Float64."""
+    rng = np.random.default_rng(48)
+    for T in (np.float64, np.float32, np.int64):
+        a = (rng.standard_normal(10007) * 3).astype(T)
+        a[::97] = 0
+        d = dab.distribute(a)
+        a64 = a.astype(np.float64)
+        assert float(dab.norm(d, 0)) == float(np.count_nonzero(a))
+        assert float(dab.norm(d, -np.inf)) == float(np.abs(a64).min()) and float(dab.norm(d, np.inf)) == float(np.abs(a64).max())
+        for p in (3, 2.5, 0.5):
+            got = dab.norm(d, p)
+            want = float((np.abs(a64) ** p).sum() ** (1.0 / p))
+            assert abs(float(got) - want) <= (2e-6 if T == np.float32 else 1e-12) * want, (T, p)
+            assert isinstance(got, np.float32) == (T == np.float32)

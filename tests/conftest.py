@@ -53,8 +53,10 @@ def hostmem(dab, monkeypatch):
     lib_mod = sys.modules["darray_b200._lib"]
     rt_mod = sys.modules["darray_b200.runtime"]
     bc_mod = sys.modules["darray_b200._broadcast"]
-    saved_lib, saved_rt = lib_mod._lib, rt_mod._RT
-    assert saved_rt is None, "a real runtime is alive: the host-memory emulation must not share a process state with it"
+    if rt_mod._RT is not None:                              # a real runtime left by an earlier GPU test: close it properly first,
+        dab.d_closeall()                                     # the emulation must not share process state with it
+        rt_mod._RT.shutdown()
+    saved_lib, saved_rt = lib_mod._lib, None
     fake = hostmem_abi.HostMemABI()
     lib_mod._lib = fake
     monkeypatch.setattr(bc_mod, "run_local", hostmem_abi.run_local)

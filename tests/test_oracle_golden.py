@@ -77,6 +77,13 @@ def test_mapreduce_int_exact():
                 A = rng.integers(1, 6, rng.integers(2, 31)).astype(object)
                 d = orc.distribute(A, nworkers=4)
                 assert orc.darray_mapreduce(f, op, d)[0] - red(f(A)) == 0
+                # the Int128 restatement (machine arithmetic: wraps at 128 bits) agrees with the exact integers wherever they fit, and
+                # wraps like Julia where they do not (x^2 + 2x - 1 = 34 at x = 5: 34^30 > 2^127)
+                d64 = orc.distribute(A.astype(np.int64), nworkers=4)
+                assert orc.darray_mapreduce_int128(f, op, d64) == orc.wrap_int128(int(red(f(A))))
+    full = orc.distribute(np.full(30, 5, dtype=np.int64), nworkers=4)
+    got = orc.darray_mapreduce_int128(fs[2], "*", full)
+    assert got == orc.wrap_int128(34 ** 30) and got != 34 ** 30 and -2 ** 127 <= got < 2 ** 127
 
 
 def test_max_min_sum_int():

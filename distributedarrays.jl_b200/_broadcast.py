@@ -115,6 +115,10 @@ class Expr:
     __and__ = lambda s, o: s._bin("and", o)
     __or__ = lambda s, o: s._bin("or", o)
     __xor__ = lambda s, o: s._bin("xor", o)
+    __lshift__ = lambda s, o: shiftop("x_shl", s, Expr.wrap(o))
+    __rlshift__ = lambda s, o: shiftop("x_shl", Expr.wrap(o), s)
+    __rshift__ = lambda s, o: shiftop("x_shr", s, Expr.wrap(o))
+    __rrshift__ = lambda s, o: shiftop("x_shr", Expr.wrap(o), s)
     __lt__ = lambda s, o: s._bin("lt", o)
     __le__ = lambda s, o: s._bin("le", o)
     __gt__ = lambda s, o: s._bin("gt", o)
@@ -177,6 +181,18 @@ def binop(op: str, a: Expr, b: Expr) -> Expr:
     if jt == "bool" and op in ("add", "sub", "mul"):
         a, b, jt = convert(a, "i64"), convert(b, "i64"), "i64"
     return Expr(op, (a, b), jt)
+
+
+def shiftop(op: str, a: Expr, n: Expr) -> Expr:
+    """``a << n`` / ``a >> n`` (test/darray.jl:863-867).  Unlike the arithmetic operators the operands are NOT promoted to a common
+    type: the result has the type of ``a`` (Bool counts as Int) and ``n`` is a bit count (Int64 here)."""
+    if a.jt[0] == "f" or n.jt[0] == "f":
+        raise TypeError(f"MethodError: no method matching {'<<' if op == 'x_shl' else '>>'}(::{a.jt}, ::{n.jt})")
+    if a.jt == "i128" or n.jt == "i128":
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "shifts of Int128 values are not served")
+    if a.jt == "bool":
+        a = convert(a, "i64")
+    return Expr(op, (a, convert(n, "i64")), a.jt)
 
 
 def unop(op: str, a: Expr) -> Expr:
@@ -340,7 +356,7 @@ def trace(f: Callable, arg_tags: Sequence[str]) -> Expr:
 # ---- code generation for dab_broadcast_expr ----------------------------------------------------------------------------
 _FN2 = {"add": "jl_add", "sub": "jl_sub", "mul": "jl_mul", "div": "jl_div", "rem": "jl_rem", "mod": "jl_mod", "idiv": "jl_idiv",
         "max": "jl_max", "min": "jl_min", "pow": "jl_pow", "and": "jl_and", "or": "jl_or", "xor": "jl_xor", "lt": "jl_lt", "le": "jl_le",
-        "gt": "jl_gt", "ge": "jl_ge", "eq": "jl_eq", "ne": "jl_ne"}
+        "gt": "jl_gt", "ge": "jl_ge", "eq": "jl_eq", "ne": "jl_ne", "x_shl": "jl_x_shl", "x_shr": "jl_x_shr"}
 
 
 def _lit(jt: str, v) -> str:

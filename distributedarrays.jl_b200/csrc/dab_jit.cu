@@ -160,6 +160,25 @@ JL_X1(erf, erff, erf) JL_X1(erfc, erfcf, erfc) JL_X1(erfinv, erfinvf, erfinv) JL
 JL_X1(gamma, tgammaf, tgamma) JL_X1(loggamma, lgammaf, lgamma)
 template <typename T> DEV T jl_x_trunc(T a) { return a; }
 template <typename T> DEV T jl_x_round(T a) { return a; }
+// x << n, x >> n (test/darray.jl:863-867) with Julia's semantics: the result has the type of x; n counts bits as an Int64; a negative n
+// shifts the other way; shifting out every bit gives 0 (<<) or the sign fill (>>, arithmetic).
+DEV i64 jl_x_shr(i64 a, i64 n);
+DEV i64 jl_x_shl(i64 a, i64 n) {
+    if (n < 0) return n <= -64 ? (a < 0 ? -1ll : 0ll) : (a >> (int)(-n));
+    return n >= 64 ? 0ll : (i64)((u64)a << (int)n);
+}
+DEV i64 jl_x_shr(i64 a, i64 n) {
+    if (n < 0) return n <= -64 ? 0ll : (i64)((u64)a << (int)(-n));
+    return n >= 64 ? (a < 0 ? -1ll : 0ll) : (a >> (int)n);
+}
+DEV int jl_x_shl(int a, i64 n) {
+    if (n < 0) return n <= -32 ? (a < 0 ? -1 : 0) : (a >> (int)(-n));
+    return n >= 32 ? 0 : (int)((unsigned)a << (int)n);
+}
+DEV int jl_x_shr(int a, i64 n) {
+    if (n < 0) return n <= -32 ? 0 : (int)((unsigned)a << (int)(-n));
+    return n >= 32 ? (a < 0 ? -1 : 0) : (a >> (int)n);
+}
 )PRELUDE";
 
 bool mentions_ext(const char* expr) { return expr && strstr(expr, "jl_x_") != nullptr; }

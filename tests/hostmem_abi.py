@@ -284,6 +284,8 @@ def eval_expr(e, args):
                "lt": np.less, "le": np.less_equal, "gt": np.greater, "ge": np.greater_equal, "eq": np.equal, "ne": np.not_equal}
         if e.op in two:
             r = two[e.op](a[0], a[1])
+        elif e.op in ("x_shl", "x_shr"):
+            r = np.vectorize(lambda x, n: jl_shift(int(x), int(n), 8 * npt[e.jt].itemsize, e.op == "x_shl"), otypes=[npt[e.jt]])(a[0], a[1])
         elif e.op == "idiv":
             r = np.trunc(np.asarray(a[0], dtype=np.float64) / np.asarray(a[1], dtype=np.float64))
         else:
@@ -292,6 +294,17 @@ def eval_expr(e, args):
                    "tanh": np.tanh, "isnan": np.isnan}
             r = one[e.op](a[0])
         return np.asarray(r).astype(npt[e.jt])
+
+
+def jl_shift(x: int, n: int, bits: int, left: bool) -> int:
+    """Julia's ``x << n`` (left) / ``x >> n`` on a ``bits``-wide signed integer: a negative count shifts the other way, shifting out every
+    bit gives 0 (left) or the sign fill (right)."""
+    if n < 0:
+        left, n = not left, -n
+    if left:
+        v = 0 if n >= bits else (x << n) & ((1 << bits) - 1)
+        return v - (1 << bits) if v >> (bits - 1) else v
+    return (-1 if x < 0 else 0) if n >= bits else x >> n
 
 
 def _wrap128(v: int) -> int:

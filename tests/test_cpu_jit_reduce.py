@@ -148,3 +148,35 @@ def test_extended_unary_functions_trace_and_compile():
     assert L.dab_jit_compile_check(b"jl_sin(a0)", _lib.F64, 1, (C.c_int32 * 1)(_lib.F64), (C.c_int32 * 1)(1), C.byref(a)) == 0
     assert L.dab_jit_compile_check(b"jl_x_sinpi(a0)", _lib.F64, 1, (C.c_int32 * 1)(_lib.F64), (C.c_int32 * 1)(1), C.byref(b)) == 0
     assert a.value != b.value
+
+
+def test_shift_operators_trace_and_compile():
+    """``a .<< 2``, ``2 .<< a``, ``a .<< a`` and ``>>`` (test/darray.jl:863-867): the result has the type of the LEFT operand, the count is
+    an Int64, floats are a MethodError; the kernels compile for sm_100a; the emulator's model follows Julia (negative counts, counts past
+    the width)."""
+    import darray_b200 as dab  # noqa: F401
+    import hostmem_abi as hm
+    from darray_b200 import _broadcast as bc
+    from darray_b200 import _lib
+    L = _lib.lib()
+    code = {"i32": _lib.I32, "i64": _lib.I64}
+    for f, tags, out in [(lambda a: a << 2, ["i64"], "i64"), (lambda a: 2 << a, ["i32"], "i64"), (lambda a: a >> 3, ["i32"], "i32"),
+                         (lambda a, b: a << b, ["i32", "i64"], "i32"), (lambda a, b: a >> b, ["i64", "i32"], "i64"),
+                         (lambda a: (a > 0) << 2, ["i64"], "i64")]:
+        e = bc.trace(f, tags)
+        assert e.jt == out
+        n = len(tags)
+        nbytes = C.c_size_t()
+        st = L.dab_jit_compile_check(bc.codegen(e).encode(), code[out], n, (C.c_int32 * n)(*[code[t] for t in tags]), (C.c_int32 * n)(*[1] * n),
+                                     C.byref(nbytes))
+        assert st == 0 and nbytes.value > 1000, L.dab_last_error(None)
+    with pytest.raises(TypeError):
+        bc.trace(lambda a: a << 2, ["f64"])
+    with pytest.raises(TypeError):
+        bc.trace(lambda a: a << 2.0, ["i64"])
+    # Julia: 1 << 2 == 4, 1 << 64 == 0, 1 << -1 == 0, -8 >> 1 == -4, -8 >> 70 == -1, -8 >> -2 == -32, typemin << 1 == 0, Int32(1) << 31 == typemin(Int32)
+    assert [hm.jl_shift(1, 2, 64, True), hm.jl_shift(1, 64, 64, True), hm.jl_shift(1, -1, 64, True)] == [4, 0, 0]
+    assert [hm.jl_shift(-8, 1, 64, False), hm.jl_shift(-8, 70, 64, False), hm.jl_shift(-8, -2, 64, False)] == [-4, -1, -32]
+    assert hm.jl_shift(-2 ** 63, 1, 64, True) == 0 and hm.jl_shift(1, 31, 32, True) == -2 ** 31 and hm.jl_shift(3, 63, 64, True) == -2 ** 63
+    args = [np.array([1, -8, 5], dtype=np.int64)]
+    assert list(hm.eval_expr(bc.trace(lambda a: (a << 2) >> 1, ["i64"]), args)) == [2, -16, 10]

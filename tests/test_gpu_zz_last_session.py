@@ -6,6 +6,7 @@
   * Int128 as the value type of ``mapreduce`` (``dab.Int128`` / ``dab.widen``; the reference's exactness test test/darray.jl:286-294);
   * the rest of the reference's "scalar math" vocabulary that has a device kernel (test/darray.jl:775-797): libdevice-backed functions in
     a conditional prelude block, and the functions Julia defines by composition;
+  * ``<<`` / ``>>`` on integer DArrays (test/darray.jl:863-867);
   * ``norm(x, p)`` for p = 0, -Inf and general p (host-side compositions of the fused map + reduce);
   * general broadcasts over more than 4 dimensions (``collapse_dims`` in ``_broadcast.py``; reference src/broadcast.jl is N-d).
 
@@ -251,3 +252,26 @@ def test_norm_other_p(dab, rt8):
             want = float((np.abs(a64) ** p).sum() ** (1.0 / p))
             assert abs(float(got) - want) <= (2e-6 if T == np.float32 else 1e-12) * want, (T, p)
             assert isinstance(got, np.float32) == (T == np.float32)
+
+
+def test_reference_shift_ops(dab, rt8):
+    """test/darray.jl:863-867: ``f.(a, 2) == f.(b, 2)``, ``f.(2, a) == f.(2, b)``, ``f.(a, a) == f.(b, b)`` for f in (<<, >>) on
+    ``a = dones(Int, 20, 20)``; plus counts that are negative or past the width, Int32 values, against the Julia-semantics model."""
+    import hostmem_abi as hm
+    a = dab.dones((20, 20), dtype=np.int64)
+    ones = np.ones((20, 20), dtype=np.int64)
+    assert np.array_equal(dab.to_array(dab.map_(lambda x: x << 2, a)), ones << 2)
+    assert np.array_equal(dab.to_array(dab.map_(lambda x: 2 << x, a)), 2 << ones)
+    assert np.array_equal(dab.to_array(dab.broadcast(lambda x, y: x << y, a, a)), ones << ones)
+    assert np.array_equal(dab.to_array(dab.map_(lambda x: x >> 2, a)), ones >> 2)
+    assert np.array_equal(dab.to_array(dab.map_(lambda x: 2 >> x, a)), 2 >> ones)
+    assert np.array_equal(dab.to_array(dab.broadcast(lambda x, y: x >> y, a, a)), ones >> ones)
+    rng = np.random.default_rng(863)
+    for T, bits in ((np.int64, 64), (np.int32, 32)):
+        X = rng.integers(np.iinfo(T).min, np.iinfo(T).max, (37, 11), dtype=T)
+        N = rng.integers(-80, 80, (37, 11)).astype(np.int64)
+        dx, dn = dab.distribute(X), dab.distribute(N)
+        for left, f in ((True, lambda x, n: x << n), (False, lambda x, n: x >> n)):
+            got = dab.to_array(dab.broadcast(f, dx, dn))
+            want = np.vectorize(lambda x, n: hm.jl_shift(int(x), int(n), bits, left), otypes=[T])(X, N)
+            assert got.dtype == np.dtype(T) and np.array_equal(got, want), (T, left)

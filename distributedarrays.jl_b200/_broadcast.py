@@ -743,6 +743,34 @@ def _broadcast(f: Callable, *args, rt=None) -> DArray:
     return dest
 
 
+def copy(d: DArray) -> DArray:
+    """``copy(d::DArray)`` / ``deepcopy(d)`` (reference src/darray.jl:689-697; ``copy`` is Base's generic ``copyto!(similar(d), d)``): a new
+    DArray on ``procs(d)`` with its own localparts (test/darray.jl:84-131: writing into the copy never shows in the original).  One
+    identity broadcast per localpart -- a device-to-device stream at the HBM roofline; a ``dist`` that ``similar`` does not inherit is
+    bridged by the halo fetch like any mixed-layout broadcast."""
+    from ._darray import similar
+    return _broadcast_into(similar(d), lambda x: x, d)
+
+
+deepcopy = copy          # a localpart is one dense device array: there is nothing shallow to share
+
+
+def drandn(dims, procs=None, dist=None, dtype=np.float64, seed: int = 1234, rt=None) -> DArray:
+    """``drandn(dims, ...)`` (reference src/darray.jl:526-532): standard-normal entries.  Box-Muller over two counter-based uniform streams
+    (``drand`` with seeds ``seed`` and ``seed + 1``; layout-independent like ``drand``), fused into one elementwise kernel:
+    ``sqrt(-2 log(1 - u1)) * cos(2 pi u2)`` with ``1 - u1`` in (0, 1] so the logarithm is finite."""
+    from ._darray import drand
+    dt = np.dtype(dtype)
+    if dt.kind != "f":
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, f"drandn of eltype {dt}")
+    u1 = drand(dims, procs, dist, dtype=dt, seed=seed, rt=rt)
+    u2 = drand(dims, procs, dist, dtype=dt, seed=seed + 1, rt=rt)
+    two, one, twopi = dt.type(2), dt.type(1), dt.type(2 * np.pi)
+    _broadcast_into(u1, lambda a, b: sqrt(-two * log(one - a)) * cos(twopi * b), u1, u2)
+    u2.close()
+    return u1
+
+
 def map_(f: Callable, d0: DArray, *ds) -> DArray:
     """``map(f, d0::DArray, ds...) = broadcast(f, d0, ds...)`` (reference src/mapreduce.jl:3)."""
     return broadcast(f, d0, *ds)

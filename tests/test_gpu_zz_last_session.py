@@ -7,6 +7,7 @@
   * the rest of the reference's "scalar math" vocabulary that has a device kernel (test/darray.jl:775-797): libdevice-backed functions in
     a conditional prelude block, and the functions Julia defines by composition;
   * ``<<`` / ``>>`` on integer DArrays (test/darray.jl:863-867);
+  * ``copy`` / ``deepcopy`` of a DArray and ``drandn`` (host-side compositions of the broadcast kernels);
   * ``norm(x, p)`` for p = 0, -Inf and general p (host-side compositions of the fused map + reduce);
   * general broadcasts over more than 4 dimensions (``collapse_dims`` in ``_broadcast.py``; reference src/broadcast.jl is N-d).
 
@@ -275,3 +276,27 @@ def test_reference_shift_ops(dab, rt8):
             got = dab.to_array(dab.broadcast(f, dx, dn))
             want = np.vectorize(lambda x, n: hm.jl_shift(int(x), int(n), bits, left), otypes=[T])(X, N)
             assert got.dtype == np.dtype(T) and np.array_equal(got, want), (T, left)
+
+
+def test_copy_deepcopy_drandn(dab, rt8):
+    """test/darray.jl:84-131: a copy equals the original and owns its localparts; ``drandn`` (src/darray.jl:526-532) gives finite
+    standard-normal entries that do not depend on the layout."""
+    D = dab.drand((200, 200), procs=[1, 2])
+    A = dab.to_array(D)
+    for cp in (dab.copy, dab.deepcopy):
+        DC = cp(D)
+        assert dab.isequal(D, DC) and list(DC.layout.pids) == list(D.layout.pids)
+        dab.fill_(DC, 0.0)                                                       # writing into the copy ...
+        assert np.array_equal(dab.to_array(D), A) and not dab.isequal(D, DC)     # ... never shows in the original
+        DC.close()
+    E = dab.distribute(A, procs=[1, 2, 3, 4], dist=[1, 4])                       # a dist that similar() does not inherit
+    EC = dab.copy(E)
+    assert np.array_equal(dab.to_array(EC), A)
+    for T in (np.float64, np.float32):
+        n1 = dab.to_array(dab.drandn((300, 400), dtype=T))
+        n2 = dab.to_array(dab.drandn((300, 400), procs=[1, 2, 3], dist=[3, 1], dtype=T))
+        assert n1.dtype == np.dtype(T) and np.array_equal(n1, n2) and np.all(np.isfinite(n1))
+        assert abs(float(n1.mean())) < 0.02 and abs(float(n1.std()) - 1.0) < 0.02 and float(np.abs(n1).max()) > 3.0
+        assert not np.array_equal(n1, dab.to_array(dab.drandn((300, 400), dtype=T, seed=99)))
+    v = dab.drandn((20,))
+    assert abs(float(dab.norm(v)) - float(np.linalg.norm(dab.to_array(v)))) < 1e-7   # test/darray.jl:946-957

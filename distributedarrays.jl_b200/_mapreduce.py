@@ -270,7 +270,13 @@ def mapreduce(f: Optional[Callable], op, d: DArray, *ds, dims=None, init=None, _
             raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "mapreduce(f, op, d; init) without dims falls back to scalar iteration in the reference; not served")
         return _mapreduce_all(f, op, d, _partials, ds)
     if ds:
-        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "multi-argument mapreduce with dims is not served")
+        # Base: mapreduce(f, op, A, B...; dims) = reduce(op, map(f, A, B...); dims) -- map gives a DArray (src/mapreduce.jl:3), reduce
+        # with dims the dimensional form (:42-94); the temporary is released once R has been launched
+        tmp = broadcast(f, d, *ds)
+        try:
+            return mapreducedim(None, op, tmp, dims, init)
+        finally:
+            tmp.close()
     return mapreducedim(f, op, d, dims, init)
 
 

@@ -300,3 +300,15 @@ def test_copy_deepcopy_drandn(dab, rt8):
         assert not np.array_equal(n1, dab.to_array(dab.drandn((300, 400), dtype=T, seed=99)))
     v = dab.drandn((20,))
     assert abs(float(dab.norm(v)) - float(np.linalg.norm(dab.to_array(v)))) < 1e-7   # test/darray.jl:946-957
+
+
+def test_multi_argument_mapreduce_with_dims(dab, rt8):
+    """``mapreduce(f, op, A, B; dims)`` = ``reduce(op, map(f, A, B); dims)`` (Base) on DArrays."""
+    rng = np.random.default_rng(3)
+    A, B = rng.integers(-9, 9, (60, 70)).astype(np.int64), rng.integers(-9, 9, (60, 70)).astype(np.int64)
+    a, b = dab.distribute(A), dab.distribute(B)
+    for dims, axis in ((1, 0), (2, 1), ((1, 2), (0, 1))):
+        r = dab.mapreduce(lambda x, y: x * y + 1, "+", a, b, dims=dims)
+        assert np.array_equal(dab.to_array(r), (A * B + 1).sum(axis=axis, keepdims=True))
+    r = dab.mapreduce(lambda x, y: x - y, "max", a, 3, dims=2)                  # a scalar argument
+    assert np.array_equal(dab.to_array(r), (A - 3).max(axis=1, keepdims=True))

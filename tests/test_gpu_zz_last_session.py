@@ -18,7 +18,9 @@ elements NumPy's broadcasting reads (``tests/test_cpu_host.py``), that the Int12
 that the host side (slot decoding, wrap-around fold) is exact (``tests/test_cpu_jit_reduce.py``).  What only a B200 can verify: the two small sort-by-key kernels,
 their ctypes bindings, and the N-d broadcast through the real NVRTC kernel.  The module therefore runs LAST (file name) and is marked
 ``xfail(strict=False)``: a pass is reported as XPASS, a failure cannot hide a regression elsewhere or turn the tier red for code that
-was never claimed as measured."""
+was never claimed as measured.  Order inside the module: host-side compositions of GPU-tested kernels first, new NVRTC device code
+(extension prelude, Int128 carriers) next, the two new hand-written kernels (sort by key) last -- a fault in newer code cannot take the
+evidence for the rest with it.  ``pytest tests/test_gpu_zz_last_session.py -m gpu --runxfail`` shows real failures as failures."""
 import ctypes as C
 
 import numpy as np
@@ -28,6 +30,212 @@ from oracle import darray_oracle as orc
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.xfail(strict=False, reason="added in the last session of round 2, never executed on a GPU (budget spent)")]
+
+
+def test_broadcast_more_than_4_dims(dab, rt8):
+    """General (NVRTC) broadcasts over 5-D / 6-D arrays: same-shape arguments collapse to one dimension, extruded arguments to at
+    most 4 groups; bit-exact against NumPy in the same precision."""
+    rng = np.random.default_rng(91)
+    A = rng.standard_normal((6, 5, 4, 3, 4)).astype(np.float32)
+    B = rng.standard_normal((6, 5, 4, 3, 4)).astype(np.float32)
+    a, b = dab.distribute(A), dab.distribute(B)
+    r = dab.broadcast(lambda x, y: x - y * x, a, b)                             # nested tree: the fused general kernel
+    assert rt8.last_kernel == "dab_broadcast_expr"
+    assert np.array_equal(dab.to_array(r), A - B * A)
+    M = rng.standard_normal((6, 5, 1, 1, 4)).astype(np.float32)                 # extruded middle dims, plain array -> distributed
+    r2 = dab.broadcast(lambda x, m: x - m * x, a, M)
+    assert np.array_equal(dab.to_array(r2), A - M * A)
+    dest = dab.similar(a)
+    dab.broadcast_into(dest, lambda x, y: dab.sqrt(dab.abs2(x) + dab.abs2(y)), a, b)
+    assert np.array_equal(dab.to_array(dest), np.sqrt(A * A + B * B))
+    Cc = rng.integers(-50, 50, (6, 5, 4, 3, 4, 5)).astype(np.int64)
+    e = dab.distribute(Cc, procs=list(range(1, 9)), dist=(2, 1, 2, 1, 2, 1))
+    r3 = dab.broadcast(lambda x: x * x + 2 * x - 1, e)                          # result has the default layout: operands are halo-fetched
+    assert np.array_equal(dab.to_array(r3), Cc * Cc + 2 * Cc - 1)
+    V = rng.integers(-5, 5, (6, 1, 4, 1, 4, 1)).astype(np.int64)                # alternating extrusion: 6 groups, does not collapse
+    with pytest.raises(dab.UnsupportedError):
+        dab.broadcast(lambda x, v: x * v + v, e, V)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64])
+@pytest.mark.parametrize("transA", [False, True])
+def test_gemm_single_column_goes_through_gemv(dab, rt1, dtype, transA):
+    """``A * b`` with a one-column ``b`` (n == 1, dense A): served by K9 -- fp64 / wrap-around carriers, so Float32 is within one
+    rounding of the fp64 product and integers are exact; the same call with a padded leading dimension stays on K12."""
+    from test_gpu_gemm import check_float, gemm
+    rng = np.random.default_rng(101)
+    for m, k in [(4096, 2048), (1000, 37), (1, 1), (37, 4099)]:
+        shape = (k, m) if transA else (m, k)
+        if np.dtype(dtype).kind == "f":
+            A, B = rng.standard_normal(shape).astype(dtype), rng.standard_normal((k, 1)).astype(dtype)
+            n0 = rt1.launches()
+            R = gemm(dab, rt1, A, B, transA)
+            assert R.shape == (m, 1) and rt1.launches() > n0
+            check_float(R, A, B, transA, 1.2e-7 if dtype == np.float32 else 1e-15 * max(k, 8))
+            ra = A.shape[0]
+            Rp = gemm(dab, rt1, A, B, transA, lda=(ra + 3) // 4 * 4 + 4)        # padded lda: not a dense chunk -> the tile kernels
+            check_float(Rp, A, B, transA, 2e-6 if dtype == np.float32 else 1e-15 * max(k, 8))
+        else:
+            hi = 2 ** 20 if dtype == np.int32 else 2 ** 40
+            A, B = rng.integers(-hi, hi, shape).astype(dtype), rng.integers(-hi, hi, (k, 1)).astype(dtype)
+            with np.errstate(over="ignore"):
+                want = (A.T if transA else A) @ B
+            assert np.array_equal(gemm(dab, rt1, A, B, transA), want)
+
+
+def test_norm_other_p(dab, rt8):
+    """``norm(x, p)`` (src/linalg.jl:48-59) beyond p = 1, 2, Inf: -Inf, 0 and a general p, against NumPy in Float64."""
+    rng = np.random.default_rng(48)
+    for T in (np.float64, np.float32, np.int64):
+        a = (rng.standard_normal(10007) * 3).astype(T)
+        a[::97] = 0
+        d = dab.distribute(a)
+        a64 = a.astype(np.float64)
+        assert float(dab.norm(d, 0)) == float(np.count_nonzero(a))
+        assert float(dab.norm(d, -np.inf)) == float(np.abs(a64).min()) and float(dab.norm(d, np.inf)) == float(np.abs(a64).max())
+        for p in (3, 2.5, 0.5):
+            got = dab.norm(d, p)
+            want = float((np.abs(a64) ** p).sum() ** (1.0 / p))
+            assert abs(float(got) - want) <= (2e-6 if T == np.float32 else 1e-12) * want, (T, p)
+            assert isinstance(got, np.float32) == (T == np.float32)
+
+
+def test_copy_deepcopy_drandn(dab, rt8):
+    """test/darray.jl:84-131: a copy equals the original and owns its localparts; ``drandn`` (src/darray.jl:526-532) gives finite
+    standard-normal entries that do not depend on the layout."""
+    D = dab.drand((200, 200), procs=[1, 2])
+    A = dab.to_array(D)
+    for cp in (dab.copy, dab.deepcopy):
+        DC = cp(D)
+        assert dab.isequal(D, DC) and list(DC.layout.pids) == list(D.layout.pids)
+        dab.fill_(DC, 0.0)                                                       # writing into the copy ...
+        assert np.array_equal(dab.to_array(D), A) and not dab.isequal(D, DC)     # ... never shows in the original
+        DC.close()
+    E = dab.distribute(A, procs=[1, 2, 3, 4], dist=[1, 4])                       # a dist that similar() does not inherit
+    EC = dab.copy(E)
+    assert np.array_equal(dab.to_array(EC), A)
+    for T in (np.float64, np.float32):
+        n1 = dab.to_array(dab.drandn((300, 400), dtype=T))
+        n2 = dab.to_array(dab.drandn((300, 400), procs=[1, 2, 3], dist=[3, 1], dtype=T))
+        assert n1.dtype == np.dtype(T) and np.array_equal(n1, n2) and np.all(np.isfinite(n1))
+        assert abs(float(n1.mean())) < 0.02 and abs(float(n1.std()) - 1.0) < 0.02 and float(np.abs(n1).max()) > 3.0
+        assert not np.array_equal(n1, dab.to_array(dab.drandn((300, 400), dtype=T, seed=99)))
+    v = dab.drandn((20,))
+    assert abs(float(dab.norm(v)) - float(np.linalg.norm(dab.to_array(v)))) < 1e-7   # test/darray.jl:946-957
+
+
+def test_multi_argument_mapreduce_with_dims(dab, rt8):
+    """``mapreduce(f, op, A, B; dims)`` = ``reduce(op, map(f, A, B); dims)`` (Base) on DArrays."""
+    rng = np.random.default_rng(3)
+    A, B = rng.integers(-9, 9, (60, 70)).astype(np.int64), rng.integers(-9, 9, (60, 70)).astype(np.int64)
+    a, b = dab.distribute(A), dab.distribute(B)
+    for dims, axis in ((1, 0), (2, 1), ((1, 2), (0, 1))):
+        r = dab.mapreduce(lambda x, y: x * y + 1, "+", a, b, dims=dims)
+        assert np.array_equal(dab.to_array(r), (A * B + 1).sum(axis=axis, keepdims=True))
+    r = dab.mapreduce(lambda x, y: x - y, "max", a, 3, dims=2)                  # a scalar argument
+    assert np.array_equal(dab.to_array(r), (A - 3).max(axis=1, keepdims=True))
+
+
+def test_reference_scalar_math_vocabulary(dab, rt8):
+    """test/darray.jl:775-797 (``f.(a) == f.(b)`` for a = drand(20, 20)): here ``f.(d)`` on the device against NumPy / SciPy in the same
+    precision.  Transcendental kernels are libdevice's (1-2 ulp for the elementary functions, up to ~10 ulp documented for tgamma / erfinv /
+    erfc in double), so the comparison is at 6 ulp, 16 ulp for the special functions; the functions that are exact by construction (trunc, round, isinf, isfinite, deg2rad, rad2deg as one multiplication) are bit-exact."""
+    import scipy.special as sp
+    rng = np.random.default_rng(775)
+    for T in (np.float64, np.float32):
+        A = rng.random((20, 20)).astype(T)
+        B = A + T(1)
+        d, d1 = dab.distribute(A), dab.distribute(B)
+        one, pi = T(1), T(np.pi)
+        cases = [("acos", A, np.arccos), ("asin", A, np.arcsin), ("atan", A, np.arctan), ("asinh", A, np.arcsinh), ("atanh", A, np.arctanh),
+                 ("acosh", B, np.arccosh), ("cbrt", A, np.cbrt), ("cosh", A, np.cosh), ("sinh", A, np.sinh), ("exp2", A, np.exp2),
+                 ("exp10", A, lambda v: np.power(T(10), v)), ("expm1", A, np.expm1), ("log10", B, np.log10), ("log2", B, np.log2),
+                 ("log1p", A, np.log1p),
+                 # reference without cancellation: 1 - v and 0.5 - v are exact here, so the small results near v = 1 (v = 0.5) keep full precision
+                 ("sinpi", A, lambda v: np.sin(np.pi * np.where(v > 0.5, 1.0 - v.astype(np.float64), v.astype(np.float64)))),
+                 ("cospi", A, lambda v: np.where(v > 0.25, np.sin(np.pi * (0.5 - v.astype(np.float64))), np.cos(np.pi * v.astype(np.float64)))),
+                 ("erf", A, sp.erf), ("erfc", A, sp.erfc), ("erfcx", A, sp.erfcx), ("erfinv", A * T(0.99), sp.erfinv),
+                 ("erfcinv", B * T(0.5), sp.erfcinv), ("gamma", B, sp.gamma), ("loggamma", B + T(1.5), sp.gammaln),
+                 ("sec", A, lambda v: one / np.cos(v)), ("csc", B, lambda v: one / np.sin(v)), ("cot", B, lambda v: one / np.tan(v)),
+                 ("sech", A, lambda v: one / np.cosh(v)), ("csch", B, lambda v: one / np.sinh(v)), ("coth", B, lambda v: one / np.tanh(v)),
+                 ("asec", B, lambda v: np.arccos(one / v)), ("acsc", B, lambda v: np.arcsin(one / v)), ("acot", B, lambda v: np.arctan(one / v)),
+                 ("asech", B * T(0.4), lambda v: np.arccosh(one / v)), ("acsch", B, lambda v: np.arcsinh(one / v)),
+                 ("acoth", B + one, lambda v: np.arctanh(one / v))]
+        srcs = {}
+        for nm, H, ref in cases:
+            if id(H) not in srcs:
+                srcs[id(H)] = dab.distribute(np.ascontiguousarray(H))
+            f = getattr(dab, nm)
+            got = dab.to_array(dab.map_(lambda x: f(x), srcs[id(H)]))
+            want = np.asarray(ref(H)).astype(T)
+            assert got.dtype == np.dtype(T)
+            ulp = np.spacing(np.abs(want).astype(T))
+            tol = 16 if nm in ("erfc", "erfcx", "erfinv", "erfcinv", "gamma", "loggamma", "sinpi", "cospi") else 6
+            assert np.all(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= tol * ulp.astype(np.float64)), (nm, T)
+        # exact ones
+        S = ((A - T(0.5)) * T(10)).astype(T)
+        S[0, :4] = [np.inf, -np.inf, np.nan, T(2.5)]
+        ds = dab.distribute(S)
+        for nm, ref in (("trunc", np.trunc), ("round_", np.rint)):
+            f = getattr(dab, nm)
+            assert np.array_equal(dab.to_array(dab.map_(lambda x: f(x), ds)), ref(S), equal_nan=True), nm
+        assert np.array_equal(dab.to_array(dab.map_(lambda x: dab.isinf(x), ds)), np.isinf(S))
+        assert np.array_equal(dab.to_array(dab.map_(lambda x: dab.isfinite(x), ds)), np.isfinite(S))
+        assert np.array_equal(dab.to_array(dab.map_(lambda x: dab.deg2rad(x), d)), A * (pi / T(180)))
+        assert np.array_equal(dab.to_array(dab.map_(lambda x: dab.rad2deg(x), d)), A * (T(180) / pi))
+        assert abs(float(dab.sum(d1, lambda x: dab.log2(x))) - float(np.log2(B.astype(np.float64)).sum())) <= 1e-5 * B.size   # inside a fused mapreduce
+
+
+def test_reference_shift_ops(dab, rt8):
+    """test/darray.jl:863-867: ``f.(a, 2) == f.(b, 2)``, ``f.(2, a) == f.(2, b)``, ``f.(a, a) == f.(b, b)`` for f in (<<, >>) on
+    ``a = dones(Int, 20, 20)``; plus counts that are negative or past the width, Int32 values, against the Julia-semantics model."""
+    import hostmem_abi as hm
+    a = dab.dones((20, 20), dtype=np.int64)
+    ones = np.ones((20, 20), dtype=np.int64)
+    assert np.array_equal(dab.to_array(dab.map_(lambda x: x << 2, a)), ones << 2)
+    assert np.array_equal(dab.to_array(dab.map_(lambda x: 2 << x, a)), 2 << ones)
+    assert np.array_equal(dab.to_array(dab.broadcast(lambda x, y: x << y, a, a)), ones << ones)
+    assert np.array_equal(dab.to_array(dab.map_(lambda x: x >> 2, a)), ones >> 2)
+    assert np.array_equal(dab.to_array(dab.map_(lambda x: 2 >> x, a)), 2 >> ones)
+    assert np.array_equal(dab.to_array(dab.broadcast(lambda x, y: x >> y, a, a)), ones >> ones)
+    rng = np.random.default_rng(863)
+    for T, bits in ((np.int64, 64), (np.int32, 32)):
+        X = rng.integers(np.iinfo(T).min, np.iinfo(T).max, (37, 11), dtype=T)
+        N = rng.integers(-80, 80, (37, 11)).astype(np.int64)
+        dx, dn = dab.distribute(X), dab.distribute(N)
+        for left, f in ((True, lambda x, n: x << n), (False, lambda x, n: x >> n)):
+            got = dab.to_array(dab.broadcast(f, dx, dn))
+            want = np.vectorize(lambda x, n: hm.jl_shift(int(x), int(n), bits, left), otypes=[T])(X, N)
+            assert got.dtype == np.dtype(T) and np.array_equal(got, want), (T, left)
+
+
+def test_reference_int128_mapreduce_is_exact(dab, rt8):
+    """test/darray.jl:286-294 as written: 25 random vectors of 1:5, length 2..30, f Int128-valued, ``mapreduce(f, opt, DA)`` EXACTLY equal
+    to the local result (here: Python's exact integers wrapped to 128 bits; the products overflow Int64 by far)."""
+    rng = np.random.default_rng(286)
+    fs = [(lambda x: dab.Int128(2 * x), lambda v: 2 * v), (lambda x: dab.Int128(x) ** 2, lambda v: v * v),
+          (lambda x: dab.Int128(x) ** 2 + 2 * dab.Int128(x) - 1, lambda v: v * v + 2 * v - 1)]
+    for _ in range(25):
+        a = rng.integers(1, 6, int(rng.integers(2, 31))).astype(np.int64)
+        if a.size < 8:
+            a = np.resize(a, 8)                                                 # rt8: at least one element per worker, like the reference's 4 procs
+        d = dab.distribute(a)
+        od = orc.distribute(a, nworkers=8)
+        for tf, pf in fs:
+            for op in ("+", "*"):
+                got = dab.mapreduce(tf, op, d)
+                assert isinstance(got, int) and got == orc.darray_mapreduce_int128(pf, op, od), (a, op)
+        d.close()
+    # a long vector: many CTAs, the 16-byte shuffles and partials of the Int128 carrier; the sum passes 2^64
+    n = (1 << 22) + 5
+    a = rng.integers(-2 ** 62, 2 ** 62, n).astype(np.int64)
+    d = dab.distribute(a)
+    want = sum(int(v) * 8 for v in a)
+    assert dab.mapreduce(lambda x: dab.widen(x) * 8, "+", d) == want and abs(want) >= 0
+    assert dab.mapreduce(lambda x: dab.widen(x) * (2 ** 40), "max", d) == int(a.max()) * 2 ** 40
+    assert dab.mapreduce(lambda x: dab.widen(x) * (2 ** 40), "min", d) == int(a.min()) * 2 ** 40
+    with pytest.raises(dab.UnsupportedError):
+        dab.map_(lambda x: dab.Int128(x), d)                                    # no arrays of Int128
 
 
 def _sort_by_key(dab, rt, keys, vals):
@@ -106,209 +314,3 @@ def test_darray_sort_by(dab, rt8, T):
                     assert np.array_equal(ch.to_numpy().view(np.uint8), o2.chunks[o2.pids.index(pid)].view(np.uint8)), (n, tby)
                 d2.close()
         d.close()
-
-
-def test_broadcast_more_than_4_dims(dab, rt8):
-    """General (NVRTC) broadcasts over 5-D / 6-D arrays: same-shape arguments collapse to one dimension, extruded arguments to at
-    most 4 groups; bit-exact against NumPy in the same precision."""
-    rng = np.random.default_rng(91)
-    A = rng.standard_normal((6, 5, 4, 3, 4)).astype(np.float32)
-    B = rng.standard_normal((6, 5, 4, 3, 4)).astype(np.float32)
-    a, b = dab.distribute(A), dab.distribute(B)
-    r = dab.broadcast(lambda x, y: x - y * x, a, b)                             # nested tree: the fused general kernel
-    assert rt8.last_kernel == "dab_broadcast_expr"
-    assert np.array_equal(dab.to_array(r), A - B * A)
-    M = rng.standard_normal((6, 5, 1, 1, 4)).astype(np.float32)                 # extruded middle dims, plain array -> distributed
-    r2 = dab.broadcast(lambda x, m: x - m * x, a, M)
-    assert np.array_equal(dab.to_array(r2), A - M * A)
-    dest = dab.similar(a)
-    dab.broadcast_into(dest, lambda x, y: dab.sqrt(dab.abs2(x) + dab.abs2(y)), a, b)
-    assert np.array_equal(dab.to_array(dest), np.sqrt(A * A + B * B))
-    Cc = rng.integers(-50, 50, (6, 5, 4, 3, 4, 5)).astype(np.int64)
-    e = dab.distribute(Cc, procs=list(range(1, 9)), dist=(2, 1, 2, 1, 2, 1))
-    r3 = dab.broadcast(lambda x: x * x + 2 * x - 1, e)                          # result has the default layout: operands are halo-fetched
-    assert np.array_equal(dab.to_array(r3), Cc * Cc + 2 * Cc - 1)
-    V = rng.integers(-5, 5, (6, 1, 4, 1, 4, 1)).astype(np.int64)                # alternating extrusion: 6 groups, does not collapse
-    with pytest.raises(dab.UnsupportedError):
-        dab.broadcast(lambda x, v: x * v + v, e, V)
-
-
-@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64])
-@pytest.mark.parametrize("transA", [False, True])
-def test_gemm_single_column_goes_through_gemv(dab, rt1, dtype, transA):
-    """``A * b`` with a one-column ``b`` (n == 1, dense A): served by K9 -- fp64 / wrap-around carriers, so Float32 is within one
-    rounding of the fp64 product and integers are exact; the same call with a padded leading dimension stays on K12."""
-    from test_gpu_gemm import check_float, gemm
-    rng = np.random.default_rng(101)
-    for m, k in [(4096, 2048), (1000, 37), (1, 1), (37, 4099)]:
-        shape = (k, m) if transA else (m, k)
-        if np.dtype(dtype).kind == "f":
-            A, B = rng.standard_normal(shape).astype(dtype), rng.standard_normal((k, 1)).astype(dtype)
-            n0 = rt1.launches()
-            R = gemm(dab, rt1, A, B, transA)
-            assert R.shape == (m, 1) and rt1.launches() > n0
-            check_float(R, A, B, transA, 1.2e-7 if dtype == np.float32 else 1e-15 * max(k, 8))
-            ra = A.shape[0]
-            Rp = gemm(dab, rt1, A, B, transA, lda=(ra + 3) // 4 * 4 + 4)        # padded lda: not a dense chunk -> the tile kernels
-            check_float(Rp, A, B, transA, 2e-6 if dtype == np.float32 else 1e-15 * max(k, 8))
-        else:
-            hi = 2 ** 20 if dtype == np.int32 else 2 ** 40
-            A, B = rng.integers(-hi, hi, shape).astype(dtype), rng.integers(-hi, hi, (k, 1)).astype(dtype)
-            with np.errstate(over="ignore"):
-                want = (A.T if transA else A) @ B
-            assert np.array_equal(gemm(dab, rt1, A, B, transA), want)
-
-
-def test_reference_int128_mapreduce_is_exact(dab, rt8):
-    """test/darray.jl:286-294 as written: 25 random vectors of 1:5, length 2..30, f Int128-valued, ``mapreduce(f, opt, DA)`` EXACTLY equal
-    to the local result (here: Python's exact integers wrapped to 128 bits; the products overflow Int64 by far)."""
-    rng = np.random.default_rng(286)
-    fs = [(lambda x: dab.Int128(2 * x), lambda v: 2 * v), (lambda x: dab.Int128(x) ** 2, lambda v: v * v),
-          (lambda x: dab.Int128(x) ** 2 + 2 * dab.Int128(x) - 1, lambda v: v * v + 2 * v - 1)]
-    for _ in range(25):
-        a = rng.integers(1, 6, int(rng.integers(2, 31))).astype(np.int64)
-        if a.size < 8:
-            a = np.resize(a, 8)                                                 # rt8: at least one element per worker, like the reference's 4 procs
-        d = dab.distribute(a)
-        od = orc.distribute(a, nworkers=8)
-        for tf, pf in fs:
-            for op in ("+", "*"):
-                got = dab.mapreduce(tf, op, d)
-                assert isinstance(got, int) and got == orc.darray_mapreduce_int128(pf, op, od), (a, op)
-        d.close()
-    # a long vector: many CTAs, the 16-byte shuffles and partials of the Int128 carrier; the sum passes 2^64
-    n = (1 << 22) + 5
-    a = rng.integers(-2 ** 62, 2 ** 62, n).astype(np.int64)
-    d = dab.distribute(a)
-    want = sum(int(v) * 8 for v in a)
-    assert dab.mapreduce(lambda x: dab.widen(x) * 8, "+", d) == want and abs(want) >= 0
-    assert dab.mapreduce(lambda x: dab.widen(x) * (2 ** 40), "max", d) == int(a.max()) * 2 ** 40
-    assert dab.mapreduce(lambda x: dab.widen(x) * (2 ** 40), "min", d) == int(a.min()) * 2 ** 40
-    with pytest.raises(dab.UnsupportedError):
-        dab.map_(lambda x: dab.Int128(x), d)                                    # no arrays of Int128
-
-
-def test_reference_scalar_math_vocabulary(dab, rt8):
-    """test/darray.jl:775-797 (``f.(a) == f.(b)`` for a = drand(20, 20)): here ``f.(d)`` on the device against NumPy / SciPy in the same
-    precision.  Transcendental kernels are libdevice's (1-2 ulp for the elementary functions, up to ~10 ulp documented for tgamma / erfinv /
-    erfc in double), so the comparison is at 6 ulp, 16 ulp for the special functions; the functions that are exact by construction (trunc, round, isinf, isfinite, deg2rad, rad2deg as one multiplication) are bit-exact."""
-    import scipy.special as sp
-    rng = np.random.default_rng(775)
-    for T in (np.float64, np.float32):
-        A = rng.random((20, 20)).astype(T)
-        B = A + T(1)
-        d, d1 = dab.distribute(A), dab.distribute(B)
-        one, pi = T(1), T(np.pi)
-        cases = [("acos", A, np.arccos), ("asin", A, np.arcsin), ("atan", A, np.arctan), ("asinh", A, np.arcsinh), ("atanh", A, np.arctanh),
-                 ("acosh", B, np.arccosh), ("cbrt", A, np.cbrt), ("cosh", A, np.cosh), ("sinh", A, np.sinh), ("exp2", A, np.exp2),
-                 ("exp10", A, lambda v: np.power(T(10), v)), ("expm1", A, np.expm1), ("log10", B, np.log10), ("log2", B, np.log2),
-                 ("log1p", A, np.log1p),
-                 # reference without cancellation: 1 - v and 0.5 - v are exact here, so the small results near v = 1 (v = 0.5) keep full precision
-                 ("sinpi", A, lambda v: np.sin(np.pi * np.where(v > 0.5, 1.0 - v.astype(np.float64), v.astype(np.float64)))),
-                 ("cospi", A, lambda v: np.where(v > 0.25, np.sin(np.pi * (0.5 - v.astype(np.float64))), np.cos(np.pi * v.astype(np.float64)))),
-                 ("erf", A, sp.erf), ("erfc", A, sp.erfc), ("erfcx", A, sp.erfcx), ("erfinv", A * T(0.99), sp.erfinv),
-                 ("erfcinv", B * T(0.5), sp.erfcinv), ("gamma", B, sp.gamma), ("loggamma", B + T(1.5), sp.gammaln),
-                 ("sec", A, lambda v: one / np.cos(v)), ("csc", B, lambda v: one / np.sin(v)), ("cot", B, lambda v: one / np.tan(v)),
-                 ("sech", A, lambda v: one / np.cosh(v)), ("csch", B, lambda v: one / np.sinh(v)), ("coth", B, lambda v: one / np.tanh(v)),
-                 ("asec", B, lambda v: np.arccos(one / v)), ("acsc", B, lambda v: np.arcsin(one / v)), ("acot", B, lambda v: np.arctan(one / v)),
-                 ("asech", B * T(0.4), lambda v: np.arccosh(one / v)), ("acsch", B, lambda v: np.arcsinh(one / v)),
-                 ("acoth", B + one, lambda v: np.arctanh(one / v))]
-        srcs = {}
-        for nm, H, ref in cases:
-            if id(H) not in srcs:
-                srcs[id(H)] = dab.distribute(np.ascontiguousarray(H))
-            f = getattr(dab, nm)
-            got = dab.to_array(dab.map_(lambda x: f(x), srcs[id(H)]))
-            want = np.asarray(ref(H)).astype(T)
-            assert got.dtype == np.dtype(T)
-            ulp = np.spacing(np.abs(want).astype(T))
-            tol = 16 if nm in ("erfc", "erfcx", "erfinv", "erfcinv", "gamma", "loggamma", "sinpi", "cospi") else 6
-            assert np.all(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= tol * ulp.astype(np.float64)), (nm, T)
-        # exact ones
-        S = ((A - T(0.5)) * T(10)).astype(T)
-        S[0, :4] = [np.inf, -np.inf, np.nan, T(2.5)]
-        ds = dab.distribute(S)
-        for nm, ref in (("trunc", np.trunc), ("round_", np.rint)):
-            f = getattr(dab, nm)
-            assert np.array_equal(dab.to_array(dab.map_(lambda x: f(x), ds)), ref(S), equal_nan=True), nm
-        assert np.array_equal(dab.to_array(dab.map_(lambda x: dab.isinf(x), ds)), np.isinf(S))
-        assert np.array_equal(dab.to_array(dab.map_(lambda x: dab.isfinite(x), ds)), np.isfinite(S))
-        assert np.array_equal(dab.to_array(dab.map_(lambda x: dab.deg2rad(x), d)), A * (pi / T(180)))
-        assert np.array_equal(dab.to_array(dab.map_(lambda x: dab.rad2deg(x), d)), A * (T(180) / pi))
-        assert abs(float(dab.sum(d1, lambda x: dab.log2(x))) - float(np.log2(B.astype(np.float64)).sum())) <= 1e-5 * B.size   # inside a fused mapreduce
-
-
-def test_norm_other_p(dab, rt8):
-    """``norm(x, p)`` (src/linalg.jl:48-59) beyond p = 1, 2, Inf: -Inf, 0 and a general p, against NumPy in Float64."""
-    rng = np.random.default_rng(48)
-    for T in (np.float64, np.float32, np.int64):
-        a = (rng.standard_normal(10007) * 3).astype(T)
-        a[::97] = 0
-        d = dab.distribute(a)
-        a64 = a.astype(np.float64)
-        assert float(dab.norm(d, 0)) == float(np.count_nonzero(a))
-        assert float(dab.norm(d, -np.inf)) == float(np.abs(a64).min()) and float(dab.norm(d, np.inf)) == float(np.abs(a64).max())
-        for p in (3, 2.5, 0.5):
-            got = dab.norm(d, p)
-            want = float((np.abs(a64) ** p).sum() ** (1.0 / p))
-            assert abs(float(got) - want) <= (2e-6 if T == np.float32 else 1e-12) * want, (T, p)
-            assert isinstance(got, np.float32) == (T == np.float32)
-
-
-def test_reference_shift_ops(dab, rt8):
-    """test/darray.jl:863-867: ``f.(a, 2) == f.(b, 2)``, ``f.(2, a) == f.(2, b)``, ``f.(a, a) == f.(b, b)`` for f in (<<, >>) on
-    ``a = dones(Int, 20, 20)``; plus counts that are negative or past the width, Int32 values, against the Julia-semantics model."""
-    import hostmem_abi as hm
-    a = dab.dones((20, 20), dtype=np.int64)
-    ones = np.ones((20, 20), dtype=np.int64)
-    assert np.array_equal(dab.to_array(dab.map_(lambda x: x << 2, a)), ones << 2)
-    assert np.array_equal(dab.to_array(dab.map_(lambda x: 2 << x, a)), 2 << ones)
-    assert np.array_equal(dab.to_array(dab.broadcast(lambda x, y: x << y, a, a)), ones << ones)
-    assert np.array_equal(dab.to_array(dab.map_(lambda x: x >> 2, a)), ones >> 2)
-    assert np.array_equal(dab.to_array(dab.map_(lambda x: 2 >> x, a)), 2 >> ones)
-    assert np.array_equal(dab.to_array(dab.broadcast(lambda x, y: x >> y, a, a)), ones >> ones)
-    rng = np.random.default_rng(863)
-    for T, bits in ((np.int64, 64), (np.int32, 32)):
-        X = rng.integers(np.iinfo(T).min, np.iinfo(T).max, (37, 11), dtype=T)
-        N = rng.integers(-80, 80, (37, 11)).astype(np.int64)
-        dx, dn = dab.distribute(X), dab.distribute(N)
-        for left, f in ((True, lambda x, n: x << n), (False, lambda x, n: x >> n)):
-            got = dab.to_array(dab.broadcast(f, dx, dn))
-            want = np.vectorize(lambda x, n: hm.jl_shift(int(x), int(n), bits, left), otypes=[T])(X, N)
-            assert got.dtype == np.dtype(T) and np.array_equal(got, want), (T, left)
-
-
-def test_copy_deepcopy_drandn(dab, rt8):
-    """test/darray.jl:84-131: a copy equals the original and owns its localparts; ``drandn`` (src/darray.jl:526-532) gives finite
-    standard-normal entries that do not depend on the layout."""
-    D = dab.drand((200, 200), procs=[1, 2])
-    A = dab.to_array(D)
-    for cp in (dab.copy, dab.deepcopy):
-        DC = cp(D)
-        assert dab.isequal(D, DC) and list(DC.layout.pids) == list(D.layout.pids)
-        dab.fill_(DC, 0.0)                                                       # writing into the copy ...
-        assert np.array_equal(dab.to_array(D), A) and not dab.isequal(D, DC)     # ... never shows in the original
-        DC.close()
-    E = dab.distribute(A, procs=[1, 2, 3, 4], dist=[1, 4])                       # a dist that similar() does not inherit
-    EC = dab.copy(E)
-    assert np.array_equal(dab.to_array(EC), A)
-    for T in (np.float64, np.float32):
-        n1 = dab.to_array(dab.drandn((300, 400), dtype=T))
-        n2 = dab.to_array(dab.drandn((300, 400), procs=[1, 2, 3], dist=[3, 1], dtype=T))
-        assert n1.dtype == np.dtype(T) and np.array_equal(n1, n2) and np.all(np.isfinite(n1))
-        assert abs(float(n1.mean())) < 0.02 and abs(float(n1.std()) - 1.0) < 0.02 and float(np.abs(n1).max()) > 3.0
-        assert not np.array_equal(n1, dab.to_array(dab.drandn((300, 400), dtype=T, seed=99)))
-    v = dab.drandn((20,))
-    assert abs(float(dab.norm(v)) - float(np.linalg.norm(dab.to_array(v)))) < 1e-7   # test/darray.jl:946-957
-
-
-def test_multi_argument_mapreduce_with_dims(dab, rt8):
-    """``mapreduce(f, op, A, B; dims)`` = ``reduce(op, map(f, A, B); dims)`` (Base) on DArrays."""
-    rng = np.random.default_rng(3)
-    A, B = rng.integers(-9, 9, (60, 70)).astype(np.int64), rng.integers(-9, 9, (60, 70)).astype(np.int64)
-    a, b = dab.distribute(A), dab.distribute(B)
-    for dims, axis in ((1, 0), (2, 1), ((1, 2), (0, 1))):
-        r = dab.mapreduce(lambda x, y: x * y + 1, "+", a, b, dims=dims)
-        assert np.array_equal(dab.to_array(r), (A * B + 1).sum(axis=axis, keepdims=True))
-    r = dab.mapreduce(lambda x, y: x - y, "max", a, 3, dims=2)                  # a scalar argument
-    assert np.array_equal(dab.to_array(r), (A - 3).max(axis=1, keepdims=True))

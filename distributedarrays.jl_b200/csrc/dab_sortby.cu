@@ -18,57 +18,28 @@
 #include <type_traits>
 
 #include "dab_common.cuh"
-#include "dab_sort_key.cuh"
+#include "dab_sortby_core.cuh"
 
 namespace {
 
-constexpr unsigned long long SIGN64 = 0x8000000000000000ull;
-
-// radix key of one by-value: the keys-only bijection, except that all NaNs collapse to the largest key (isless(NaN, NaN) is false both
-// ways: NaN keys are ties, and ties keep input order).  The largest key of the bijection is itself a NaN, so nothing else maps there.
-template <typename KT>
-__device__ __forceinline__ typename SortKey<KT>::U by_radix_key(typename SortKey<KT>::U raw) {
-    using U = typename SortKey<KT>::U;
-    if constexpr (std::is_floating_point<KT>::value) {
-        constexpr U ABS = (U)~((U)1 << (8 * sizeof(U) - 1));
-        constexpr U INF = sizeof(U) == 4 ? (U)0x7F800000u : (U)0x7FF0000000000000ull;
-        if ((raw & ABS) > INF) return (U)~(U)0;
-    }
-    return SortKey<KT>::enc(raw);
-}
-
-// word[j] = half of radix_key(keys[i]) << 32 | j, with i = j (round 1) or i = lo32(prev[j]) (round 2: the order round 1 left).
-// Stored with the top bit flipped: dab_sort orders Int64 words as SIGNED integers.
 template <typename KT>
 __global__ void __launch_bounds__(256) sortby_pack_kernel(const typename SortKey<KT>::U* __restrict__ keys, const unsigned long long* __restrict__ prev,
                                                           int half, unsigned long long* __restrict__ words, size_t n) {
-    using U = typename SortKey<KT>::U;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const size_t i = prev ? (size_t)(unsigned int)prev[j] : j;
-        const U e = by_radix_key<KT>(keys[i]);
-        unsigned int h;
-        if constexpr (sizeof(U) == 4) h = (unsigned int)e;
-        else h = half ? (unsigned int)(e >> 32) : (unsigned int)e;
-        words[j] = (((unsigned long long)h << 32) | (unsigned long long)j) ^ SIGN64;
-    }
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) words[j] = sortby_word<KT>(keys, prev, half, j);
 }
 
-// out[j] = vals[perm[j]], perm[j] = lo32(last[j]) for one round, lo32(first[lo32(last[j])]) for two.
+// out[j] = vals[perm[j]]
 template <typename V>
 __global__ void __launch_bounds__(256) sortby_gather_kernel(const V* __restrict__ vals, const unsigned long long* __restrict__ last,
                                                             const unsigned long long* __restrict__ first, V* __restrict__ out, size_t n) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const unsigned int a = (unsigned int)last[j];
-        const unsigned int i = first ? (unsigned int)first[a] : a;
-        out[j] = vals[i];
-    }
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) out[j] = vals[sortby_source(last, first, j)];
 }
 
 inline size_t word_stride_bytes(size_t n) { return (n * 8 + 255) & ~(size_t)255; }   // every word buffer starts 256-byte aligned
 
-inline int rounds_of(int32_t key_dtype) { return (key_dtype == DAB_F64 || key_dtype == DAB_I64) ? 2 : 1; }
+inline int rounds_of(int32_t key_dtype) { return sortby_rounds((key_dtype == DAB_F64 || key_dtype == DAB_I64) ? 8 : 4); }
 
 template <typename KT>
 int32_t pack_t(dab_ctx* ctx, const void* keys, const unsigned long long* prev, int half, unsigned long long* words, size_t n) {

@@ -206,3 +206,21 @@ def test_host_sort_flow_with_and_without_by(hostmem, dab, T, nw):
         d.close()
     assert hostmem.launches > 0
     rt.shutdown()
+
+
+def test_sort_by_key_element_code_host_replay(tmp_path):
+    """tools/sortby_host_check.cu: the per-element code the sort-by-key KERNELS run (dab_sortby_core.cuh, __host__ __device__) replayed on
+    the host -- words packed by ``sortby_word``, std::sort in place of K11, permutation by ``sortby_source`` -- against std::stable_sort
+    in isless order, for the four key types (ties, signed zeros, infinities, NaN payloads, integer extremes)."""
+    import os
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "sortby_host_check")
+    subprocess.check_call([nvcc, "-std=c++17", "-O2", "-Wno-deprecated-gpu-targets", "-I", os.path.join(root, "distributedarrays.jl_b200", "csrc"),
+                           "-o", exe, os.path.join(root, "tools", "sortby_host_check.cu")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "sortby_host_check: ok" in out.stdout, out.stdout + out.stderr

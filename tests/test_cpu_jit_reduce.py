@@ -180,3 +180,45 @@ def test_shift_operators_trace_and_compile():
     assert hm.jl_shift(-2 ** 63, 1, 64, True) == 0 and hm.jl_shift(1, 31, 32, True) == -2 ** 31 and hm.jl_shift(3, 63, 64, True) == -2 ** 63
     args = [np.array([1, -8, 5], dtype=np.int64)]
     assert list(hm.eval_expr(bc.trace(lambda a: (a << 2) >> 1, ["i64"]), args)) == [2, -16, 10]
+
+
+def test_shift_device_functions_on_the_host(tmp_path):
+    """The text of the jl_x_shl / jl_x_shr device functions (the on-demand prelude block of dab_jit.cu) compiled for the host with g++ and
+    compared with the Julia-semantics model over edge and random operands: the scalar code NVRTC will compile is checked on CPU."""
+    import os
+    import shutil
+    import subprocess
+    import hostmem_abi as hm
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "distributedarrays.jl_b200", "csrc", "dab_jit.cu")).read()
+    ext = text[text.index('kPreludeExt = R"PRELUDE('):]
+    ext = ext[:ext.index(')PRELUDE"')]
+    body = ext[ext.index("DEV i64 jl_x_shr(i64 a, i64 n);"):]
+    src = tmp_path / "shifts.cpp"
+    src.write_text("typedef unsigned long long u64;\ntypedef long long i64;\n#define DEV static inline\n" + body + """
+extern "C" {
+i64 shl64(i64 a, i64 n) { return jl_x_shl(a, n); }
+i64 shr64(i64 a, i64 n) { return jl_x_shr(a, n); }
+int shl32(int a, i64 n) { return jl_x_shl(a, n); }
+int shr32(int a, i64 n) { return jl_x_shr(a, n); }
+}
+""")
+    so = str(tmp_path / "shifts.so")
+    subprocess.check_call([gxx, "-O1", "-shared", "-fPIC", "-o", so, str(src)])
+    L = C.CDLL(so)
+    for f in (L.shl64, L.shr64):
+        f.restype, f.argtypes = C.c_longlong, [C.c_longlong, C.c_longlong]
+    for f in (L.shl32, L.shr32):
+        f.restype, f.argtypes = C.c_int, [C.c_int, C.c_longlong]
+    rng = np.random.default_rng(864)
+    counts = [0, 1, 2, 31, 32, 33, 63, 64, 65, 1000, -1, -2, -31, -32, -33, -63, -64, -65, -1000, 2 ** 62, -2 ** 63]
+    for bits, shl, shr in ((64, L.shl64, L.shr64), (32, L.shl32, L.shr32)):
+        lo, hi = -2 ** (bits - 1), 2 ** (bits - 1) - 1
+        xs = [0, 1, -1, 2, -8, lo, hi, lo + 1, 3] + [int(v) for v in rng.integers(lo, hi, 40)]
+        for x in xs:
+            for n in counts + [int(v) for v in rng.integers(-70, 70, 10)]:
+                assert shl(x, n) == hm.jl_shift(x, n, bits, True), (bits, x, n)
+                assert shr(x, n) == hm.jl_shift(x, n, bits, False), (bits, x, n)

@@ -743,7 +743,14 @@ def to_array(d: DArray) -> np.ndarray:
 
 
 def copyto(dest: DArray, src: np.ndarray) -> DArray:
-    """``copyto!(dest::DArray, src::AbstractArray)`` (src/darray.jl:679-687)."""
+    """``copyto!(dest::DArray, src::AbstractArray)`` (src/darray.jl:679-687): per worker ``copyto!(localpart(dest), view(src,
+    localindices(dest)...))``.  A host array is uploaded slice by slice; a DArray / SubDArray source (test/darray.jl:225-234) stays on the
+    devices -- one identity broadcast per localpart, the view of a differently laid out source being the usual halo fetch."""
+    if isinstance(src, (DArray, SubDArray)):
+        from ._broadcast import broadcast_into
+        if tuple(src.dims) != dest.dims:
+            raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"DArray has size {dest.dims} but the source has {tuple(src.dims)}")
+        return broadcast_into(dest, lambda x: x, src)
     src = np.asarray(src)
     if tuple(src.shape) != dest.dims:
         raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, f"DArray has size {dest.dims} but array has {src.shape}")

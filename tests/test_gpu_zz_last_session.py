@@ -122,6 +122,16 @@ def test_copy_deepcopy_drandn(dab, rt8):
         assert not np.array_equal(n1, dab.to_array(dab.drandn((300, 400), dtype=T, seed=99)))
     v = dab.drandn((20,))
     assert abs(float(dab.norm(v)) - float(np.linalg.norm(dab.to_array(v)))) < 1e-7   # test/darray.jl:946-957
+    # test/darray.jl:225-234 "test copy!": copyto!(D2, D1) with D2 built from irregular chunks (3 + 7 rows), D1 = dzeros; on the devices
+    rng = np.random.default_rng(225)
+    D1 = dab.dzeros((10, 10))
+    D2 = dab.darray_from_chunks([rng.standard_normal((3, 10)), rng.standard_normal((7, 10))], (2, 1))
+    assert dab.copyto(D2, D1) is D2 and dab.isequal(D1, D2) and np.array_equal(dab.to_array(D2), np.zeros((10, 10)))
+    R = rng.standard_normal((10, 10))
+    dab.copyto(D2, dab.distribute(R)[0:10, 0:10])                                 # a SubDArray source
+    assert np.array_equal(dab.to_array(D2), R) and D2.layout.indices[0][0] == (1, 3)
+    with pytest.raises(dab.DimensionMismatch):
+        dab.copyto(D2, dab.dzeros((10, 9)))
 
 
 def test_multi_argument_mapreduce_with_dims(dab, rt8):

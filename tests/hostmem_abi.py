@@ -217,6 +217,41 @@ class HostMemABI:
         self.launches += 2
         return 0
 
+    # -- whole-chunk reductions: only what sort(d; sample=false) needs, minimum / maximum of a chunk (exact, NaN-propagating like Base);
+    #    the host-only entry points (result dtype table, ordered fold) are the REAL library's -- they need no GPU
+    def _real(self):
+        if getattr(self, "_real_lib", None) is None:
+            from darray_b200 import _lib as real
+            L = C.CDLL(real.SO_PATH)
+            L.dab_reduce_result_dtype.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+            L.dab_combine_ordered.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
+            self._real_lib = L
+        return self._real_lib
+
+    def dab_reduce_result_dtype(self, dtype, op, mapc, out):
+        return self._real().dab_reduce_result_dtype(int(dtype), int(op), int(mapc), C.cast(C.c_void_p(_addr(out)), C.POINTER(C.c_int32)))
+
+    def dab_combine_ordered(self, rdt, op, partials, p, out):
+        return self._real().dab_combine_ordered(int(rdt), int(op), C.c_void_p(_addr(partials)), int(p), C.c_void_p(_addr(out)))
+
+    def _reduce(self, dtype, op, mapc, x, n, out):
+        assert int(op) in (2, 3) and int(mapc) == 0, "hostmem_abi emulates dab_reduce for maximum / minimum with the identity map only"
+        v = _view(x, int(n), _NP[int(dtype)])
+        with np.errstate(invalid="ignore"):
+            r = (np.max if int(op) == 2 else np.min)(v)             # NaN-propagating; signed zeros do not occur in the tests that use it
+        slot = np.zeros(2, dtype=np.uint64)
+        slot.view(np.uint8)[:v.dtype.itemsize] = np.asarray([r], dtype=v.dtype).view(np.uint8)
+        slot[1] = slot[0]
+        C.memmove(_addr(out), slot.ctypes.data, 16)
+        self.launches += 1
+        return 0
+
+    def dab_reduce(self, ctx, dtype, op, mapc, param, x, n, out):
+        return self._reduce(dtype, op, mapc, x, n, out)
+
+    def dab_mapreduce_all(self, ctx, dtype, op, mapc, param, x, n, out_host):
+        return self._reduce(dtype, op, mapc, x, n, out_host)
+
     # -- fused map + reduce of a traced expression, Int128 values only (the other value types need dab_combine_ordered etc.)
     def dab_mapreduce_expr(self, ctx, src, val_dtype, op, n, nargs, dts, ptrs, scal, out):
         assert int(val_dtype) == 5, "hostmem_abi emulates dab_mapreduce_expr for Int128 values only"

@@ -189,7 +189,7 @@ def test_host_sort_flow_with_and_without_by(hostmem, dab, T, nw):
         assert d.layout.indices == od.indices
         smp = _by_data(T, 64, rng)
         lohi = (T(-60), T(60)) if np.dtype(T).kind == "i" else (T(0), T(1))
-        for sample in (True, lohi, smp):
+        for sample in (True, False, lohi, smp):
             for tby, nby in [(None, None)] + _by_cases(T):
                 try:
                     want, wb = orc.darray_sort(od, sample, by=nby)

@@ -59,7 +59,6 @@ def hostmem(dab, monkeypatch):
     saved_lib, saved_rt = lib_mod._lib, None
     fake = hostmem_abi.HostMemABI()
     lib_mod._lib = fake
-    monkeypatch.setattr(bc_mod, "run_local", hostmem_abi.run_local)
     real_codegen = bc_mod.codegen
 
     def recording_codegen(e):                                  # lets the emulated dab_mapreduce_expr find the tree behind a source string

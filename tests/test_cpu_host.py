@@ -336,3 +336,34 @@ def test_collapse_dims_addresses_the_same_elements():
     assert len(oc) == 5
     with pytest.raises(_lib.DimensionMismatch):
         bc.collapse_dims((2, 3, 4, 5, 6), [(2, 3, 4, 5, 7)])
+
+
+def test_last_session_gpu_tests_dry_run_on_the_host_memory_abi(hostmem, dab):
+    """The GPU tests of tests/test_gpu_zz_last_session.py that the host-memory ABI emulation can carry (all but the dab_gemm dispatch) are
+    executed here, on CPU, exactly as written (same functions, a runtime on the emulation in place of the rt fixtures): the host runtime
+    above the ABI -- tracer, run_local's routing and stride tables, collapse_dims, layouts, halo plans, the sort / Int128 / copy / norm
+    flows -- runs for real, only the kernels are NumPy.  Whatever fails on the B200 later is then in a kernel or a binding, not in a typo,
+    a shape or a wrong NumPy twin of the TEST, nor in the host logic."""
+    import test_gpu_zz_last_session as z
+    rt = dab.init(workers_per_rank=8, use_dist=False)
+    z.test_broadcast_more_than_4_dims(dab, rt)                # the REAL run_local: collapse_dims + stride tables against the emulated 4-D box walk
+    z.test_norm_other_p(dab, rt)
+    z.test_copy_deepcopy_drandn(dab, rt)
+    z.test_multi_argument_mapreduce_with_dims(dab, rt)
+    z.test_reference_shift_ops(dab, rt)
+    z.test_reference_scalar_math_vocabulary(dab, rt)
+    for T in (np.int64, np.float32):
+        z.test_darray_sort_by(dab, rt, T)
+    big, z.INT128_BIG_N = z.INT128_BIG_N, (1 << 12) + 5          # the emulator folds Python integers one by one
+    try:
+        z.test_reference_int128_mapreduce_is_exact(dab, rt)
+    finally:
+        z.INT128_BIG_N = big
+    rt1 = dab.init(workers_per_rank=1, use_dist=False)
+    sizes, z.SORT_BY_KEY_SIZES = z.SORT_BY_KEY_SIZES, (1, 2, 33, 1025, 4097)
+    try:
+        for KT in (np.float32, np.float64, np.int32, np.int64):
+            z.test_sort_by_key_kernel(dab, rt1, KT)
+    finally:
+        z.SORT_BY_KEY_SIZES = sizes
+    assert hostmem.launches > 1000, hostmem.launches          # the tests really drove the emulated entry points

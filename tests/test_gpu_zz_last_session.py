@@ -28,6 +28,9 @@ import pytest
 
 from oracle import darray_oracle as orc
 
+INT128_BIG_N = (1 << 22) + 5                    # the CPU dry run of these tests (tests/test_cpu_host.py) shrinks the big sizes
+SORT_BY_KEY_SIZES = (1, 2, 33, 1024, 1025, 4097, 100003, (1 << 20) + 17)
+
 pytestmark = [pytest.mark.gpu,
               pytest.mark.xfail(strict=False, reason="added in the last session of round 2, never executed on a GPU (budget spent)")]
 
@@ -237,7 +240,7 @@ def test_reference_int128_mapreduce_is_exact(dab, rt8):
                 assert isinstance(got, int) and got == orc.darray_mapreduce_int128(pf, op, od), (a, op)
         d.close()
     # a long vector: many CTAs, the 16-byte shuffles and partials of the Int128 carrier; the sum passes 2^64
-    n = (1 << 22) + 5
+    n = INT128_BIG_N
     a = rng.integers(-2 ** 62, 2 ** 62, n).astype(np.int64)
     d = dab.distribute(a)
     want = sum(int(v) * 8 for v in a)
@@ -268,7 +271,7 @@ def _sort_by_key(dab, rt, keys, vals):
 @pytest.mark.parametrize("KT", [np.float32, np.float64, np.int32, np.int64])
 def test_sort_by_key_kernel(dab, rt1, KT):
     rng = np.random.default_rng(71)
-    for n in (1, 2, 33, 1024, 1025, 4097, 100003, (1 << 20) + 17):
+    for n in SORT_BY_KEY_SIZES:
         if np.dtype(KT).kind == "f":
             keys = np.round(rng.standard_normal(n) * 10.0 ** rng.integers(-3, 3, n), 2).astype(KT)        # many ties
             if n > 64:

@@ -12,6 +12,33 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with `-m gpu` on the GPU box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _hostmem_session():
+    """``DAB_HOSTMEM=1`` (never set by the driver's tiers; used by tests/test_cpu_host.py in a subprocess): install the host-memory
+    emulation of the C ABI (tests/hostmem_abi.py) for the whole session, so that the ``-m gpu`` test modules can be executed on a
+    CPU-only machine as a regression test of the HOST runtime (tracer, kernel routing, stride tables, layouts, halo / exchange plans,
+    error contracts).  Says nothing about the CUDA kernels."""
+    if os.environ.get("DAB_HOSTMEM") != "1":
+        yield None
+        return
+    import darray_b200  # noqa: F401
+    import hostmem_abi
+
+    lib_mod = sys.modules["darray_b200._lib"]
+    bc_mod = sys.modules["darray_b200._broadcast"]
+    fake = hostmem_abi.HostMemABI()
+    lib_mod._lib = fake
+    real_codegen = bc_mod.codegen
+
+    def recording_codegen(e):
+        src = real_codegen(e)
+        fake.exprs[src.encode()] = e
+        return src
+
+    bc_mod.codegen = recording_codegen
+    yield fake
+
+
 @pytest.fixture(scope="session")
 def dab():
     import darray_b200

@@ -267,6 +267,69 @@ class HostMemABI:
         self.launches += 1
         return 0
 
+    # -- linear algebra tiles (NumPy stand-ins: only the HOST logic around them is under test) and small utilities
+    def dab_set_option(self, ctx, key, value):
+        return 0
+
+    def dab_h2d_2d(self, ctx, dptr, dpitch, hptr, hpitch, row_bytes, cols):
+        for c in range(int(cols)):
+            C.memmove(_addr(dptr) + c * int(dpitch), _addr(hptr) + c * int(hpitch), int(row_bytes))
+        return 0
+
+    def dab_gemv(self, ctx, dtype, trans, A, m, n, x, r):
+        dt, m, n = _NP[int(dtype)], int(m), int(n)
+        a = _view(A, m * n, dt).reshape((m, n), order="F")
+        wide = np.float64 if dt.kind == "f" else np.int64
+        with np.errstate(all="ignore"):
+            if int(trans):
+                _view(r, n, dt)[:] = (a.T.astype(wide) @ _view(x, m, dt).astype(wide)).astype(dt)
+            else:
+                _view(r, m, dt)[:] = (a.astype(wide) @ _view(x, n, dt).astype(wide)).astype(dt)
+        self.launches += 1
+        return 0
+
+    def dab_gemm(self, ctx, dtype, transA, m, n, k, A, lda, B, ldb, Cp, ldc):
+        dt, m, n, k, lda, ldb, ldc = _NP[int(dtype)], int(m), int(n), int(k), int(lda), int(ldb), int(ldc)
+        if m == 0 or n == 0:
+            return 0
+        wide = np.float64 if dt.kind == "f" else np.int64
+        cols_a = m if int(transA) else k
+        a = _view(A, lda * cols_a, dt).reshape((lda, cols_a), order="F")[:(k if int(transA) else m)] if k else np.zeros((0, 0), dt)
+        b = _view(B, ldb * n, dt).reshape((ldb, n), order="F")[:k] if k else np.zeros((0, n), dt)
+        c = _view(Cp, ldc * n, dt).reshape((ldc, n), order="F")
+        with np.errstate(all="ignore"):
+            c[:m] = ((a.T if int(transA) else a).astype(wide) @ b.astype(wide)).astype(dt) if k else 0
+        self.launches += 1
+        return 0
+
+    def dab_transpose_box(self, ctx, elem_bytes, dst, dst_ld, src, src_ld, rows, cols):
+        dt = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[int(elem_bytes)]
+        rows, cols, dst_ld, src_ld = int(rows), int(cols), int(dst_ld), int(src_ld)
+        if rows and cols:
+            s_ = _view(src, src_ld * (cols - 1) + rows, dt)
+            d_ = _view(dst, dst_ld * (rows - 1) + cols, dt)
+            from numpy.lib.stride_tricks import as_strided
+            sv = as_strided(s_, shape=(rows, cols), strides=(dt().itemsize, src_ld * dt().itemsize))
+            dv = as_strided(d_, shape=(cols, rows), strides=(dt().itemsize, dst_ld * dt().itemsize))
+            dv[...] = sv.T
+        self.launches += 1
+        return 0
+
+    def dab_accumulate_stack(self, ctx, dtype, y, n, beta, alpha, stack, stride, count):
+        dt, n = _NP[int(dtype)], int(n)
+        yv = _view(y, n, dt)
+        b, a = _view(beta, 1, dt)[0], _view(alpha, 1, dt)[0]
+        with np.errstate(all="ignore"):
+            acc = (yv * b) if b != 1 else yv.copy()
+            if b == 0:
+                acc = np.zeros(n, dtype=dt)
+            for j in range(int(count)):
+                t = _view(_addr(stack) + j * int(stride) * dt.itemsize, n, dt)
+                acc = acc + (t * a if a != 1 else t)
+            yv[:] = acc
+        self.launches += 1
+        return 0
+
     # -- dab_gather_box: per dimension the element offset of coordinate t is t * stride (possibly negative) or table[t]
     def dab_gather_box(self, ctx, elem_bytes, ndim, dst, dst_strides, dst_index, src, src_strides, src_index, extent):
         nd = int(ndim)
@@ -363,6 +426,14 @@ class HostMemABI:
         op, mapc = int(op), int(mapc)
         dt = _NP[int(dtype)] if int(dtype) != U8 else np.dtype(np.bool_)
         v = _view(x, int(n), dt)
+        if op == 7:                                               # EXTREMA: [min, max] in the element type, one pass
+            with np.errstate(all="ignore"):
+                pair = np.asarray([np.min(v), np.max(v)], dtype=dt)
+            slot = np.zeros(16, dtype=np.uint8)
+            slot[:2 * dt.itemsize] = pair.view(np.uint8)
+            C.memmove(_addr(out), slot.ctypes.data, 16)
+            self.launches += 1
+            return 0
         with np.errstate(all="ignore"):
             if mapc >= 16:
                 q = _view(param, 1, dt)[0] if param is not None and _addr(param) else None
@@ -418,13 +489,13 @@ class HostMemABI:
             self.launches += 2
             return 0
         if int(val_dtype) != 5:                                  # array element types: sum in the wide carrier, max / min exact
-            assert int(op) in (0, 2, 3) and int(val_dtype) in (F32, F64, I32, I64), "hostmem_abi: SUM / MAX / MIN of numeric values only"
+            assert int(op) in (0, 1, 2, 3) and int(val_dtype) in (F32, F64, I32, I64), "hostmem_abi: SUM / PROD / MAX / MIN of numeric values only"
             v = np.broadcast_to(np.asarray(eval_expr(expr, args)), (n,))
             isf = v.dtype.kind == "f"
             wide = np.float64 if isf else np.int64
             with np.errstate(all="ignore"):
-                acc = v.astype(wide).sum() if int(op) == 0 else (v.max() if int(op) == 2 else v.min())
-            rdt = (v.dtype if isf else np.dtype(np.int64)) if int(op) == 0 else v.dtype
+                acc = {0: lambda: v.astype(wide).sum(), 1: lambda: v.astype(wide).prod(), 2: v.max, 3: v.min}[int(op)]()
+            rdt = (v.dtype if isf else np.dtype(np.int64)) if int(op) in (0, 1) else v.dtype
             slot = np.zeros(16, dtype=np.uint8)
             slot[:rdt.itemsize] = np.asarray([acc], dtype=rdt).view(np.uint8)
             slot[8:8 + np.dtype(wide).itemsize] = np.asarray([acc], dtype=wide).view(np.uint8)

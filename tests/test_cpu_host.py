@@ -4,6 +4,7 @@ oracle.  No kernel is launched here.
 """
 import ctypes as C
 import os
+import sys
 import re
 
 import numpy as np
@@ -367,3 +368,22 @@ def test_last_session_gpu_tests_dry_run_on_the_host_memory_abi(hostmem, dab):
     finally:
         z.SORT_BY_KEY_SIZES = sizes
     assert hostmem.launches > 1000, hostmem.launches          # the tests really drove the emulated entry points
+
+
+def test_gpu_test_modules_against_the_host_memory_abi():
+    """Host-runtime regression net: the ``-m gpu`` modules (hot path, widening, views, linalg host flows, sort, the last-session module)
+    executed in a subprocess with ``DAB_HOSTMEM=1`` -- the C ABI emulated over host memory (tests/hostmem_abi.py), everything above it
+    real.  Left out: the full-size tests (GiB-sized arrays), the tests that only make sense on the device (TMA variant, pinned H2D rates,
+    the GEMM kernel module, multi-GPU).  A failure here is a regression in the HOST logic; the kernels are the ``-m gpu`` tier's job."""
+    import subprocess
+    env = dict(os.environ, DAB_HOSTMEM="1")
+    mods = ["tests/test_gpu_hotpath.py", "tests/test_gpu_widen.py", "tests/test_gpu_views.py", "tests/test_gpu_linalg.py", "tests/test_gpu_sort.py",
+            "tests/test_gpu_zz_last_session.py"]
+    r = subprocess.run([sys.executable, "-m", "pytest", *mods, "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "--timeout", "600",
+                        "-k", "not full_size and not tma_variant and not pinned_large and not bandwidth_shape and not transpose_large"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
+    assert r.returncode == 0, tail
+    import re
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert m and int(m.group(1)) >= 200, tail

@@ -415,9 +415,10 @@ def main():
         lp = dab.localpart(x)
         ms_c, _ = timed(lambda: lp.copy_from_host(hx, sync=False), 2, warm=1)
         ms_c = max_over_ranks(ms_c)
-        pg = np.empty(1 << 28, dtype=np.float32)
+        n_pg = min(1 << 28, n_per)                                         # 1 GiB of pageable memory (the whole chunk when it is smaller)
+        pg = np.empty(n_pg, dtype=np.float32)
         pg[:] = 0.5
-        lpv = dab.B200Array(rt, lp.ptr, (1 << 28,), np.float32, own=False)
+        lpv = dab.B200Array(rt, lp.ptr, (n_pg,), np.float32, own=False)
         ms_p, _ = timed(lambda: lpv.copy_from_host(pg, sync=False), 2, warm=1)
         ms_p = max_over_ranks(ms_p)
         del pg
@@ -425,7 +426,7 @@ def main():
         e2e = {"value": 12.0 * N * e2e_steps / (ms_e * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 4 * N,
                "d2h_bytes_per_step": 16 * world, "ms_per_step": ms_e / e2e_steps,
                "path": "copyto!(x::DArray, host Array) [pinned H2D] -> y .= a.*x .+ b -> sum(y) -> host scalar",
-               "h2d_pinned_GBs_per_gpu": h2d, "h2d_pageable_pipelined_GBs_per_gpu": 4.0 * (1 << 28) * 2 / (ms_p * 1e-3) / 1e9,
+               "h2d_pinned_GBs_per_gpu": h2d, "h2d_pageable_pipelined_GBs_per_gpu": 4.0 * n_pg * 2 / (ms_p * 1e-3) / 1e9,
                "bound": f"PCIe-bound: 4 of the 12 credited bytes/element cross the host link, so e2e <= 3 x H2D = {3 * h2d * world:.0f} GB/s at "
                         f"{world} GPU(s); the device part of the step is {ms / args.steps:.2f} ms of the {ms_e / e2e_steps:.1f} ms. A CPU worker pool "
                         "streams the same step from host DRAM (no link to cross), which is why one GPU cannot win this leg however fast its kernels are"}

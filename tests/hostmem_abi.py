@@ -143,6 +143,35 @@ class HostMemABI:
         out._obj.value = self.launches
         return 0
 
+    # -- events (wall clock), device info, pinned host memory: what bench.py needs to run its host logic against the emulation
+    def dab_event_create(self, ctx, out):
+        self._events = getattr(self, "_events", {})
+        h = 0xE000 + 8 * len(self._events)
+        self._events[h] = 0.0
+        out._obj.value = h
+        return 0
+
+    def dab_event_record(self, ctx, ev):
+        import time
+        self._events[_addr(ev)] = time.perf_counter()
+        return 0
+
+    def dab_event_elapsed_ms(self, ctx, e0, e1, out):
+        out._obj.value = max(1e-6, (self._events[_addr(e1)] - self._events[_addr(e0)]) * 1e3)
+        return 0
+
+    def dab_event_destroy(self, ctx, ev):
+        self._events.pop(_addr(ev), None)
+        return 0
+
+    def dab_device_info(self, ctx, sm, cc, free_b, total_b):
+        sm._obj.value, cc._obj.value, free_b._obj.value, total_b._obj.value = 148, 100, 1 << 30, 1 << 30
+        return 0
+
+    def dab_stream(self, ctx, out):
+        out._obj.value = 0
+        return 0
+
     # -- buffers
     def _alloc(self, ctx, nbytes, out):
         buf = C.create_string_buffer(max(int(nbytes), 1) + 256)
@@ -155,8 +184,8 @@ class HostMemABI:
         self.blocks.pop(_addr(p), None)
         return 0
 
-    dab_alloc = dab_alloc_async = _alloc
-    dab_free = dab_free_async = _free
+    dab_alloc = dab_alloc_async = dab_host_alloc = _alloc
+    dab_free = dab_free_async = dab_host_free = _free
 
     def _copy(self, ctx, dst, src, n):
         n = int(n)
@@ -463,6 +492,8 @@ class HostMemABI:
 
     def dab_mapreduce_all(self, ctx, dtype, op, mapc, param, x, n, out_host):
         return self._reduce(dtype, op, mapc, param, x, n, out_host)
+
+    dab_reduce_host = dab_mapreduce_all
 
     def dab_rand_u01(self, ctx, dtype, x, n, seed, offset):
         from oracle import darray_oracle as orc

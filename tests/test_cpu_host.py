@@ -387,3 +387,29 @@ def test_gpu_test_modules_against_the_host_memory_abi():
     import re
     m = re.search(r"(\d+) passed", r.stdout)
     assert m and int(m.group(1)) >= 200, tail
+
+
+def test_bench_host_logic_against_the_host_memory_abi():
+    """bench.py end to end (N = 1, 2^16 elements, no extras, no CPU leg) with the C ABI emulated over host memory: the JSON line is complete
+    and the in-run parity block -- exact sums, ordered fold, maximum, bit-exact windows -- comes out true.  Checks the HOST side of the
+    driver-run artifact after changes to shared host code; the numbers themselves mean nothing here."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_on_hostmem.py"), "bench.py", "--log2n", "16", "--steps", "2", "--warmup", "3",
+                        "--no-cpu", "--no-extras"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config",
+                "roofline", "e2e", "gpu_launches", "clocks", "parity"):
+        assert key in line, key
+    assert line["parity"]["ok"] is True, line["parity"]
+    assert line["n_gpus"] == 1 and line["steps"] == 2 and line["e2e"]["h2d_bytes_per_step"] == 4 * (1 << 16) and line["gpu_launches"] > 0
+
+
+def test_smoke_host_logic_against_the_host_memory_abi():
+    """``__graft_entry__.smoke()`` (what the driver runs on the B200 before the bench) with the C ABI emulated over host memory: its host side
+    -- layouts vs the oracle, map!, broadcast, sum / maximum, sum(dims=1), the halo read, A*B, the strided view, sort -- runs through."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_on_hostmem.py"), "__graft_entry__.py", "smoke"], cwd=ROOT,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "smoke ok" in r.stdout, (r.stdout + r.stderr)[-2000:]

@@ -224,3 +224,31 @@ def test_sort_by_key_element_code_host_replay(tmp_path):
                            "-o", exe, os.path.join(root, "tools", "sortby_host_check.cu")])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "sortby_host_check: ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_host_sort_flow_by_with_nan_values_and_nan_keys(hostmem, dab):
+    """NaN values, NaN keys (sqrt of negatives) and signed zeros through the keyed samplesort: NaN keys tie and keep input order behind
+    everything else, a NaN key never exceeds a boundary -- product flow (emulated kernels) and oracle agree bit for bit."""
+    rng = np.random.default_rng(4)
+    for nw in (1, 3, 8):
+        dab.init(workers_per_rank=nw, use_dist=False)
+        for T in (np.float64, np.float32):
+            for n in (nw, 50, 2000):
+                a = rng.standard_normal(n).astype(T)
+                a[rng.integers(0, n, max(1, n // 10))] = np.nan
+                a[rng.integers(0, n, max(1, n // 10))] = -0.0
+                od, d = orc.distribute(a, nworkers=nw), dab.distribute(a)
+                for tby, nby in [(lambda x: x * 1, lambda v: v * 1), (lambda x: abs(x), np.abs), (lambda x: dab.sqrt(x), lambda v: np.sqrt(v)),
+                                 (lambda x: dab.ifelse(x > 0, x, 0 * x), lambda v: np.where(v > 0, v, 0 * v))]:
+                    for sample in (True, a[rng.integers(0, n, min(n, 32))]):
+                        try:
+                            with np.errstate(all="ignore"):
+                                want, wb = orc.darray_sort(od, sample, by=nby)
+                        except ValueError:
+                            with pytest.raises(dab.ArgumentError):
+                                dab.sort_with_boundaries(d, sample, tby)
+                            continue
+                        got, gb = dab.sort_with_boundaries(d, sample, tby)
+                        assert np.array_equal(gb, wb, equal_nan=True) and got.layout.indices == want.indices
+                        assert np.array_equal(dab.to_array(got).view(np.uint8), orc.to_array(want).view(np.uint8)), (nw, T, n)
+                d.close()

@@ -413,3 +413,31 @@ def test_smoke_host_logic_against_the_host_memory_abi():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_on_hostmem.py"), "__graft_entry__.py", "smoke"], cwd=ROOT,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "smoke ok" in r.stdout, (r.stdout + r.stderr)[-2000:]
+
+
+def test_nd_broadcast_random_shapes_on_the_host_memory_abi(hostmem, dab):
+    """General broadcasts over 5..7 dimensions with random extents and random extrusion patterns, through the REAL run_local (collapse_dims,
+    stride tables) and the emulated strided box walk, against NumPy's broadcasting; patterns that do not collapse to 4 groups must raise."""
+    rng = np.random.default_rng(55)
+    dab.init(workers_per_rank=4, use_dist=False)
+    served = refused = 0
+    for trial in range(60):
+        nd = int(rng.integers(5, 8))
+        shape = tuple(int(v) for v in rng.integers(1, 5, nd))
+        if int(np.prod(shape)) < 4:
+            continue
+        A = rng.integers(-9, 9, shape).astype(np.int64)
+        ext = rng.random(nd) < 0.35
+        mshape = tuple(1 if e else s for e, s in zip(ext, shape))
+        M = rng.integers(-9, 9, mshape).astype(np.int64)
+        a = dab.distribute(A)
+        try:
+            r = dab.broadcast(lambda x, m: x * m - m, a, M)
+        except dab.UnsupportedError:
+            refused += 1
+            continue                                            # per-chunk shapes decide; a refusal is an exception, never silent
+        assert np.array_equal(dab.to_array(r), A * M - M), (shape, mshape)
+        served += 1
+        r.close()
+        a.close()
+    assert served >= 30, (served, refused)

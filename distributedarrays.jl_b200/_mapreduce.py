@@ -314,19 +314,60 @@ def _pred_reduce(opc: int, d: DArray, f: Optional[Callable]):
     return _mapreduce_all(f, opc, d)
 
 
-def all(d: DArray, f: Optional[Callable] = None) -> bool:  # noqa: A001
-    """``Base._all(f, A::DArray, ::Colon)`` (reference src/mapreduce.jl:97-104)."""
-    return bool(_pred_reduce(_lib.ALL, d, f))
+def _count_dims(d: DArray, f: Optional[Callable], dims) -> Tuple[DArray, int]:
+    """``count(f, d; dims)`` as a DArray of Int64 plus the number of elements behind each entry.  Base sends the dimensional forms of
+    all / any / count through ``mapreduce(f, op, A; dims)``, i.e. through the reference's ``mapreducedim!`` (src/mapreduce.jl:83-94); here
+    the predicate is mapped to 0 / 1 in one elementwise launch and summed by the dimensional reduction kernels."""
+    from ._broadcast import ifelse
+    from ._darray import SubDArray
+    if isinstance(d, SubDArray):
+        tmp = d.to_darray()
+        try:
+            return _count_dims(tmp, f, dims)
+        finally:
+            tmp.close()
+    if f is None and d.dtype != np.dtype(np.bool_):
+        raise TypeError("TypeError: non-boolean used in boolean context")
+    pred = (lambda x: x) if f is None else f
+    e = trace(pred, [tag_of(d.dtype)])
+    if e.jt != "bool":
+        raise TypeError("TypeError: non-boolean used in boolean context")
+    ones = broadcast(lambda x: ifelse(pred(x), 1, 0), d)
+    try:
+        r = mapreducedim(None, "+", ones, dims)
+    finally:
+        ones.close()
+    region = _normalise_region(dims, d.ndim)
+    return r, int(np.prod([d.dims[k - 1] for k in region if k <= d.ndim], dtype=np.int64))
 
 
-def any(d: DArray, f: Optional[Callable] = None) -> bool:  # noqa: A001
-    """reference src/mapreduce.jl:106-113."""
-    return bool(_pred_reduce(_lib.ANY, d, f))
+def all(d: DArray, f: Optional[Callable] = None, dims=None):  # noqa: A001
+    """``Base._all(f, A::DArray, ::Colon)`` (reference src/mapreduce.jl:97-104); with ``dims`` a Bool DArray (``all(f, d; dims)``)."""
+    if dims is None:
+        return bool(_pred_reduce(_lib.ALL, d, f))
+    r, extent = _count_dims(d, f, dims)
+    try:
+        return broadcast(lambda c: c == extent, r)
+    finally:
+        r.close()
 
 
-def count(d: DArray, f: Optional[Callable] = None) -> int:
-    """reference src/mapreduce.jl:115-122."""
-    return int(_pred_reduce(_lib.COUNT, d, f))
+def any(d: DArray, f: Optional[Callable] = None, dims=None):  # noqa: A001
+    """reference src/mapreduce.jl:106-113; with ``dims`` a Bool DArray."""
+    if dims is None:
+        return bool(_pred_reduce(_lib.ANY, d, f))
+    r, _ = _count_dims(d, f, dims)
+    try:
+        return broadcast(lambda c: c > 0, r)
+    finally:
+        r.close()
+
+
+def count(d: DArray, f: Optional[Callable] = None, dims=None):
+    """reference src/mapreduce.jl:115-122; with ``dims`` an Int64 DArray."""
+    if dims is None:
+        return int(_pred_reduce(_lib.COUNT, d, f))
+    return _count_dims(d, f, dims)[0]
 
 
 def extrema(d: DArray):
@@ -455,8 +496,10 @@ def mapreducedim(f: Optional[Callable], op, d: DArray, dims, init=None) -> DArra
     region = _normalise_region(dims, N)
     reg_in = tuple(r for r in region if r <= N)
     mapc, param, expr = classify_map(f, d.dtype)
-    if param is not None:
-        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "predicate maps with dims are not served")
+    if param is not None or (expr is not None and expr.jt == "bool"):
+        if opc == _lib.SUM and init is None:
+            return _count_dims(d, f, dims)[0]                    # sum(pred, d; dims): Bools add up as Int (Base.add_sum)
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "Bool-valued maps with dims are served for + only (count / any / all build on it)")
     src, tmp = d, None
     if mapc is None:
         from ._broadcast import LocalArg, run_local

@@ -8,6 +8,7 @@
     a conditional prelude block, and the functions Julia defines by composition;
   * ``<<`` / ``>>`` on integer DArrays (test/darray.jl:863-867);
   * ``copy`` / ``deepcopy`` of a DArray and ``drandn`` (host-side compositions of the broadcast kernels);
+  * ``all`` / ``any`` / ``count`` with ``dims`` (host-side compositions: predicate -> 0 / 1, dimensional sum, compare);
   * ``norm(x, p)`` for p = 0, -Inf and general p (host-side compositions of the fused map + reduce);
   * general broadcasts over more than 4 dimensions (``collapse_dims`` in ``_broadcast.py``; reference src/broadcast.jl is N-d).
 
@@ -147,6 +148,28 @@ def test_multi_argument_mapreduce_with_dims(dab, rt8):
         assert np.array_equal(dab.to_array(r), (A * B + 1).sum(axis=axis, keepdims=True))
     r = dab.mapreduce(lambda x, y: x - y, "max", a, 3, dims=2)                  # a scalar argument
     assert np.array_equal(dab.to_array(r), (A - 3).max(axis=1, keepdims=True))
+
+
+def test_predicates_with_dims(dab, rt8):
+    """``count(f, d; dims)`` -> Int64 DArray, ``any`` / ``all(f, d; dims)`` -> Bool DArray (Base routes them through mapreduce(...; dims), i.e.
+    the reference's mapreducedim!, src/mapreduce.jl:83-94), for every kind of region; Bool arrays without a predicate; the whole-array forms
+    are unchanged."""
+    rng = np.random.default_rng(1)
+    A = rng.integers(-5, 5, (30, 22, 6)).astype(np.int64)
+    a = dab.distribute(A)
+    for dims, axis in ((1, 0), (2, 1), ((1, 3), (0, 2)), ((1, 2, 3), (0, 1, 2))):
+        c = dab.count(a, lambda x: x > 2, dims=dims)
+        assert c.dtype == np.int64 and np.array_equal(dab.to_array(c), (A > 2).sum(axis=axis, keepdims=True)), dims
+        assert np.array_equal(dab.to_array(dab.any(a, lambda x: x > 3, dims=dims)), (A > 3).any(axis=axis, keepdims=True))
+        r = dab.to_array(dab.all(a, lambda x: x > -5, dims=dims))
+        assert r.dtype == np.bool_ and np.array_equal(r, (A > -5).all(axis=axis, keepdims=True))
+    B = A > 0
+    b = dab.distribute(B)
+    assert np.array_equal(dab.to_array(dab.count(b, dims=2)), B.sum(axis=1, keepdims=True))
+    assert np.array_equal(dab.to_array(dab.all(b, dims=(1, 2))), B.all(axis=(0, 1), keepdims=True))
+    with pytest.raises(TypeError):
+        dab.count(a, dims=1)                                                    # non-boolean used in boolean context
+    assert dab.count(a, lambda x: x > 2) == int((A > 2).sum()) and dab.all(b) == bool(B.all())
 
 
 def test_reference_scalar_math_vocabulary(dab, rt8):

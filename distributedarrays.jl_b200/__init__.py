@@ -20,7 +20,7 @@ from ._darray import (B200Array, DArray, SubDArray, allowscalar, dab_dtype, np_d
                      dfill, distribute, dones, drand, dzeros, fill_, localindices, localpart, locate, makelocal, pinned_empty, procs,
                      registry_size, similar, to_array)
 from .layout import Layout, chunk_idxs, cuts_for, defaultdist, make_layout, slab_plan
-from ._mapreduce import (all, any, axpy_, count, dot, extrema, isequal, mapreduce, mapreducedim, maximum, mean, minimum, norm,  # noqa: A004
+from ._mapreduce import (all, any, axpy_, count, dot, extrema, isequal, mapreduce, mapreducedim, maximum, mean, minimum, nnz, norm,  # noqa: A004
                          prod, reduce, rmul_, sum)
 from ._linalg import Adjoint, Transpose, adjoint, copy_transposed, lmul_diag, matmat, matmul, mul_, mul_mat_, rmul_diag, transpose
 from ._sort import sort, sort_with_boundaries

@@ -370,6 +370,12 @@ def count(d: DArray, f: Optional[Callable] = None, dims=None):
     return _count_dims(d, f, dims)[0]
 
 
+def nnz(d: DArray) -> int:
+    """``nnz(A::DArray)`` (reference ext/SparseArraysExt.jl:7-12: the per-worker ``nnz(localpart)`` summed).  Chunks are dense here, so the
+    stored-entry count of the reference's sparse chunks becomes the number of nonzero elements -- one predicate count per localpart."""
+    return count(d, lambda x: x != 0)
+
+
 def extrema(d: DArray):
     """``extrema(d)`` (reference src/mapreduce.jl:124-131): per-chunk (min, max) in ONE pass over the chunk, then the fold
     ``(t, s) -> (min(t[1], s[1]), max(t[2], s[2]))`` over the workers in procs order."""

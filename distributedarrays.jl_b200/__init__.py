@@ -18,7 +18,7 @@ from ._broadcast import (acos, acosh, acot, acoth, acsc, acsch, asec, asech, asi
                         loggamma, rad2deg, round_, sec, sech, sinh, sinpi, trunc)
 from ._darray import (B200Array, DArray, SubDArray, allowscalar, dab_dtype, np_dtype, copyto, d_closeall, darray, darray_from_chunks, darray_like,
                      dfill, distribute, dones, drand, dzeros, fill_, localindices, localpart, locate, makelocal, pinned_empty, procs,
-                     registry_size, similar, to_array)
+                     registry_size, reshape, similar, to_array)
 from .layout import Layout, chunk_idxs, cuts_for, defaultdist, make_layout, slab_plan
 from ._mapreduce import (all, any, axpy_, count, dot, extrema, isequal, mapreduce, mapreducedim, maximum, mean, minimum, nnz, norm,  # noqa: A004
                          prod, reduce, rmul_, sum)

@@ -769,6 +769,42 @@ def similar(d: DArray, dtype=None, dims=None) -> DArray:
     return darray(lambda I: B200Array.empty(d.rt, shape_of(I), dt), d.dims if dims is None else dims, procs(d), dtype=dt, rt=d.rt)
 
 
+def reshape(A: DArray, dims) -> DArray:
+    """``reshape(A::DVector, d::Dims)`` (reference src/darray.jl:612-636): a NEW DArray of size ``d`` with the default layout whose chunk
+    ``I`` holds, column by column, the runs ``A[a:a+nr-1]`` of the vector (``a`` = the linear index of the column's first element).  Here
+    the whole chunk is ONE vector-indexed view of ``A`` -- the linear indices of the chunk's elements in column-major order -- read by the
+    gather kernel straight into the new localpart (the owners of the runs may be several workers).  Like the reference: only for a
+    one-dimensional DArray, ``DimensionMismatch`` unless ``prod(d) == length(A)``."""
+    dims = tuple(int(v) for v in (dims if isinstance(dims, (tuple, list)) else (dims,)))
+    if A.ndim != 1:
+        raise _lib.UnsupportedError(_lib.ERR_UNSUPPORTED, "reshape is defined for a one-dimensional DArray (reference src/darray.jl:612)")
+    if int(np.prod(dims, dtype=np.int64)) != A.size:
+        raise _lib.DimensionMismatch(_lib.ERR_DIM_MISMATCH, "dimensions must be consistent with array size")
+    rt = A.rt
+    remote = rt.world > 1
+    if remote:
+        if A._handles is None:
+            A.share()
+        rt.device_barrier()
+    strides = np.cumprod((1,) + dims[:-1]).astype(np.int64)
+
+    def init(I):
+        ch = B200Array.empty(rt, shape_of(I), A.dtype)
+        if ch.size:
+            lin = np.zeros((), dtype=np.int64)
+            for k in range(len(dims) - 1, -1, -1):               # column-major order of the chunk: the first dimension varies fastest
+                lo, hi = I[k]
+                lin = lin[..., None] + np.arange(lo - 1, hi, dtype=np.int64) * strides[k]
+            view = A[lin.reshape(-1)]
+            view.copy_to(B200Array(rt, ch.ptr, view.full_shape, A.dtype, own=False))
+        return ch
+
+    out = darray(init, dims, dtype=A.dtype, rt=rt)
+    if remote:
+        rt.device_barrier()
+    return out
+
+
 def fill_(d: DArray, x) -> DArray:
     """``fill!(A::DArray, x)`` (src/darray.jl:822-827)."""
     v = np.asarray(x, dtype=d.dtype)

@@ -352,6 +352,7 @@ def test_last_session_gpu_tests_dry_run_on_the_host_memory_abi(hostmem, dab):
     z.test_copy_deepcopy_drandn(dab, rt)
     z.test_multi_argument_mapreduce_with_dims(dab, rt)
     z.test_predicates_with_dims(dab, rt)
+    z.test_reshape_dvector(dab, rt)
     z.test_reference_shift_ops(dab, rt)
     z.test_reference_scalar_math_vocabulary(dab, rt)
     for T in (np.int64, np.float32):

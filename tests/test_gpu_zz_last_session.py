@@ -7,6 +7,7 @@
   * the rest of the reference's "scalar math" vocabulary that has a device kernel (test/darray.jl:775-797): libdevice-backed functions in
     a conditional prelude block, and the functions Julia defines by composition;
   * ``<<`` / ``>>`` on integer DArrays (test/darray.jl:863-867);
+  * ``reshape(A::DVector, dims)`` (one vector-indexed view per new localpart, the gather kernel of round 2);
   * ``copy`` / ``deepcopy`` of a DArray and ``drandn`` (host-side compositions of the broadcast kernels);
   * ``all`` / ``any`` / ``count`` with ``dims`` (host-side compositions: predicate -> 0 / 1, dimensional sum, compare);
   * ``norm(x, p)`` for p = 0, -Inf and general p (host-side compositions of the fused map + reduce);
@@ -148,6 +149,26 @@ def test_multi_argument_mapreduce_with_dims(dab, rt8):
         assert np.array_equal(dab.to_array(r), (A * B + 1).sum(axis=axis, keepdims=True))
     r = dab.mapreduce(lambda x, y: x - y, "max", a, 3, dims=2)                  # a scalar argument
     assert np.array_equal(dab.to_array(r), (A - 3).max(axis=1, keepdims=True))
+
+
+def test_reshape_dvector(dab, rt8):
+    """``reshape(A::DVector, d::Dims)`` (src/darray.jl:612-636; test/darray.jl:150-165): column-major relabelling into a new DArray with the
+    default layout; ``DimensionMismatch`` unless the sizes agree; ``nnz``."""
+    rng = np.random.default_rng(612)
+    for n, dims in ((40000, (100, 400)), (40000, (200, 200)), (360, (3, 4, 5, 6)), (17 * 9, (17, 9)), (64, (64,)), (64, (1, 64))):
+        a = rng.standard_normal(n)
+        d = dab.distribute(a)
+        r = dab.reshape(d, dims)
+        assert r.dims == dims and np.array_equal(dab.to_array(r), a.reshape(dims, order="F")), dims
+        assert list(r.layout.indices) == list(dab.similar(r).layout.indices)
+    with pytest.raises(dab.DimensionMismatch):
+        dab.reshape(d, (100, 100))
+    with pytest.raises(dab.UnsupportedError):
+        dab.reshape(r, (64,))                                                   # only a one-dimensional DArray, as in the reference
+    ii = rng.integers(-3, 3, 600).astype(np.int32)
+    di = dab.distribute(ii)
+    assert np.array_equal(dab.to_array(dab.reshape(di, (20, 30))), ii.reshape((20, 30), order="F"))
+    assert dab.nnz(di) == int(np.count_nonzero(ii))
 
 
 def test_predicates_with_dims(dab, rt8):
